@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the GP-transport posterior path (BASELINE.json metric: query-points/sec for mean + std + Jacobian at N
+training pairs; fit ms at N).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c4|c2] [--impl b200|reference]
+
+A "step" is one pass of the hot path over one batch of M synthetic query points per GPU (mode A: posterior mean,
+predictive std and analytic Jacobian).  Workloads (BASELINE.json configs):
+  c3 (default)  N = 4096 pairs, M = 2^20 queries per step per GPU          -- "synthetic 3D GPT N=4096, M=1M, 1 B200"
+  c4            N = 16384 pairs, M = 2^17 queries per step per GPU         -- a batch of config 4's 64M-query stream
+  c2            N = 834 (shipped cloud size), M = 2^20                      -- small-N regime
+Multi-GPU: fit on rank 0, one NCCL broadcast of the model state, queries block-partitioned (weak scaling: M per GPU
+fixed), no data-path collective.
+`value`  : inputs/outputs resident in HBM (gptb_query_dev).
+`e2e`    : the same step through the host-pointer C-ABI call (gptb_query) with pinned host buffers; H2D and D2H inside
+           the timed region.
+`roofline`: the dominant kernel (variance triangular multiply on FP64 DMMA) against the measured cuBLAS FP64 GEMM rate.
+`cpu_baseline`: the CPU oracle port (sklearn GaussianProcessRegressor + the reference wrapper restated) on a bounded
+           sample of the same workload on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c3": dict(N=4096, M=1 << 20, name="c3: synthetic 3D GPT N=4096 pairs, M=2^20 queries/step/GPU, mean+std+Jacobian"),
+    "c4": dict(N=16384, M=1 << 17, name="c4: synthetic 3D GPT N=16384 pairs, M=2^17-query batch/step/GPU of the 64M stream, mean+std+Jacobian"),
+    "c2": dict(N=834, M=1 << 20, name="c2-size: N=834 pairs, M=2^20 queries/step/GPU, mean+std+Jacobian"),
+}
+KERNEL = dict(c=0.1, ell=[0.1, 0.1, 0.1], s2=1e-4, jitter=1e-10)
+METRIC = "GP transport query-points/sec (mean+std+Jacobian) @N train"
+
+
+def make_inputs(N, M, rank=0):
+    from oracle.gp_oracle import synthetic_pairs  # input generator only (shared with the tests); no oracle compute here
+    S, T = synthetic_pairs(N, 3, seed=0)
+    rng = np.random.default_rng(1000 + rank)
+    xq = -0.1 + 1.2 * rng.random((M, 3))
+    return S, T, xq
+
+
+def affine_and_delta(S, T):
+    from gaussian_process_transportation_b200 import AffineTransform
+    import contextlib, io
+    a = AffineTransform()
+    with contextlib.redirect_stdout(io.StringIO()):
+        a.fit(S, T)
+    Sr = a.predict(S)
+    return a, Sr, T - Sr
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+                for n, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measure_dgemm_peak(torch, dev, n=6144):
+    """cuBLAS FP64 GEMM rate on this GPU right now (the FP64 analogue of MEASURED_PEAKS.json's bf16 figure, which the
+    driver file does not carry): best of 5, CUDA events."""
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    c = torch.empty_like(a)
+    torch.matmul(a, b, out=c)
+    torch.cuda.synchronize(dev)
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize(dev)
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    return 2.0 * n ** 3 / best * 1e-9
+
+
+def cpu_baseline_sample(N, n_queries, threads_note=True):
+    """The CPU path (oracle port over the real sklearn regressor) on a bounded sample: fit(optimizer=None) at N, then mode A
+    = predict(return_std) + derivative() on `n_queries` points, chunked like BASELINE.md section 3."""
+    import contextlib, io, warnings
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+    from oracle.gp_oracle import SkGaussianProcess
+    warnings.filterwarnings("ignore")
+    S, T, xq = make_inputs(N, n_queries)
+    _, Sr, D = affine_and_delta(S, T)
+    kern = C(KERNEL["c"]) * RBF(KERNEL["ell"]) + WhiteKernel(KERNEL["s2"])
+    gp = SkGaussianProcess(kern, optimizer=None)
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        gp.fit(Sr, D)
+    fit_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    outs = []
+    for i in range(0, n_queries, 2048):
+        xb = xq[i:i + 2048]
+        m, s = gp.predict(xb, return_std=True)
+        J = gp.derivative(xb)
+        outs.append((m, s, J))
+    q_s = time.perf_counter() - t0
+    try:
+        from threadpoolctl import threadpool_info
+        blas_threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        blas_threads = os.cpu_count()
+    return dict(qps=n_queries / q_s, fit_ms=fit_s * 1e3, cores=int(blas_threads), host_cpus=os.cpu_count(), xq=xq, outs=outs)
+
+
+def run_reference(args):
+    """Reference arm: the CPU path (oracle port over the real sklearn regressor, all BLAS threads) on this box's host
+    cores, same metric/config; each step is a bounded sample of the workload's queries."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import contextlib, io, warnings
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+    from oracle.gp_oracle import SkGaussianProcess
+    warnings.filterwarnings("ignore")
+    wl = WORKLOADS[args.workload]
+    N = wl["N"]
+    nq = {4096: 4096, 16384: 1024}.get(N, 8192)
+    S, T, xq = make_inputs(N, nq)
+    _, Sr, D = affine_and_delta(S, T)
+    gp = SkGaussianProcess(C(KERNEL["c"]) * RBF(KERNEL["ell"]) + WhiteKernel(KERNEL["s2"]), optimizer=None)
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        gp.fit(Sr, D)
+    fit_ms = (time.perf_counter() - t0) * 1e3
+    step_t = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        for i in range(0, nq, 2048):
+            gp.predict(xq[i:i + 2048], return_std=True)
+            gp.derivative(xq[i:i + 2048])
+        if it >= args.warmup:
+            step_t.append(time.perf_counter() - t0)
+    tot = sum(step_t)
+    value = nq * len(step_t) / tot
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count()
+    import sklearn
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "query-points/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(step_t), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "N": N, "queries_per_step": nq, "mode": "A (mean+std+Jacobian)",
+                       "kernel": "C(0.1)*RBF([0.1]*3)+White(1e-4)"},
+            "cpu_baseline": {"value": value, "unit": "query-points/s", "cores": int(cores), "kind": "port",
+                             "sample": f"oracle port (sklearn {sklearn.__version__} GaussianProcessRegressor + restated reference "
+                                       f"wrapper): predict(return_std)+derivative() on {nq} of the workload's queries per step, "
+                                       f"chunks of 2048; host has {os.cpu_count()} cpus"},
+            "fit_ms": fit_ms,
+            "e2e": {"value": value, "unit": "query-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--queries", type=int, default=0, help="override queries per step per GPU")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    from gaussian_process_transportation_b200 import _lib as L
+    from gaussian_process_transportation_b200.distributed import broadcast_model
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS[args.workload]
+    N, M = wl["N"], (args.queries or wl["M"])
+    d = p = 3
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    eng = L.Engine(local_rank)
+    S, T, xq = make_inputs(N, M, rank)
+    fit_ms = prep_ms = bcast_ms = None
+    if rank == 0:
+        aff, Sr, D = affine_and_delta(S, T)
+        eng.set_train(Sr, D)
+        eng.factorize(KERNEL["c"], KERNEL["ell"], KERNEL["s2"], KERNEL["jitter"])          # warm-up (allocation, module load)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        info, lml = eng.factorize(KERNEL["c"], KERNEL["ell"], KERNEL["s2"], KERNEL["jitter"], want_lml=False)
+        fit_ms = (time.perf_counter() - t0) * 1e3
+        assert info == 0
+        t0 = time.perf_counter()
+        eng.prepare_variance()
+        prep_ms = (time.perf_counter() - t0) * 1e3
+        aff_pack = np.concatenate([aff.rotation_matrix.ravel(), [float(aff.scale)], aff.S_centroid, aff.T_centroid])
+    else:
+        aff_pack = np.zeros(d * d + 1 + 2 * d)
+    if world > 1:
+        t0 = time.perf_counter()
+        broadcast_model(eng, src=0)
+        ap_t = torch.from_numpy(aff_pack).to(dev)
+        dist.broadcast(ap_t, src=0)
+        aff_pack = ap_t.cpu().numpy()
+        torch.cuda.synchronize(dev)
+        bcast_ms = (time.perf_counter() - t0) * 1e3
+    eng.set_affine(aff_pack[:9].reshape(3, 3), aff_pack[9], aff_pack[10:13], aff_pack[13:16])
+
+    flags = L.MEAN | L.STD | L.JAC | L.AFFINE_IN
+    stream = torch.cuda.ExternalStream(eng.stream(), device=dev)
+    x_dev = torch.from_numpy(xq).to(dev)
+    mean_d = torch.empty(M, p, dtype=torch.float64, device=dev)
+    std_d = torch.empty(M, p, dtype=torch.float64, device=dev)
+    jac_d = torch.empty(M, p, d, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize(dev)
+
+    def step_dev():
+        eng.query_dev(x_dev.data_ptr(), M, flags, 0, mean_d.data_ptr(), std_d.data_ptr(), jac_d.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident throughput ---------------------------------------------------------------------------
+    for _ in range(W):
+        step_dev()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = eng.launch_count()
+    eng.timing(True); eng.timing_reset()
+    ms_total = timed(step_dev, K)
+    trmm_ms, trmm_n = eng.kernel_time(0)
+    gen_ms, gen_n = eng.kernel_time(1)
+    eng.timing(False); eng.timing_reset()
+    launches = eng.launch_count() - launches0
+    value = world * M * K / (ms_total * 1e-3)
+
+    # ---- end to end through the host-pointer C ABI with pinned buffers ------------------------------------------
+    xh = torch.from_numpy(xq).pin_memory()
+    mean_h = torch.empty(M, p, dtype=torch.float64).pin_memory()
+    std_h = torch.empty(M, p, dtype=torch.float64).pin_memory()
+    jac_h = torch.empty(M, p, d, dtype=torch.float64).pin_memory()
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    cast = lambda t: C.cast(t.data_ptr(), dp)
+
+    def step_e2e():
+        rc = eng.lib.gptb_query(eng.h, cast(xh), M, flags, None, cast(mean_h), cast(std_h), cast(jac_h), None, None, None, None, None, None)
+        assert rc == 0, eng.error()
+
+    step_e2e()
+    Ke = max(1, min(K, 3))
+    e2e_ms = timed(step_e2e, Ke)
+    e2e_value = world * M * Ke / (e2e_ms * 1e-3)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    h2d = M * d * 8
+    d2h = M * (p + p + p * d) * 8
+
+    if rank == 0:
+        peak = measure_dgemm_peak(torch, dev)
+        Npad = (N + 127) // 128 * 128
+        # algorithmic flops of the triangular multiply per launch: sum over row tiles of 2*128*128*128*(ti+1)
+        launches_per_step = max(1, trmm_n // max(K, 1))
+        q_per_launch = M / launches_per_step
+        flops_per_launch = q_per_launch * Npad * (Npad + 128.0)
+        avg_launch_ms = trmm_ms / max(trmm_n, 1)
+        achieved = flops_per_launch / (avg_launch_ms * 1e-3) * 1e-12
+        roofline = {"bound": "tensor", "kernel": "trmm_sumsq_kernel (FP64 DMMA mma.sync.m8n8k4)", "achieved": achieved, "peak": peak,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": "cuBLAS FP64 GEMM 6144^3 measured live in this run (MEASURED_PEAKS.json has no FP64 entry); "
+                                   "DMMA/DFMA pipe peak 37.0 TFLOP/s (profiles/r01_fp64_peaks.json)",
+                    "algorithmic_flops_per_query": Npad * (Npad + 128.0), "share_of_step": trmm_ms / ms_total,
+                    "generator_share_of_step": gen_ms / ms_total}
+        cpu = None
+        if not args.no_cpu_baseline:
+            nq = {4096: 4096, 16384: 1024}.get(N, 8192)
+            cb = cpu_baseline_sample(N, nq)
+            # parity spot-check of the timed configuration on the CPU sample (same hyper-parameters, same queries)
+            xs = cb["xq"]
+            eng.set_affine(None)
+            o = eng.query(xs[:2048], L.MEAN | L.STD | L.JAC)
+            m, s, J = cb["outs"][0]
+            rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+            parity = {"mean_rel": rel(o["mean"], m), "jac_rel": rel(o["jac"], J),
+                      "std_abs_over_sqrt_prior": float(np.max(np.abs(o["std"] - s)) / np.sqrt(KERNEL["c"] + KERNEL["s2"]))}
+            cpu = {"value": cb["qps"], "unit": "query-points/s", "cores": cb["cores"], "kind": "port",
+                   "sample": f"oracle port (sklearn GaussianProcessRegressor + restated reference wrapper) on {nq} of the workload's "
+                             f"queries, predict(return_std)+derivative(), chunks of 2048; host has {cb['host_cpus']} cpus",
+                   "fit_ms": cb["fit_ms"], "parity_vs_gpu": parity}
+        line = {"metric": METRIC, "value": value, "unit": "query-points/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": wl["name"], "N": N, "queries_per_step_per_gpu": M, "mode": "A (mean+std+Jacobian)",
+                           "kernel": "C(0.1)*RBF([0.1]*3)+White(1e-4)", "parallelism": f"query-sharded x{world}",
+                           "l2_policy": "inputs larger than L2: each step streams a >=2 GiB k* workspace"},
+                "fit_ms": fit_ms, "prepare_variance_ms": prep_ms, "bcast_ms": bcast_ms,
+                "e2e": {"value": e2e_value, "unit": "query-points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_ms / Ke, "steps": Ke},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "clocks": sampler.summary() if sampler else None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,240 @@
+"""ctypes binding of libgptb200.so (include/gptb200.h).  There is no fallback: a missing library or a missing CUDA
+device raises immediately."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgptb200.so")
+
+MEAN, STD, JAC, JACVAR, AFFINE_IN, TRANSPORT, VELOCITY, JPHI, DVAR = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40, 0x80, 0x100
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+
+SYMBOLS = {
+    "gptb_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "gptb_destroy": (None, [C.c_void_p]),
+    "gptb_last_error": (C.c_char_p, [C.c_void_p]),
+    "gptb_version": (C.c_int, []),
+    "gptb_set_train": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_int, C.c_int]),
+    "gptb_factorize": (C.c_int, [C.c_void_p, C.c_double, _dp, C.c_double, C.c_double, _dp]),
+    "gptb_lml": (C.c_int, [C.c_void_p, C.c_double, _dp, C.c_double, C.c_double, C.c_int, _dp, _dp]),
+    "gptb_prepare_variance": (C.c_int, [C.c_void_p]),
+    "gptb_set_affine": (C.c_int, [C.c_void_p, _dp, C.c_double, _dp, _dp]),
+    "gptb_query": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_uint32, _dp] + [_dp] * 9),
+    "gptb_query_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p] + [C.c_void_p] * 9),
+    "gptb_export_L": (C.c_int, [C.c_void_p, _dp]),
+    "gptb_export_alpha": (C.c_int, [C.c_void_p, _dp]),
+    "gptb_export_Kinv": (C.c_int, [C.c_void_p, _dp]),
+    "gptb_state_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int]),
+    "gptb_state_buffer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "gptb_state_commit": (C.c_int, [C.c_void_p]),
+    "gptb_launch_count": (C.c_int64, [C.c_void_p]),
+    "gptb_kernel_time": (C.c_int, [C.c_void_p, C.c_int, _dp, C.POINTER(C.c_int64)]),
+    "gptb_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "gptb_timing_reset": (C.c_int, [C.c_void_p]),
+    "gptb_stream": (C.c_void_p, [C.c_void_p]),
+    "gptb_set_workspace_limit": (C.c_int, [C.c_void_p, C.c_int64]),
+    "gptb_test_gemm_nt": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gptb_test_potrf_tile": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.POINTER(C.c_int)]),
+}
+
+
+def load():
+    """Load libgptb200.so and declare every prototype of include/gptb200.h.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()). "
+            "gaussian_process_transportation_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def as_f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+class GptbError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One handle = one device + stream + model state (not thread-safe, cf. include/gptb200.h)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.gptb_create(int(device), C.byref(h))
+        if rc != 0:
+            raise GptbError(
+                f"gptb_create(device={device}) failed with status {rc}"
+                + (": no CUDA device is visible and this package has no CPU fallback" if rc == -4 else ""))
+        self.h = h
+        self.device = int(device)
+        self.N = self.d = self.p = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gptb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc < 0:
+            raise GptbError(f"{what}: {self.lib.gptb_last_error(self.h).decode()} (status {rc})")
+        return rc
+
+    def error(self):
+        return self.lib.gptb_last_error(self.h).decode()
+
+    # -- model -----------------------------------------------------------------------------------------------
+    def set_train(self, X, Y):
+        X = as_f64(X)
+        Y = as_f64(Y)
+        if Y.ndim == 1:
+            Y = Y[:, None]
+        self.N, self.d = X.shape
+        self.p = Y.shape[1]
+        self._check(self.lib.gptb_set_train(self.h, ptr(X), ptr(Y), self.N, self.d, self.p), "gptb_set_train")
+
+    def _ell(self, ell):
+        e = np.atleast_1d(np.asarray(ell, dtype=np.float64)).ravel()
+        if e.size == 1:
+            e = np.repeat(e, self.d)
+        if e.size != self.d:
+            raise ValueError(f"length_scale has {e.size} entries for {self.d} input dimensions")
+        return np.ascontiguousarray(e)
+
+    def factorize(self, c, ell, s2, jitter, want_lml=True):
+        """Returns (info, lml); info > 0 means not positive definite."""
+        e = self._ell(ell)
+        out = C.c_double(float("nan"))
+        rc = self.lib.gptb_factorize(self.h, float(c), ptr(e), float(s2), float(jitter), C.byref(out) if want_lml else None)
+        self._check(rc, "gptb_factorize")
+        return rc, out.value
+
+    def lml(self, c, ell, s2, jitter, want_grad=True):
+        """Returns (info, lml, grad[2+d]) with grad = d/dlog [c, ell_0.., s2]."""
+        e = self._ell(ell)
+        out = C.c_double(float("nan"))
+        g = np.zeros(2 + self.d)
+        rc = self.lib.gptb_lml(self.h, float(c), ptr(e), float(s2), float(jitter), int(bool(want_grad)), C.byref(out), ptr(g))
+        self._check(rc, "gptb_lml")
+        return rc, out.value, g
+
+    def prepare_variance(self):
+        self._check(self.lib.gptb_prepare_variance(self.h), "gptb_prepare_variance")
+
+    def set_affine(self, R=None, s=1.0, Sbar=None, Tbar=None):
+        if R is None:
+            self._check(self.lib.gptb_set_affine(self.h, None, 1.0, None, None), "gptb_set_affine")
+            return
+        R, Sbar, Tbar = as_f64(R), as_f64(Sbar), as_f64(Tbar)
+        self._check(self.lib.gptb_set_affine(self.h, ptr(R), float(s), ptr(Sbar), ptr(Tbar)), "gptb_set_affine")
+
+    def query(self, x, flags, vel=None):
+        """Host-pointer query; returns a dict of numpy arrays in the reference layouts."""
+        x = as_f64(x)
+        if x.ndim != 2 or x.shape[1] != self.d:
+            raise ValueError(f"query points must have shape (M, {self.d}), got {x.shape}")
+        M, d, p = x.shape[0], self.d, self.p
+        o = {}
+        if flags & MEAN: o["mean"] = np.empty((M, p))
+        if flags & STD: o["std"] = np.empty((M, p))
+        if flags & JAC: o["jac"] = np.empty((M, p, d))
+        if flags & JACVAR: o["jacvar"] = np.empty((M, p, d))
+        if flags & TRANSPORT: o["xhat"] = np.empty((M, d))
+        if flags & VELOCITY:
+            o["vhat"] = np.empty((M, d))
+            if flags & JACVAR: o["vvar"] = np.empty((M, p))
+        if flags & JPHI: o["jphi"] = np.empty((M, d, d))
+        if flags & DVAR: o["dvar"] = np.empty((d, M))
+        v = as_f64(vel) if vel is not None else None
+        if M == 0:
+            return o
+        g = o.get
+        rc = self.lib.gptb_query(self.h, ptr(x), M, int(flags), ptr(v), ptr(g("mean")), ptr(g("std")), ptr(g("jac")), ptr(g("jacvar")),
+                                 ptr(g("xhat")), ptr(g("vhat")), ptr(g("vvar")), ptr(g("jphi")), ptr(g("dvar")))
+        self._check(rc, "gptb_query")
+        return o
+
+    def query_dev(self, x_ptr, M, flags, vel_ptr=0, mean=0, std=0, jac=0, jacvar=0, xhat=0, vhat=0, vvar=0, jphi=0, dvar=0):
+        rc = self.lib.gptb_query_dev(self.h, x_ptr, M, int(flags), vel_ptr or None, mean or None, std or None, jac or None, jacvar or None,
+                                     xhat or None, vhat or None, vvar or None, jphi or None, dvar or None)
+        self._check(rc, "gptb_query_dev")
+
+    def export_L(self):
+        L = np.empty((self.N, self.N))
+        self._check(self.lib.gptb_export_L(self.h, ptr(L)), "gptb_export_L")
+        return L
+
+    def export_alpha(self):
+        a = np.empty((self.N, self.p))
+        self._check(self.lib.gptb_export_alpha(self.h, ptr(a)), "gptb_export_alpha")
+        return a
+
+    def export_Kinv(self):
+        K = np.empty((self.N, self.N))
+        self._check(self.lib.gptb_export_Kinv(self.h, ptr(K)), "gptb_export_Kinv")
+        return K
+
+    # -- instrumentation -------------------------------------------------------------------------------------
+    def launch_count(self):
+        return int(self.lib.gptb_launch_count(self.h))
+
+    def timing(self, on):
+        self.lib.gptb_timing_enable(self.h, int(on))
+
+    def timing_reset(self):
+        self.lib.gptb_timing_reset(self.h)
+
+    def kernel_time(self, which):
+        ms = C.c_double(0.0)
+        n = C.c_int64(0)
+        self._check(self.lib.gptb_kernel_time(self.h, which, C.byref(ms), C.byref(n)), "gptb_kernel_time")
+        return ms.value, n.value
+
+    def stream(self):
+        return self.lib.gptb_stream(self.h)
+
+    def set_workspace_limit(self, nbytes):
+        self._check(self.lib.gptb_set_workspace_limit(self.h, int(nbytes)), "gptb_set_workspace_limit")
+
+    # -- state exchange --------------------------------------------------------------------------------------
+    def state_alloc(self, N, d, p, with_variance=True):
+        self.N, self.d, self.p = int(N), int(d), int(p)
+        self._check(self.lib.gptb_state_alloc(self.h, self.N, self.d, self.p, int(with_variance)), "gptb_state_alloc")
+
+    def state_buffer(self, which):
+        p = C.c_void_p()
+        n = C.c_int64(0)
+        self._check(self.lib.gptb_state_buffer(self.h, which, C.byref(p), C.byref(n)), "gptb_state_buffer")
+        return p.value, n.value
+
+    def state_commit(self):
+        self._check(self.lib.gptb_state_commit(self.h), "gptb_state_commit")

@@ -1,0 +1,731 @@
+// libgptb200.so -- C ABI (include/gptb200.h) over the sm_100a kernels in gemm_engine.cuh / factor.cuh / query.cuh.
+// Host code here is orchestration only: allocation, launch order, chunking of query batches, status mapping.
+#include "../../include/gptb200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "query.cuh"
+
+using namespace gptb;
+
+namespace {
+
+struct EvPair { cudaEvent_t a, b; };
+
+}  // namespace
+
+struct gptb_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long N = 0, Npad = 0;
+    int T = 0, d = 0, p = 0;
+    double *X = nullptr, *Y = nullptr, *Xs = nullptr, *alpha = nullptr, *tmp1 = nullptr, *tmp2 = nullptr;
+    double *Lbuf = nullptr, *Dinv = nullptr, *Minv = nullptr, *Wbuf = nullptr, *gradpart = nullptr, *scal = nullptr;
+    double* header = nullptr;
+    int* info = nullptr;
+    KParams kp{};
+    Affine af{};
+    bool have_train = false, have_factor = false, have_alpha = false, have_minv = false, have_kinv = false;
+    // query workspace
+    double* ws = nullptr;
+    size_t ws_bytes = 0;
+    long long ws_limit = 8LL << 30;
+    // staging for the host-pointer query
+    double* stage = nullptr;
+    size_t stage_bytes = 0;
+    long long launches = 0;
+    bool timing = false;
+    std::vector<EvPair> ev[3];
+};
+
+#define GPTB_FAIL(h, code, ...)                               \
+    do {                                                      \
+        char _b[512];                                         \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                \
+        (h)->err = _b;                                        \
+        return (code);                                        \
+    } while (0)
+
+#define CU(h, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess) GPTB_FAIL(h, -2, "CUDA error %s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCH_CHECK(h)                                                                               \
+    do {                                                                                              \
+        (h)->launches++;                                                                              \
+        cudaError_t _e = cudaGetLastError();                                                          \
+        if (_e != cudaSuccess) GPTB_FAIL(h, -3, "kernel launch failed: %s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+static void tic(gptb_handle* h, int cls) {
+    if (!h->timing) return;
+    EvPair e;
+    cudaEventCreate(&e.a);
+    cudaEventCreate(&e.b);
+    cudaEventRecord(e.a, h->stream);
+    h->ev[cls].push_back(e);
+}
+static void toc(gptb_handle* h, int cls) {
+    if (!h->timing) return;
+    cudaEventRecord(h->ev[cls].back().b, h->stream);
+}
+
+static void free_model(gptb_handle* h) {
+    double** ptrs[] = {&h->X, &h->Y, &h->Xs, &h->alpha, &h->tmp1, &h->tmp2, &h->Lbuf, &h->Dinv, &h->Minv, &h->Wbuf, &h->gradpart};
+    for (auto pp : ptrs) {
+        if (*pp) cudaFree(*pp);
+        *pp = nullptr;
+    }
+    h->have_train = h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = false;
+}
+
+static int set_kernel_attrs(gptb_handle* h) {
+    CU(h, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(potrf_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(trtri_level_p1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(trtri_level_p2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(kinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(trmm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    return 0;
+}
+
+extern "C" int gptb_version(void) { return 100; }
+
+extern "C" int gptb_create(int device, gptb_handle** out) {
+    if (!out) return -1;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -4;   // no CUDA device: there is no fallback
+    if (device < 0 || device >= ndev) return -1;
+    gptb_handle* h = new gptb_handle();
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return -2; }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return -2; }
+    if (cudaMalloc(&h->info, sizeof(int)) != cudaSuccess || cudaMalloc(&h->scal, 64 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->header, 32 * sizeof(double)) != cudaSuccess) {
+        delete h;
+        return -2;
+    }
+    int rc = set_kernel_attrs(h);
+    if (rc) { delete h; return rc; }
+    h->af.on = 0;
+    h->af.s = 1.0;
+    for (int i = 0; i < MAXD; ++i)
+        for (int j = 0; j < MAXD; ++j) h->af.R[i][j] = (i == j) ? 1.0 : 0.0;
+    *out = h;
+    return 0;
+}
+
+extern "C" void gptb_destroy(gptb_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_model(h);
+    if (h->ws) cudaFree(h->ws);
+    if (h->stage) cudaFree(h->stage);
+    cudaFree(h->info);
+    cudaFree(h->scal);
+    cudaFree(h->header);
+    for (auto& v : h->ev)
+        for (auto& e : v) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char* gptb_last_error(gptb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" int64_t gptb_launch_count(gptb_handle* h) { return h ? h->launches : 0; }
+extern "C" void* gptb_stream(gptb_handle* h) { return h ? (void*)h->stream : nullptr; }
+extern "C" int gptb_set_workspace_limit(gptb_handle* h, int64_t bytes) {
+    if (!h || bytes < (1 << 20)) return -1;
+    h->ws_limit = bytes;
+    return 0;
+}
+extern "C" int gptb_timing_enable(gptb_handle* h, int on) { if (!h) return -1; h->timing = on != 0; return 0; }
+extern "C" int gptb_timing_reset(gptb_handle* h) {
+    if (!h) return -1;
+    cudaStreamSynchronize(h->stream);
+    for (auto& v : h->ev) {
+        for (auto& e : v) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        v.clear();
+    }
+    return 0;
+}
+extern "C" int gptb_kernel_time(gptb_handle* h, int which, double* ms, int64_t* n) {
+    if (!h || which < 0 || which > 2) return -1;
+    CU(h, cudaStreamSynchronize(h->stream));
+    double tot = 0.0;
+    for (auto& e : h->ev[which]) {
+        float t = 0.f;
+        CU(h, cudaEventElapsedTime(&t, e.a, e.b));
+        tot += t;
+    }
+    if (ms) *ms = tot;
+    if (n) *n = (int64_t)h->ev[which].size();
+    return 0;
+}
+
+static int alloc_model(gptb_handle* h, long long N, int d, int p, bool train) {
+    if (N < 1 || d < 1 || d > MAXD || p < 1 || p > MAXP) GPTB_FAIL(h, -1, "unsupported shape N=%lld d=%d p=%d (need 1<=d<=%d, 1<=p<=%d)", N, d, p, MAXD, MAXP);
+    CU(h, cudaSetDevice(h->device));
+    long long Npad = (N + TS - 1) / TS * TS;
+    if (Npad != h->Npad || d != h->d || p != h->p || (train && !h->Lbuf)) {
+        CU(h, cudaStreamSynchronize(h->stream));
+        free_model(h);
+        h->Npad = Npad; h->T = (int)(Npad / TS); h->d = d; h->p = p;
+        CU(h, cudaMalloc(&h->X, sizeof(double) * d * Npad));
+        CU(h, cudaMalloc(&h->Xs, sizeof(double) * d * Npad));
+        CU(h, cudaMalloc(&h->alpha, sizeof(double) * p * Npad));
+        if (train) {
+            CU(h, cudaMalloc(&h->Y, sizeof(double) * p * Npad));
+            CU(h, cudaMalloc(&h->tmp1, sizeof(double) * p * Npad));
+            CU(h, cudaMalloc(&h->tmp2, sizeof(double) * p * Npad));
+            CU(h, cudaMalloc(&h->Lbuf, sizeof(double) * Npad * Npad));
+            CU(h, cudaMalloc(&h->Dinv, sizeof(double) * Npad * TS));
+        }
+    }
+    h->N = N;
+    h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = false;
+    return 0;
+}
+
+extern "C" int gptb_set_train(gptb_handle* h, const double* X, const double* Y, int64_t N, int d, int p) {
+    if (!h || !X || !Y) return -1;
+    int rc = alloc_model(h, N, d, p, true);
+    if (rc) return rc;
+    const long long Npad = h->Npad;
+    std::vector<double> xs((size_t)d * Npad, 0.0), ys((size_t)p * Npad, 0.0);
+    for (long long n = 0; n < N; ++n) {
+        for (int a = 0; a < d; ++a) xs[(size_t)a * Npad + n] = X[n * d + a];
+        for (int o = 0; o < p; ++o) ys[(size_t)o * Npad + n] = Y[n * p + o];
+    }
+    CU(h, cudaMemcpyAsync(h->X, xs.data(), sizeof(double) * d * Npad, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->Y, ys.data(), sizeof(double) * p * Npad, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->have_train = true;
+    return 0;
+}
+
+static int set_params(gptb_handle* h, double c, const double* ell, double s2, double jitter) {
+    if (!(c > 0.0) || !(s2 >= 0.0) || !(jitter >= 0.0)) GPTB_FAIL(h, -1, "invalid hyper-parameters c=%g s2=%g jitter=%g", c, s2, jitter);
+    h->kp.c = c; h->kp.s2 = s2; h->kp.jitter = jitter;
+    for (int a = 0; a < MAXD; ++a) {
+        double e = (a < h->d) ? ell[a] : 1.0;
+        if (!(e > 0.0)) GPTB_FAIL(h, -1, "invalid length-scale %g", e);
+        h->kp.ell[a] = e;
+        h->kp.inv_ell[a] = 1.0 / e;
+    }
+    return 0;
+}
+
+template <typename F>
+static void dispatch_d(int d, F f) {
+    switch (d) {
+        case 1: f(std::integral_constant<int, 1>{}); break;
+        case 2: f(std::integral_constant<int, 2>{}); break;
+        case 3: f(std::integral_constant<int, 3>{}); break;
+        default: f(std::integral_constant<int, 4>{}); break;
+    }
+}
+
+static int launch_scale(gptb_handle* h) {
+    scale_inputs_kernel<<<(unsigned)((h->Npad + 255) / 256), 256, 0, h->stream>>>(h->X, h->Xs, (int)h->N, (int)h->Npad, h->d, h->kp);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// Gram + blocked right-looking Cholesky.  Returns LAPACK-style info through the handle's device flag.
+static int factorize_device(gptb_handle* h) {
+    const int T = h->T;
+    const long long ld = h->Npad;
+    CU(h, cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
+    int rc = launch_scale(h);
+    if (rc) return rc;
+    const unsigned ntri = (unsigned)((long long)T * (T + 1) / 2);
+    dispatch_d(h->d, [&](auto D) {
+        gram_lower_kernel<decltype(D)::value><<<ntri, 256, 0, h->stream>>>(h->Xs, h->Lbuf, (int)h->N, (int)h->Npad, h->kp);
+    });
+    LAUNCH_CHECK(h);
+    for (int kt = 0; kt < T; ++kt) {
+        potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->stream>>>(h->Lbuf, ld, kt, h->Dinv, h->info);
+        LAUNCH_CHECK(h);
+        const int r = T - kt - 1;
+        if (r > 0) {
+            potrf_panel_kernel<<<r, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->Lbuf, ld, kt, h->Dinv);
+            LAUNCH_CHECK(h);
+            tic(h, 2);
+            potrf_trailing_kernel<<<(unsigned)((long long)r * (r + 1) / 2), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->Lbuf, ld, kt, kt + 1, kt + 1);
+            toc(h, 2);
+            LAUNCH_CHECK(h);
+        }
+    }
+    int info = 0;
+    CU(h, cudaMemcpyAsync(&info, h->info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (info > 0) {
+        h->have_factor = false;
+        GPTB_FAIL(h, info, "the kernel matrix is not positive definite: leading minor of order %d", info);
+    }
+    return 0;
+}
+
+static int solve_alpha(gptb_handle* h) {
+    const int T = h->T;
+    const long long ld = h->Npad;
+    const size_t bytes = sizeof(double) * h->p * h->Npad;
+    CU(h, cudaMemcpyAsync(h->tmp1, h->Y, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    for (int kt = 0; kt < T; ++kt) {
+        int grid = T - kt - 1 > 0 ? T - kt - 1 : 1;
+        trsv_step_kernel<<<grid, 128, 0, h->stream>>>(h->Lbuf, ld, h->Dinv, h->tmp1, h->tmp2, (int)h->Npad, h->p, kt, 0);
+        LAUNCH_CHECK(h);
+    }
+    for (int kt = T - 1; kt >= 0; --kt) {
+        int grid = kt > 0 ? kt : 1;
+        trsv_step_kernel<<<grid, 128, 0, h->stream>>>(h->Lbuf, ld, h->Dinv, h->tmp2, h->alpha, (int)h->Npad, h->p, kt, 1);
+        LAUNCH_CHECK(h);
+    }
+    return 0;
+}
+
+static int lml_value(gptb_handle* h, double* lml) {
+    lml_terms_kernel<<<1, 1024, 0, h->stream>>>(h->Y, h->alpha, h->Lbuf, h->Npad, (int)h->N, (int)h->Npad, h->p, h->scal);
+    LAUNCH_CHECK(h);
+    double t[2];
+    CU(h, cudaMemcpyAsync(t, h->scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    *lml = -0.5 * t[0] - (double)h->p * t[1] - (double)h->p * (double)h->N * 0.5 * std::log(2.0 * M_PI);
+    return 0;
+}
+
+extern "C" int gptb_factorize(gptb_handle* h, double c, const double* ell, double s2, double jitter, double* lml) {
+    if (!h || !ell) return -1;
+    if (!h->have_train) GPTB_FAIL(h, -1, "gptb_factorize: no training data (call gptb_set_train)");
+    CU(h, cudaSetDevice(h->device));
+    int rc = set_params(h, c, ell, s2, jitter);
+    if (rc) return rc;
+    h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = false;
+    if ((rc = factorize_device(h))) return rc;
+    if ((rc = solve_alpha(h))) return rc;
+    h->have_factor = h->have_alpha = true;
+    if (lml) {
+        if ((rc = lml_value(h, lml))) return rc;
+    } else {
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+static int ensure_wbuf(gptb_handle* h) {
+    if (!h->Wbuf) CU(h, cudaMalloc(&h->Wbuf, sizeof(double) * h->Npad * h->Npad));
+    return 0;
+}
+
+static int build_minv(gptb_handle* h) {
+    if (h->have_minv) return 0;
+    if (!h->have_factor) GPTB_FAIL(h, -1, "no factorisation available");
+    const int T = h->T;
+    const long long ld = h->Npad;
+    if (!h->Minv) CU(h, cudaMalloc(&h->Minv, sizeof(double) * h->Npad * h->Npad));
+    int rc = ensure_wbuf(h);
+    if (rc) return rc;
+    h->have_kinv = false;
+    trtri_init_kernel<<<T, 256, 0, h->stream>>>(h->Minv, ld, h->Dinv);
+    LAUNCH_CHECK(h);
+    for (int s = 1; s < T; s *= 2) {
+        int pairs = (T + 2 * s - 1) / (2 * s);
+        unsigned grid = (unsigned)((long long)pairs * s * s);
+        trtri_level_p1_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->Lbuf, h->Minv, h->Wbuf, ld, T, s);
+        LAUNCH_CHECK(h);
+        trtri_level_p2_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->Minv, h->Wbuf, ld, T, s);
+        LAUNCH_CHECK(h);
+    }
+    h->have_minv = true;
+    return 0;
+}
+
+static int build_kinv(gptb_handle* h) {
+    if (h->have_kinv) return 0;
+    int rc = build_minv(h);
+    if (rc) return rc;
+    const int T = h->T;
+    kinv_kernel<<<(unsigned)((long long)T * (T + 1) / 2), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->Minv, h->Wbuf, h->Npad, T);
+    LAUNCH_CHECK(h);
+    h->have_kinv = true;
+    return 0;
+}
+
+extern "C" int gptb_prepare_variance(gptb_handle* h) {
+    if (!h) return -1;
+    CU(h, cudaSetDevice(h->device));
+    int rc = build_minv(h);
+    if (rc) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int gptb_lml(gptb_handle* h, double c, const double* ell, double s2, double jitter, int want_grad, double* lml, double* grad) {
+    if (!h || !lml) return -1;
+    int rc = gptb_factorize(h, c, ell, s2, jitter, lml);
+    if (rc) return rc;
+    if (!want_grad) return 0;
+    if (!grad) return -1;
+    if ((rc = build_kinv(h))) return rc;
+    const int T = h->T;
+    const long long ntri = (long long)T * (T + 1) / 2;
+    if (!h->gradpart) CU(h, cudaMalloc(&h->gradpart, sizeof(double) * ntri * (2 + MAXD)));
+    dispatch_d(h->d, [&](auto D) {
+        lml_grad_kernel<decltype(D)::value><<<(unsigned)ntri, 256, 0, h->stream>>>(h->Xs, h->alpha, h->Wbuf, (int)h->N, (int)h->Npad, h->p, h->kp, h->gradpart);
+    });
+    LAUNCH_CHECK(h);
+    lml_grad_reduce_kernel<<<1, 256, 0, h->stream>>>(h->gradpart, ntri, h->d, h->kp, h->scal + 8);
+    LAUNCH_CHECK(h);
+    double g[2 + MAXD];
+    CU(h, cudaMemcpyAsync(g, h->scal + 8, sizeof(double) * (2 + h->d), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 2 + h->d; ++i) grad[i] = g[i];
+    return 0;
+}
+
+extern "C" int gptb_set_affine(gptb_handle* h, const double* R, double s, const double* Sbar, const double* Tbar) {
+    if (!h) return -1;
+    if (!R) {   // reset to identity
+        h->af.on = 0;
+        h->af.s = 1.0;
+        for (int i = 0; i < MAXD; ++i)
+            for (int j = 0; j < MAXD; ++j) h->af.R[i][j] = (i == j) ? 1.0 : 0.0;
+        return 0;
+    }
+    if (h->d < 1) GPTB_FAIL(h, -1, "gptb_set_affine before the model shape is known");
+    if (!Sbar || !Tbar) return -1;
+    h->af.on = 1;
+    h->af.s = s;
+    for (int i = 0; i < MAXD; ++i) {
+        h->af.Sbar[i] = i < h->d ? Sbar[i] : 0.0;
+        h->af.Tbar[i] = i < h->d ? Tbar[i] : 0.0;
+        for (int j = 0; j < MAXD; ++j) h->af.R[i][j] = (i < h->d && j < h->d) ? R[i * h->d + j] : (i == j ? 1.0 : 0.0);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// queries
+// ---------------------------------------------------------------------------------------------------------------
+template <int D, int P>
+static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_dev, int B, int Bpad, unsigned flags, int nrhs,
+                       unsigned genflags, const QueryOut& out, long long q_off, long long Mtot, double* rhs, double* part,
+                       double* macc, double* xr, int nsplit) {
+    const int T = h->T;
+    const long long rows_total = (long long)nrhs * Bpad;
+    Affine af = h->af;
+    af.on = (flags & GPTB_AFFINE_IN) ? h->af.on : 0;
+    dim3 grid(Bpad / QPB, nsplit);
+    tic(h, 1);
+    kstar_kernel<D, P><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, B, Bpad, h->kp, af, genflags, rhs, xr, macc, nsplit);
+    toc(h, 1);
+    LAUNCH_CHECK(h);
+    if (nrhs > 0) {
+        const int rowtiles = (int)(rows_total / TS);
+        tic(h, 0);
+        trmm_sumsq_kernel<<<(unsigned)((long long)rowtiles * T), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(rhs, h->Minv, h->Npad, T, rowtiles, rows_total, part);
+        toc(h, 0);
+        LAUNCH_CHECK(h);
+    }
+    finalize_kernel<D, P><<<(B + 127) / 128, 128, 0, h->stream>>>(macc, nsplit, part, T, B, Bpad, rows_total, xr, vel_dev, h->kp, h->af, flags, out, q_off, Mtot);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+typedef int (*chunk_fn)(gptb_handle*, const double*, const double*, int, int, unsigned, int, unsigned, const QueryOut&, long long,
+                        long long, double*, double*, double*, double*, int);
+
+static chunk_fn pick_chunk_fn(int d, int p) {
+    static const chunk_fn table[4][4] = {
+        {query_chunk<1, 1>, query_chunk<1, 2>, query_chunk<1, 3>, query_chunk<1, 4>},
+        {query_chunk<2, 1>, query_chunk<2, 2>, query_chunk<2, 3>, query_chunk<2, 4>},
+        {query_chunk<3, 1>, query_chunk<3, 2>, query_chunk<3, 3>, query_chunk<3, 4>},
+        {query_chunk<4, 1>, query_chunk<4, 2>, query_chunk<4, 3>, query_chunk<4, 4>}};
+    return table[d - 1][p - 1];
+}
+
+extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, uint32_t flags, const double* vel_dev, double* mean_dev,
+                              double* std_dev, double* jac_dev, double* jacvar_dev, double* xhat_dev, double* vhat_dev,
+                              double* vvar_dev, double* jphi_dev, double* dvar_dev) {
+    if (!h || M < 0) return -1;
+    if (M == 0) return 0;
+    if (!x_dev) return -1;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->have_alpha) GPTB_FAIL(h, -1, "gptb_query: model is not fitted");
+    const int d = h->d, p = h->p;
+    if ((flags & GPTB_MEAN) && !mean_dev) GPTB_FAIL(h, -1, "GPTB_MEAN without output buffer");
+    if ((flags & GPTB_STD) && !std_dev) GPTB_FAIL(h, -1, "GPTB_STD without output buffer");
+    if ((flags & GPTB_JAC) && !jac_dev) GPTB_FAIL(h, -1, "GPTB_JAC without output buffer");
+    if ((flags & GPTB_JACVAR) && !jacvar_dev) GPTB_FAIL(h, -1, "GPTB_JACVAR without output buffer");
+    if ((flags & GPTB_TRANSPORT) && (!xhat_dev || d != p)) GPTB_FAIL(h, -1, "GPTB_TRANSPORT needs xhat and d == p");
+    if ((flags & GPTB_VELOCITY) && (!vhat_dev || !vel_dev || d != p)) GPTB_FAIL(h, -1, "GPTB_VELOCITY needs vel, vhat and d == p");
+    if ((flags & GPTB_VELOCITY) && (flags & GPTB_JACVAR) && !vvar_dev) GPTB_FAIL(h, -1, "GPTB_VELOCITY|GPTB_JACVAR needs vvar");
+    if ((flags & GPTB_JPHI) && (!jphi_dev || d != p)) GPTB_FAIL(h, -1, "GPTB_JPHI needs jphi and d == p");
+    if ((flags & GPTB_DVAR) && !dvar_dev) GPTB_FAIL(h, -1, "GPTB_DVAR without output buffer");
+
+    int nrhs = 0;
+    unsigned genflags = 0;
+    if (flags & (GPTB_STD | GPTB_DVAR)) { nrhs = 1; genflags |= 1u; }
+    if (flags & (GPTB_JACVAR | GPTB_DVAR)) { nrhs = 1 + d; genflags |= 2u; }
+    if (flags & GPTB_DVAR) { nrhs = 1 + 2 * d; genflags |= 4u | 1u; }
+    if (nrhs > 0) {
+        int rc = build_minv(h);
+        if (rc) return rc;
+    }
+    // batch size: bounded by the workspace for the right-hand-side rows (nrhs * Bpad * Npad doubles)
+    long long Bmax;
+    if (nrhs > 0) {
+        Bmax = h->ws_limit / (long long)(sizeof(double) * nrhs * h->Npad);
+        Bmax = Bmax / TS * TS;
+        if (Bmax < TS) Bmax = TS;
+        if (Bmax > 65536) Bmax = 65536;
+    } else {
+        Bmax = 1 << 20;
+    }
+    long long Bfirst = (M < Bmax) ? (M + TS - 1) / TS * TS : Bmax;
+    const int T = h->T;
+    const int NACC = p + p * d;
+    // split the training range when the batch is too small to fill the GPU
+    int nsplit = 1;
+    {
+        long long ctas = Bfirst / QPB;
+        while (ctas * nsplit < 296 && nsplit * 2 <= h->Npad / 32 && nsplit < 64) nsplit *= 2;
+    }
+    size_t need = 0;
+    auto carve = [&](size_t doubles) { size_t off = need; need += (doubles * sizeof(double) + 255) / 256 * 256; return off; };
+    size_t o_rhs = carve((size_t)nrhs * Bfirst * h->Npad);
+    size_t o_part = carve((size_t)(nrhs > 0 ? T : 0) * nrhs * Bfirst);
+    size_t o_macc = carve((size_t)nsplit * Bfirst * NACC);
+    size_t o_xr = carve((size_t)Bfirst * d);
+    if (need > h->ws_bytes) {
+        CU(h, cudaStreamSynchronize(h->stream));
+        if (h->ws) cudaFree(h->ws);
+        h->ws = nullptr;
+        h->ws_bytes = 0;
+        CU(h, cudaMalloc(&h->ws, need));
+        h->ws_bytes = need;
+    }
+    char* base = reinterpret_cast<char*>(h->ws);
+    double* rhs = reinterpret_cast<double*>(base + o_rhs);
+    double* part = reinterpret_cast<double*>(base + o_part);
+    double* macc = reinterpret_cast<double*>(base + o_macc);
+    double* xr = reinterpret_cast<double*>(base + o_xr);
+    QueryOut out{mean_dev, std_dev, jac_dev, jacvar_dev, xhat_dev, vhat_dev, vvar_dev, jphi_dev, dvar_dev};
+    chunk_fn fn = pick_chunk_fn(d, p);
+    for (long long q0 = 0; q0 < M; q0 += Bfirst) {
+        int B = (int)((M - q0 < Bfirst) ? (M - q0) : Bfirst);
+        int Bpad = (B + TS - 1) / TS * TS;
+        int rc = fn(h, x_dev + q0 * d, vel_dev ? vel_dev + q0 * d : nullptr, B, Bpad, flags, nrhs, genflags, out, q0, M, rhs, part, macc, xr, nsplit);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int gptb_query(gptb_handle* h, const double* x, int64_t M, uint32_t flags, const double* vel, double* mean, double* std,
+                          double* jac, double* jacvar, double* xhat, double* vhat, double* vvar, double* jphi, double* dvar) {
+    if (!h || M < 0) return -1;
+    if (M == 0) return 0;
+    if (!x) return -1;
+    CU(h, cudaSetDevice(h->device));
+    const int d = h->d, p = h->p;
+    if (d < 1) GPTB_FAIL(h, -1, "gptb_query: model is not fitted");
+    // staging layout (doubles per query)
+    struct Seg { const double* hin; double* hout; size_t per; size_t off; };
+    Seg segs[11] = {{x, nullptr, (size_t)d, 0},
+                    {(flags & GPTB_VELOCITY) ? vel : nullptr, nullptr, (size_t)d, 0},
+                    {nullptr, (flags & GPTB_MEAN) ? mean : nullptr, (size_t)p, 0},
+                    {nullptr, (flags & GPTB_STD) ? std : nullptr, (size_t)p, 0},
+                    {nullptr, (flags & GPTB_JAC) ? jac : nullptr, (size_t)p * d, 0},
+                    {nullptr, (flags & GPTB_JACVAR) ? jacvar : nullptr, (size_t)p * d, 0},
+                    {nullptr, (flags & GPTB_TRANSPORT) ? xhat : nullptr, (size_t)d, 0},
+                    {nullptr, (flags & GPTB_VELOCITY) ? vhat : nullptr, (size_t)d, 0},
+                    {nullptr, ((flags & GPTB_VELOCITY) && (flags & GPTB_JACVAR)) ? vvar : nullptr, (size_t)p, 0},
+                    {nullptr, (flags & GPTB_JPHI) ? jphi : nullptr, (size_t)d * d, 0},
+                    {nullptr, (flags & GPTB_DVAR) ? dvar : nullptr, (size_t)d, 0}};
+    if ((flags & GPTB_VELOCITY) && !vel) GPTB_FAIL(h, -1, "GPTB_VELOCITY without vel");
+    size_t tot = 0;
+    for (auto& s : segs) {
+        if (s.hin || s.hout) {
+            s.off = tot;
+            tot += (s.per * (size_t)M * sizeof(double) + 255) / 256 * 256;
+        }
+    }
+    if (tot > h->stage_bytes) {
+        CU(h, cudaStreamSynchronize(h->stream));
+        if (h->stage) cudaFree(h->stage);
+        h->stage = nullptr;
+        h->stage_bytes = 0;
+        CU(h, cudaMalloc(&h->stage, tot));
+        h->stage_bytes = tot;
+    }
+    char* sb = reinterpret_cast<char*>(h->stage);
+    auto dp = [&](int i) -> double* { return (segs[i].hin || segs[i].hout) ? reinterpret_cast<double*>(sb + segs[i].off) : nullptr; };
+    for (int i = 0; i < 2; ++i)
+        if (segs[i].hin) CU(h, cudaMemcpyAsync(dp(i), segs[i].hin, segs[i].per * M * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int rc = gptb_query_dev(h, dp(0), M, flags, dp(1), dp(2), dp(3), dp(4), dp(5), dp(6), dp(7), dp(8), dp(9), dp(10));
+    if (rc) return rc;
+    for (int i = 2; i < 11; ++i)
+        if (segs[i].hout) CU(h, cudaMemcpyAsync(segs[i].hout, dp(i), segs[i].per * M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// exports
+// ---------------------------------------------------------------------------------------------------------------
+static int export_square(gptb_handle* h, const double* src, double* dst, bool lower_only) {
+    const long long N = h->N, Npad = h->Npad;
+    CU(h, cudaMemcpy2DAsync(dst, sizeof(double) * N, src, sizeof(double) * Npad, sizeof(double) * N, N, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (lower_only)
+        for (long long i = 0; i < N; ++i)
+            for (long long j = i + 1; j < N; ++j) dst[i * N + j] = 0.0;
+    return 0;
+}
+
+extern "C" int gptb_export_L(gptb_handle* h, double* L) {
+    if (!h || !L) return -1;
+    if (!h->have_factor) GPTB_FAIL(h, -1, "gptb_export_L: model is not fitted");
+    CU(h, cudaSetDevice(h->device));
+    return export_square(h, h->Lbuf, L, true);
+}
+
+extern "C" int gptb_export_alpha(gptb_handle* h, double* alpha) {
+    if (!h || !alpha) return -1;
+    if (!h->have_alpha) GPTB_FAIL(h, -1, "gptb_export_alpha: model is not fitted");
+    CU(h, cudaSetDevice(h->device));
+    std::vector<double> tmp((size_t)h->p * h->Npad);
+    CU(h, cudaMemcpyAsync(tmp.data(), h->alpha, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (long long n = 0; n < h->N; ++n)
+        for (int o = 0; o < h->p; ++o) alpha[n * h->p + o] = tmp[(size_t)o * h->Npad + n];
+    return 0;
+}
+
+extern "C" int gptb_export_Kinv(gptb_handle* h, double* Kinv) {
+    if (!h || !Kinv) return -1;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->have_factor) GPTB_FAIL(h, -1, "gptb_export_Kinv: model is not fitted");
+    int rc = build_kinv(h);
+    if (rc) return rc;
+    return export_square(h, h->Wbuf, Kinv, false);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// state exchange for sharded queries
+// ---------------------------------------------------------------------------------------------------------------
+static int write_header(gptb_handle* h) {
+    double hd[32] = {0};
+    hd[0] = (double)h->N; hd[1] = h->d; hd[2] = h->p; hd[3] = h->kp.c; hd[4] = h->kp.s2; hd[5] = h->kp.jitter;
+    for (int a = 0; a < MAXD; ++a) hd[6 + a] = h->kp.ell[a];
+    hd[10] = h->have_minv ? 1.0 : 0.0;
+    CU(h, cudaMemcpyAsync(h->header, hd, sizeof(hd), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int gptb_state_alloc(gptb_handle* h, int64_t N, int d, int p, int with_variance) {
+    if (!h) return -1;
+    int rc = alloc_model(h, N, d, p, false);
+    if (rc) return rc;
+    if (with_variance && !h->Minv) CU(h, cudaMalloc(&h->Minv, sizeof(double) * h->Npad * h->Npad));
+    return 0;
+}
+
+extern "C" int gptb_state_buffer(gptb_handle* h, int which, void** dev_ptr, int64_t* bytes) {
+    if (!h || !dev_ptr || !bytes) return -1;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    switch (which) {
+        case 0:
+            if (h->have_alpha && h->have_train) { int rc = write_header(h); if (rc) return rc; }
+            *dev_ptr = h->header; *bytes = 32 * sizeof(double); return 0;
+        case 1: *dev_ptr = h->X; *bytes = (int64_t)sizeof(double) * h->d * h->Npad; return 0;
+        case 2: *dev_ptr = h->alpha; *bytes = (int64_t)sizeof(double) * h->p * h->Npad; return 0;
+        case 3: *dev_ptr = h->Minv; *bytes = h->Minv ? (int64_t)sizeof(double) * h->Npad * h->Npad : 0; return 0;
+        default: return -1;
+    }
+}
+
+extern "C" int gptb_state_commit(gptb_handle* h) {
+    if (!h) return -1;
+    CU(h, cudaSetDevice(h->device));
+    double hd[32];
+    CU(h, cudaMemcpy(hd, h->header, sizeof(hd), cudaMemcpyDeviceToHost));
+    if ((long long)hd[0] != h->N || (int)hd[1] != h->d || (int)hd[2] != h->p) GPTB_FAIL(h, -1, "state header does not match the allocated shape");
+    int rc = set_params(h, hd[3], &hd[6], hd[4], hd[5]);
+    if (rc) return rc;
+    if ((rc = launch_scale(h))) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->have_alpha = true;                                   // mean / Jacobian queries are served from (X, alpha)
+    h->have_minv = (hd[10] != 0.0) && (h->Minv != nullptr);  // variance queries need the inverse factor
+    h->have_kinv = false;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// unit-test hooks
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 1) test_gemm_kernel(const double* A, const double* B, double* C, int nt, int K, int maskA,
+                                                                   int maskB) {
+    extern __shared__ double smem[];
+    const int tm = blockIdx.x / nt, tn = blockIdx.x % nt;
+    double acc[8][4][2];
+    acc_clear(acc);
+    Operand a{A + (long long)tm * TS * K, K, maskA, tm};
+    Operand b{B + (long long)tn * TS * K, K, maskB, tn};
+    gemm_nt_tile(a, b, 0, K / TS, acc, smem);
+    double* out = C + (long long)tm * TS * ((long long)nt * TS) + (long long)tn * TS;
+    acc_foreach(acc, [&](int r, int c, double v0, double v1) {
+        out[(long long)r * nt * TS + c] = v0;
+        out[(long long)r * nt * TS + c + 1] = v1;
+    });
+}
+
+extern "C" int gptb_test_gemm_nt(gptb_handle* h, const double* A, const double* B, double* C, int mt, int nt, int K, int maskA, int maskB) {
+    if (!h || !A || !B || !C || mt < 1 || nt < 1 || K < TS || K % TS) return -1;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaFuncSetAttribute(test_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    double *dA, *dB, *dC;
+    size_t sa = sizeof(double) * mt * TS * K, sb = sizeof(double) * nt * TS * K, sc = sizeof(double) * mt * TS * nt * TS;
+    CU(h, cudaMalloc(&dA, sa));
+    CU(h, cudaMalloc(&dB, sb));
+    CU(h, cudaMalloc(&dC, sc));
+    // stream-ordered copies: the handle's stream is non-blocking, a legacy-stream cudaMemcpy would not order with it
+    CU(h, cudaMemcpyAsync(dA, A, sa, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(dB, B, sb, cudaMemcpyHostToDevice, h->stream));
+    test_gemm_kernel<<<mt * nt, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(dA, dB, dC, nt, K, maskA, maskB);
+    LAUNCH_CHECK(h);
+    CU(h, cudaMemcpyAsync(C, dC, sc, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    return 0;
+}
+
+extern "C" int gptb_test_potrf_tile(gptb_handle* h, const double* A128, double* L128, double* Linv128, int* info) {
+    if (!h || !A128 || !L128 || !Linv128 || !info) return -1;
+    CU(h, cudaSetDevice(h->device));
+    double *dA, *dI;
+    CU(h, cudaMalloc(&dA, sizeof(double) * TS * TS));
+    CU(h, cudaMalloc(&dI, sizeof(double) * TS * TS));
+    CU(h, cudaMemcpyAsync(dA, A128, sizeof(double) * TS * TS, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
+    potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->stream>>>(dA, TS, 0, dI, h->info);
+    LAUNCH_CHECK(h);
+    CU(h, cudaMemcpyAsync(L128, dA, sizeof(double) * TS * TS, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(Linv128, dI, sizeof(double) * TS * TS, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(info, h->info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    cudaFree(dA); cudaFree(dI);
+    return 0;
+}

@@ -1,0 +1,293 @@
+// Query-side kernels: fused k(x*,X) generator + posterior mean/Jacobian reduction, the variance triangular
+// multiply (|L^-1 k*|^2 and |L^-1 dk*/dx_a|^2 on the DMMA tile engine) and the transport epilogue.
+#pragma once
+#include "factor.cuh"
+
+namespace gptb {
+
+struct Affine {
+    int on;                 // apply gamma() to the inputs
+    double s;
+    double R[MAXD][MAXD];
+    double Sbar[MAXD];
+    double Tbar[MAXD];
+};
+
+constexpr int QPW = 4;          // queries per warp
+constexpr int QPB = 32;         // queries per CTA (8 warps)
+
+// ------------------------------------------------------------------------------------------------------------
+// Generator: for a batch of queries, regenerate k(x*, X) on the fly (never read from HBM), reduce it against alpha
+// for the mean and the analytic Jacobian, and -- only when a variance is requested -- emit the rows of the
+// right-hand-side matrix for the triangular multiply:
+//    rhs row (0*Bpad + q)       = k*            (GPTB_STD)
+//    rhs row ((1+a)*Bpad + q)   = dk*/dx_a      (GPTB_JACVAR)       = k* (X_a - x_a)/ell_a^2   gaussian_process.py:82-87
+//    rhs row ((1+d+a)*Bpad + q) = k* + dk*/dx_a (GPTB_DVAR, polarisation for the cross term) gaussian_process.py:104-126
+// Lanes run over training points (coalesced X/alpha loads and rhs stores), each warp keeps QPW queries in
+// registers; per-query accumulators are warp-reduced at the end.  grid = (Bpad/QPB, nsplit): the training range is
+// split when the batch alone cannot fill 148 SMs, partial sums are reduced in a fixed order by finalize.
+// Roofline: FP64 pipe (DFMA issue) -- ~21 DFMA slots for exp + 3D+2 for the distance + P(1+D) accumulate per pair.
+// ------------------------------------------------------------------------------------------------------------
+template <int D, int P>
+__global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ xq, const double* __restrict__ Xs,
+                                                    const double* __restrict__ alpha, int N, int Npad, int B, int Bpad,
+                                                    KParams kp, Affine af, unsigned flags, double* __restrict__ rhs,
+                                                    double* __restrict__ xr, double* __restrict__ macc, int nsplit) {
+    constexpr int NACC = P + P * D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q0 = blockIdx.x * QPB + warp * QPW;
+    double xs[QPW][D];
+    bool valid[QPW];
+#pragma unroll
+    for (int qq = 0; qq < QPW; ++qq) {
+        int q = q0 + qq;
+        valid[qq] = q < B;
+        double xin[D], xe[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) xin[a] = valid[qq] ? xq[(long long)q * D + a] : 0.0;
+        if (af.on) {
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+                double s = 0.0;
+#pragma unroll
+                for (int b = 0; b < D; ++b) s += af.R[a][b] * (xin[b] - af.Sbar[b]);
+                xe[a] = af.s * s + af.Tbar[a];
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < D; ++a) xe[a] = xin[a];
+        }
+#pragma unroll
+        for (int a = 0; a < D; ++a) xs[qq][a] = xe[a] / kp.ell[a];
+        if (blockIdx.y == 0 && lane == 0 && valid[qq])
+#pragma unroll
+            for (int a = 0; a < D; ++a) xr[(long long)q * D + a] = xe[a];
+    }
+    double acc[QPW][NACC];
+#pragma unroll
+    for (int qq = 0; qq < QPW; ++qq)
+#pragma unroll
+        for (int v = 0; v < NACC; ++v) acc[qq][v] = 0.0;
+
+    const bool st_k = flags & 1u, st_g = flags & 2u, st_kg = flags & 4u;
+    const int per = ((Npad / 32 + nsplit - 1) / nsplit) * 32;
+    const int nbeg = blockIdx.y * per;
+    const int nend = min(Npad, nbeg + per);
+    for (int n = nbeg + lane; n < nend; n += 32) {
+        double xn[D], al[P];
+#pragma unroll
+        for (int a = 0; a < D; ++a) xn[a] = Xs[(long long)a * Npad + n];
+#pragma unroll
+        for (int o = 0; o < P; ++o) al[o] = alpha[(long long)o * Npad + n];
+        const bool inb = n < N;
+#pragma unroll
+        for (int qq = 0; qq < QPW; ++qq) {
+            double df[D], s = 0.0;
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+                df[a] = xs[qq][a] - xn[a];
+                s += df[a] * df[a];
+            }
+            double k = (inb && valid[qq]) ? kp.c * exp(-0.5 * s) : 0.0;
+            const long long row = (long long)(q0 + qq) * Npad + n;
+            if (st_k) rhs[row] = k;
+#pragma unroll
+            for (int o = 0; o < P; ++o) acc[qq][o] = fma(k, al[o], acc[qq][o]);
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+                double u = -k * df[a];                 // k * (X_a - x_a)/ell_a
+                if (st_g | st_kg) {
+                    double gval = u * kp.inv_ell[a];
+                    if (st_g) rhs[(long long)(1 + a) * Bpad * Npad + row] = gval;
+                    if (st_kg) rhs[(long long)(1 + D + a) * Bpad * Npad + row] = k + gval;
+                }
+#pragma unroll
+                for (int o = 0; o < P; ++o) acc[qq][P + o * D + a] = fma(u, al[o], acc[qq][P + o * D + a]);
+            }
+        }
+    }
+#pragma unroll
+    for (int qq = 0; qq < QPW; ++qq) {
+#pragma unroll
+        for (int v = 0; v < NACC; ++v) {
+            double x = acc[qq][v];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+            acc[qq][v] = x;
+        }
+        if (lane == 0) {
+            double* dst = macc + ((long long)blockIdx.y * Bpad + q0 + qq) * NACC;
+#pragma unroll
+            for (int o = 0; o < P; ++o) dst[o] = acc[qq][o];
+#pragma unroll
+            for (int o = 0; o < P; ++o)
+#pragma unroll
+                for (int a = 0; a < D; ++a) dst[P + o * D + a] = acc[qq][P + o * D + a] * kp.inv_ell[a];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Variance triangular multiply:  W = RHS * Linv^T restricted to k <= i (Linv lower), reduced on the fly to row sums of
+// squares:  part[ti][row] = sum_{i in tile ti} ( sum_{k<=i} RHS[row][k] * Linv[i][k] )^2.
+// This is the batched TRSM of the reference (solve_triangular(L, K*^T), sklearn:_gpr.py:460) re-expressed as a TRMM with the
+// explicit inverse factor so every flop is a DMMA tile; W is never written to memory.
+// Algorithmic work per 128x128 output tile with ti: 2*128*128*128*(ti+1) flops.  Heaviest tiles are scheduled first.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 1) trmm_sumsq_kernel(const double* __restrict__ rhs, const double* __restrict__ Minv,
+                                                                    long long ld, int T, int rowtiles, long long rows_total,
+                                                                    double* __restrict__ part) {
+    extern __shared__ double smem[];
+    const int ti = T - 1 - (int)(blockIdx.x / rowtiles);
+    const int rt = (int)(blockIdx.x % rowtiles);
+    double acc[8][4][2];
+    acc_clear(acc);
+    Operand A{rhs + (long long)rt * TS * ld, ld, MASK_NONE, -1};
+    Operand B{Minv + (long long)ti * TS * ld, ld, MASK_LOWER, ti};
+    gemm_nt_tile(A, B, 0, ti + 1, acc, smem);
+    // row sums of squares: thread owns rows wm*64+mi*8+g; reduce over its 8 columns, the 4 lanes t, then the 4 wn warps
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3, wm = warp >> 2, wn = warp & 3;
+    double* red = smem;   // [4][128]
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        double s = 0.0;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            s = fma(acc[mi][ni][0], acc[mi][ni][0], s);
+            s = fma(acc[mi][ni][1], acc[mi][ni][1], s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (t == 0) red[wn * TS + wm * 64 + mi * 8 + g] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < TS) {
+        int r = threadIdx.x;
+        double s = (red[r] + red[TS + r]) + (red[2 * TS + r] + red[3 * TS + r]);
+        part[(long long)ti * rows_total + (long long)rt * TS + r] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Epilogue: fixed-order reduction of the partials, then every reference-layout output of the transport flow.
+// ------------------------------------------------------------------------------------------------------------
+struct QueryOut {
+    double* mean;    // (M,p)
+    double* std;     // (M,p)
+    double* jac;     // (M,p,d)
+    double* jacvar;  // (M,p,d)
+    double* xhat;    // (M,d)
+    double* vhat;    // (M,d)
+    double* vvar;    // (M,p)
+    double* jphi;    // (M,d,d)
+    double* dvar;    // (d,M)  -- leading dimension Mtot
+};
+
+template <int D, int P>
+__global__ void __launch_bounds__(128) finalize_kernel(const double* __restrict__ macc, int nsplit, const double* __restrict__ part,
+                                                       int T, int B, int Bpad, long long rows_total, const double* __restrict__ xr,
+                                                       const double* __restrict__ vel, KParams kp, Affine af, unsigned qflags,
+                                                       QueryOut out, long long q_off, long long Mtot) {
+    constexpr int NACC = P + P * D;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= B) return;
+    const long long gq = q_off + q;
+    double m[NACC];
+#pragma unroll
+    for (int v = 0; v < NACC; ++v) m[v] = 0.0;
+    for (int sidx = 0; sidx < nsplit; ++sidx) {
+        const double* src = macc + ((long long)sidx * Bpad + q) * NACC;
+#pragma unroll
+        for (int v = 0; v < NACC; ++v) m[v] += src[v];
+    }
+    if (qflags & 0x001u)
+#pragma unroll
+        for (int o = 0; o < P; ++o) out.mean[gq * P + o] = m[o];
+    if (qflags & 0x004u)
+#pragma unroll
+        for (int v = 0; v < P * D; ++v) out.jac[gq * P * D + v] = m[P + v];
+    if (qflags & 0x002u) {
+        double ss = 0.0;
+        for (int ti = 0; ti < T; ++ti) ss += part[(long long)ti * rows_total + q];
+        double var = (kp.c + kp.s2) - ss;
+        var = var < 0.0 ? 0.0 : var;                                    // sklearn:_gpr.py:485-491
+        double sd = sqrt(var) - sqrt(kp.s2);                            // gaussian_process.py:49
+#pragma unroll
+        for (int o = 0; o < P; ++o) out.std[gq * P + o] = sd;
+    }
+    double jv[D];
+    if (qflags & (0x008u | 0x100u)) {
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            double ss = 0.0;
+            for (int ti = 0; ti < T; ++ti) ss += part[(long long)ti * rows_total + (long long)(1 + a) * Bpad + q];
+            jv[a] = ss;
+        }
+    }
+    if (qflags & 0x100u) {
+        double s0 = 0.0;
+        for (int ti = 0; ti < T; ++ti) s0 += part[(long long)ti * rows_total + q];
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            double sk = 0.0;
+            for (int ti = 0; ti < T; ++ti) sk += part[(long long)ti * rows_total + (long long)(1 + D + a) * Bpad + q];
+            out.dvar[(long long)a * Mtot + gq] = -(sk - jv[a] - s0);     // -2 g^T K^-1 k*
+        }
+    }
+    if (qflags & 0x008u) {
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            jv[a] = kp.c / (kp.ell[a] * kp.ell[a]) - jv[a];             // gaussian_process.py:98
+#pragma unroll
+            for (int o = 0; o < P; ++o) out.jacvar[(gq * P + o) * D + a] = jv[a];
+        }
+    }
+    if (qflags & 0x020u)
+#pragma unroll
+        for (int a = 0; a < D; ++a) out.xhat[gq * D + a] = xr[(long long)q * D + a] + m[a < P ? a : 0];
+    if constexpr (D == P) {
+        if (qflags & (0x040u | 0x080u)) {
+            double jp[D][D];                                             // Jphi = R + Jpsi R   policy_transportation.py:45
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) s += m[P + i * D + k] * af.R[k][j];
+                    jp[i][j] = af.R[i][j] + s;
+                }
+            if (qflags & 0x080u)
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = 0; j < D; ++j) out.jphi[(gq * D + i) * D + j] = jp[i][j];
+            if (qflags & 0x040u) {
+                double v[D], rv[D];
+#pragma unroll
+                for (int a = 0; a < D; ++a) v[a] = vel[(long long)q * D + a];
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    double s = 0.0, s2 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        s += jp[i][j] * v[j];
+                        s2 += af.R[i][j] * v[j];
+                    }
+                    out.vhat[gq * D + i] = s;
+                    rv[i] = s2;
+                }
+                if (qflags & 0x008u) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int a = 0; a < D; ++a) s += jv[a] * (rv[a] * rv[a]);   // policy_transportation.py:51-52
+#pragma unroll
+                    for (int o = 0; o < P; ++o) out.vvar[gq * P + o] = s;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace gptb

@@ -1,0 +1,228 @@
+"""Drop-in for the reference's exact-GP "delta map" plugin
+(policy_transportation/models/gaussian_process.py:16-126) with every posterior computation on the B200 engine.
+
+Same constructor, methods, return layouts and post-fit attributes; the L-BFGS-B driver and sklearn's restart logic
+(sklearn:_gpr.py:299-344, 658-674) stay on the host exactly as in the reference, with the objective
+(log marginal likelihood + gradient) served by `gptb_lml`.
+"""
+from __future__ import annotations
+
+import warnings
+from operator import itemgetter
+
+import numpy as np
+import scipy.optimize
+from sklearn.base import clone
+from sklearn.utils import check_random_state
+
+from . import _lib
+from .kernel_spec import check_supported, map_gradient, read_params
+
+GPR_CHOLESKY_LOWER = True
+
+
+class _Regressor:
+    """What callers reach through `GaussianProcess.gp` in the reference (an sklearn GaussianProcessRegressor):
+    `alpha`, `kernel_`, `L_`, `alpha_`, `log_marginal_likelihood_value_`, `log_marginal_likelihood()`."""
+
+    def __init__(self, owner, kernel, alpha, optimizer, n_restarts_optimizer, n_targets):
+        self._o = owner
+        self.kernel = kernel
+        self.alpha = alpha
+        self.optimizer = optimizer
+        self.n_restarts_optimizer = n_restarts_optimizer
+        self.n_targets = n_targets
+        self.kernel_ = None
+        self.log_marginal_likelihood_value_ = None
+
+    @property
+    def L_(self):
+        return self._o._engine.export_L()
+
+    @property
+    def alpha_(self):
+        return self._o._engine.export_alpha()
+
+    @property
+    def X_train_(self):
+        return self._o.X
+
+    @property
+    def y_train_(self):
+        return self._o.Y
+
+    def log_marginal_likelihood(self, theta=None, eval_gradient=False, clone_kernel=True):
+        """sklearn:_gpr.py:541-656 -- evaluated on the GPU for `theta` (log-transformed, active hyper-parameters)."""
+        o = self._o
+        if theta is None:
+            if eval_gradient:
+                raise ValueError("Gradient can only be evaluated for theta!=None")
+            return self.log_marginal_likelihood_value_
+        kernel = self.kernel_.clone_with_theta(theta) if clone_kernel else self.kernel_
+        if not clone_kernel:
+            kernel.theta = theta
+        c, ell, s2 = read_params(kernel, o._engine.d)
+        info, lml, g = o._engine.lml(c, ell, s2, self.alpha, want_grad=eval_gradient)
+        o._factor_theta = None          # the handle now holds the factorisation for `theta`, not the fitted one
+        if info > 0:                    # not positive definite: sklearn:_gpr.py:590-593
+            return (-np.inf, np.zeros_like(theta)) if eval_gradient else -np.inf
+        if eval_gradient:
+            return lml, map_gradient(kernel, g, o._engine.d)
+        return lml
+
+
+class GaussianProcess:
+    def __init__(self, kernel, alpha=1e-10, optimizer='fmin_l_bfgs_b', n_restarts_optimizer=5, n_targets=None, device=None):
+        check_supported(kernel)
+        if optimizer is None:
+            n_restarts_optimizer = 0                     # gaussian_process.py:18-21 (sklearn default)
+        self.gp = _Regressor(self, kernel, alpha, optimizer, n_restarts_optimizer, n_targets)
+        self.kernel = kernel
+        self.alpha = alpha
+        self._device = device
+        self._engine_obj = None
+        self._factor_theta = None
+        self._K_inv = None
+
+    # -- engine handle (created lazily so that constructing the object never touches CUDA, like the reference) ----
+    @property
+    def _engine(self):
+        if self._engine_obj is None:
+            dev = self._device
+            if dev is None:
+                import os
+                dev = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("GPTB_DEVICE") is None else int(os.environ["GPTB_DEVICE"])
+            self._engine_obj = _lib.Engine(dev)
+        return self._engine_obj
+
+    # -- fit -------------------------------------------------------------------------------------------------------
+    def fit(self, X, Y):
+        X = np.asarray(X, dtype=np.float64)
+        Y = np.asarray(Y, dtype=np.float64)
+        if Y.ndim == 1:
+            Y = Y[:, None]
+        self.X = X
+        self.Y = Y
+        self.n_features = np.shape(self.X)[1]
+        self.n_samples = np.shape(self.X)[0]
+        self.n_outputs = np.shape(self.Y)[1]
+        mask = np.isnan(self.Y).any(axis=1)              # gaussian_process.py:33-35 (quirk Q9)
+        self.X = self.X[~mask]
+        self.Y = self.Y[~mask]
+
+        gp = self.gp
+        if gp.n_targets is not None and self.Y.shape[1] != gp.n_targets:     # sklearn:_gpr.py:268-273
+            raise ValueError(
+                "The number of targets seen in `y` is different from the parameter `n_targets`. "
+                f"Got {self.Y.shape[1]} != {gp.n_targets}.")
+        eng = self._engine
+        eng.set_train(self.X, self.Y)
+        gp.kernel_ = clone(gp.kernel)
+        rng = check_random_state(None)                   # the global numpy RNG, as in the reference (quirk Q10)
+        kernel_ = gp.kernel_
+        read_params(kernel_, eng.d)                      # validates the length-scale dimensionality early
+
+        if gp.optimizer is not None and kernel_.n_dims > 0:
+            def obj_func(theta, eval_gradient=True):
+                if eval_gradient:
+                    lml, grad = gp.log_marginal_likelihood(theta, eval_gradient=True, clone_kernel=False)
+                    return -lml, -grad
+                return -gp.log_marginal_likelihood(theta, clone_kernel=False)
+
+            optima = [self._constrained_optimization(obj_func, kernel_.theta, kernel_.bounds)]
+            if gp.n_restarts_optimizer > 0:
+                if not np.isfinite(kernel_.bounds).all():
+                    raise ValueError("Multiple optimizer restarts (n_restarts_optimizer>0) requires that all bounds are finite.")
+                bounds = kernel_.bounds
+                for _ in range(gp.n_restarts_optimizer):
+                    theta_initial = rng.uniform(bounds[:, 0], bounds[:, 1])
+                    optima.append(self._constrained_optimization(obj_func, theta_initial, bounds))
+            lml_values = list(map(itemgetter(1), optima))
+            kernel_.theta = optima[int(np.argmin(lml_values))][0]
+            kernel_._check_bounds_params()
+            gp.log_marginal_likelihood_value_ = -np.min(lml_values)
+            want_lml = False
+        else:
+            kernel_.theta = kernel_.theta                # normalises params to numpy values (quirk Q12)
+            want_lml = True
+
+        c, ell, s2 = read_params(kernel_, eng.d)
+        info, lml = eng.factorize(c, ell, s2, gp.alpha, want_lml=want_lml)   # sklearn:_gpr.py:347-367
+        if info > 0:
+            raise np.linalg.LinAlgError(
+                f"The kernel, {kernel_}, is not returning a positive definite matrix "
+                f"({info}-th leading minor). Try gradually increasing the 'alpha' parameter of your "
+                "GaussianProcessRegressor estimator.")
+        if want_lml:
+            gp.log_marginal_likelihood_value_ = lml
+        self._factor_theta = np.array(kernel_.theta, copy=True)
+        self._K_inv = None
+
+        self.kernel = kernel_
+        prm = self.kernel.get_params()
+        self.kernel_params_ = [prm['k1__k2__length_scale'], prm['k1']]
+        self.noise_var_ = gp.alpha + prm['k2__noise_level']
+        self.prior_var = prm['k1__k1__constant_value']
+        print('lenghtscales', prm['k1__k2__length_scale'])
+
+    def _constrained_optimization(self, obj_func, initial_theta, bounds):
+        gp = self.gp
+        if gp.optimizer == "fmin_l_bfgs_b":              # sklearn:_gpr.py:658-668
+            res = scipy.optimize.minimize(obj_func, initial_theta, method="L-BFGS-B", jac=True, bounds=bounds)
+            if res.status != 0:
+                from sklearn.exceptions import ConvergenceWarning
+                warnings.warn(f"lbfgs failed to converge (status={res.status}): {res.message}", ConvergenceWarning)
+            return res.x, res.fun
+        if callable(gp.optimizer):
+            theta_opt, func_min = gp.optimizer(obj_func, initial_theta, bounds=bounds)
+            return theta_opt, func_min
+        raise ValueError(f"Unknown optimizer {gp.optimizer}.")
+
+    def _ensure_fitted_factor(self):
+        """LML evaluations through `gp.log_marginal_likelihood` overwrite the handle's factor; restore the fitted one."""
+        if not hasattr(self, "X"):
+            raise RuntimeError("GaussianProcess is not fitted")
+        if self._factor_theta is None:
+            c, ell, s2 = read_params(self.kernel, self._engine.d)
+            info, _ = self._engine.factorize(c, ell, s2, self.gp.alpha, want_lml=False)
+            if info > 0:
+                raise np.linalg.LinAlgError("kernel matrix is not positive definite")
+            self._factor_theta = np.array(self.kernel.theta, copy=True)
+
+    @property
+    def K_inv(self):
+        """(c R + (alpha + s2) I)^-1, gaussian_process.py:42-43 -- built on demand from the Cholesky factor."""
+        if self._K_inv is None:
+            self._ensure_fitted_factor()
+            self._K_inv = self._engine.export_Kinv()
+        return self._K_inv
+
+    # -- queries ---------------------------------------------------------------------------------------------------
+    def _query(self, x, flags, vel=None):
+        self._ensure_fitted_factor()
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 1:
+            raise ValueError("Expected 2D array, got 1D array instead")
+        return self._engine.query(x, flags, vel)
+
+    def predict(self, x, return_std=False, return_cov=False):
+        if return_std == True:                                            # noqa: E712  (reference semantics)
+            o = self._query(x, _lib.MEAN | _lib.STD)
+            return o["mean"], o["std"]
+        if return_cov == True:                                            # noqa: E712
+            raise NotImplementedError("predict(return_cov=True) is not on the B200 path yet (SURVEY.md section 8 row f2)")
+        return self._query(x, _lib.MEAN)["mean"]
+
+    def samples(self, x):
+        raise NotImplementedError("samples() needs the joint posterior covariance (SURVEY.md section 8 row f2)")
+
+    def derivative(self, x, return_var=False):
+        """Jacobian of the posterior mean, layout (M, n_outputs, n_features) (quirk Q4), and optionally the variance of
+        each Jacobian entry (identical across outputs, quirk Q5)."""
+        if return_var == True:                                            # noqa: E712
+            o = self._query(x, _lib.JAC | _lib.JACVAR)
+            return o["jac"], o["jacvar"]
+        return self._query(x, _lib.JAC)["jac"]
+
+    def derivative_of_variance(self, x):
+        return self._query(x, _lib.DVAR)["dvar"]

@@ -1,0 +1,127 @@
+/*
+ * gptb200 -- C ABI of the B200-native exact-GP transport posterior engine (libgptb200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of vyasakash231/gaussian_process_transportation: the exact-GP
+ * posterior behind `GaussianProcess.fit / predict(return_std) / derivative` and the
+ * `PolicyTransportation` fit/apply flow.  Every entry point names the reference interface it replaces
+ * (paths relative to the reference root; `sklearn:` = scikit-learn's gaussian_process package, the un-vendored
+ * dependency that does the arithmetic there).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all arrays are C-contiguous IEEE float64 unless the name ends in `_dev`.
+ *   - host pointers may be pageable or pinned; `_dev` pointers are CUDA device pointers on the handle's device.
+ *   - every function returns 0 on success, >0 for a numerical failure (leading minor of that order is not positive
+ *     definite, LAPACK `info` convention, cf. sklearn:_gpr.py:351-361 / 590-593), <0 for CUDA / argument errors.
+ *     `gptb_last_error()` returns a human-readable message for the last non-zero status on that handle.
+ *   - a handle owns one device, one stream set and all device state; it is NOT thread-safe, distinct handles are
+ *     independent.  There is no CPU fallback anywhere behind this ABI.
+ *   - kernel family: k(x,y) = c * exp(-0.5 * sum_a ((x_a - y_a)/ell_a)^2)  [+ s2 on the training diagonal],
+ *     i.e. sklearn's ConstantKernel * RBF + WhiteKernel (sklearn:kernels.py:1273-1296,1403-1419,1558-1587).
+ *     `ell` always has d entries (isotropic kernels repeat the scalar).
+ */
+#ifndef GPTB200_H
+#define GPTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gptb_handle gptb_handle;
+
+/* query flags (OR-able) */
+#define GPTB_MEAN      0x001u  /* posterior mean  k* alpha                  gaussian_process.py:46-55 / sklearn:_gpr.py:446-447 */
+#define GPTB_STD       0x002u  /* sqrt(max(c+s2-|L^-1 k*|^2,0)) - sqrt(s2)   gaussian_process.py:49    / sklearn:_gpr.py:460-500 */
+#define GPTB_JAC       0x004u  /* d mean / d x, layout (M,p,d)               gaussian_process.py:72-90 */
+#define GPTB_JACVAR    0x008u  /* c/ell_a^2 - |L^-1 dk/dx_a|^2, (M,p,d)       gaussian_process.py:92-101 */
+#define GPTB_AFFINE_IN 0x010u  /* evaluate at gamma(x) = s R (x - Sbar) + Tbar affine_trasformation.py:51-53 */
+#define GPTB_TRANSPORT 0x020u  /* xhat = gamma(x) + mean                     policy_transportation.py:26-35 */
+#define GPTB_VELOCITY  0x040u  /* vhat = (R + J R) v, vvar = Jvar (R v)^2    policy_transportation.py:37-59 */
+#define GPTB_JPHI      0x080u  /* Jphi = R + J R, layout (M,d,d)             policy_transportation.py:61-64 */
+#define GPTB_DVAR      0x100u  /* -2 (dk/dx_a)^T K^-1 kstar, layout (d,M)      gaussian_process.py:104-126 */
+
+/* ---- lifetime ------------------------------------------------------------------------------------------------ */
+int  gptb_create(int device, gptb_handle** out);
+void gptb_destroy(gptb_handle* h);
+const char* gptb_last_error(gptb_handle* h);
+int  gptb_version(void);
+
+/* ---- training data: replaces the X/Y copies of GaussianProcess.fit (gaussian_process.py:25-35; sklearn:_gpr.py:296-297).
+ * X is (N,d), Y is (N,p).  Limits: 1 <= d <= 4, 1 <= p <= 4. */
+int gptb_set_train(gptb_handle* h, const double* X, const double* Y, int64_t N, int d, int p);
+
+/* ---- fit at fixed hyper-parameters: Gram build, L = chol(c R + (s2+jitter) I), alpha = L^-T L^-1 Y.
+ * Replaces sklearn:_gpr.py:347-367.  On return *lml (may be NULL) holds the log marginal likelihood
+ * (sklearn:_gpr.py:613-617).  Non-PD => returns the failing order (>0). */
+int gptb_factorize(gptb_handle* h, double c, const double* ell, double s2, double jitter, double* lml);
+
+/* ---- one log-marginal-likelihood evaluation with gradient w.r.t. log-hyper-parameters, the objective that
+ * scipy's L-BFGS-B drives in sklearn:_gpr.py:302-309,541-656.  grad has 2+d entries:
+ * [d/dlog c, d/dlog ell_0 .. ell_{d-1}, d/dlog s2]; an isotropic kernel's gradient is the sum of the ell entries.
+ * Non-PD => returns >0 and the caller substitutes (-inf, 0) as sklearn does (sklearn:_gpr.py:590-593).
+ * Leaves L/alpha for these hyper-parameters in the handle (a later gptb_factorize with the same values is free to
+ * recompute). */
+int gptb_lml(gptb_handle* h, double c, const double* ell, double s2, double jitter, int want_grad,
+             double* lml, double* grad);
+
+/* ---- explicit inverse factor for the variance queries (built lazily by gptb_query when needed). */
+int gptb_prepare_variance(gptb_handle* h);
+
+/* ---- affine pre-alignment gamma(x) = s R (x - Sbar) + Tbar (affine_trasformation.py:15-57).  R is (d,d) row-major.
+ * The d x d SVD stays on the host (numpy) for bit-parity; only the apply and the Jacobian algebra are fused here. */
+int gptb_set_affine(gptb_handle* h, const double* R, double s, const double* Sbar, const double* Tbar);
+
+/* ---- posterior / transport query on M points.  Any output pointer may be NULL when its flag is absent.
+ *   x (M,d) in; vel (M,d) in (GPTB_VELOCITY);
+ *   mean (M,p); std (M,p) [columns identical, sklearn:_gpr.py:494]; jac (M,p,d); jacvar (M,p,d) [identical over p];
+ *   xhat (M,d); vhat (M,d); vvar (M,p); jphi (M,d,d) [needs d==p]; dvar (d,M).
+ * Host-pointer version: copies in/out inside the call (this is the end-to-end path the benchmark's `e2e` times). */
+int gptb_query(gptb_handle* h, const double* x, int64_t M, uint32_t flags, const double* vel,
+               double* mean, double* std, double* jac, double* jacvar,
+               double* xhat, double* vhat, double* vvar, double* jphi, double* dvar);
+
+/* Device-pointer version: inputs/outputs already resident in HBM (benchmark `value`; sharded multi-GPU queries). */
+int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, uint32_t flags, const double* vel_dev,
+                   double* mean_dev, double* std_dev, double* jac_dev, double* jacvar_dev,
+                   double* xhat_dev, double* vhat_dev, double* vvar_dev, double* jphi_dev, double* dvar_dev);
+
+/* ---- read-back of fitted state (GaussianProcess attributes `gp.L_`, `gp.alpha_`, `K_inv`; gaussian_process.py:42-43).
+ * L is (N,N) lower (upper part zero), alpha is (N,p), Kinv is (N,N) symmetric. */
+int gptb_export_L(gptb_handle* h, double* L);
+int gptb_export_alpha(gptb_handle* h, double* alpha);
+int gptb_export_Kinv(gptb_handle* h, double* Kinv);
+
+/* ---- model-state exchange for query sharding: after a fit on rank 0 the immutable state is
+ * broadcast (NCCL, by the host layer) into identically-shaped buffers on every rank.
+ *   gptb_state_alloc : non-fitting ranks allocate state for (N,d,p) without training data.
+ *   gptb_state_buffer: device pointer + byte size of state buffer `which` (0: packed header/params, 1: X, 2: alpha,
+ *                      3: inverse factor) so the host can wrap it (cuda array interface) and broadcast in place.
+ *   gptb_state_commit: called on every rank after the broadcast to (re)derive cached quantities. */
+int gptb_state_alloc(gptb_handle* h, int64_t N, int d, int p, int with_variance);
+int gptb_state_buffer(gptb_handle* h, int which, void** dev_ptr, int64_t* bytes);
+int gptb_state_commit(gptb_handle* h);
+
+/* ---- instrumentation */
+/* number of kernels this library has launched on the handle since creation (benchmark `gpu_launches`). */
+int64_t gptb_launch_count(gptb_handle* h);
+/* CUDA-event time (ms) of the dominant kernel class accumulated since the last reset: which = 0 triangular-multiply
+ * (variance), 1 mean/Jacobian generator, 2 factorisation trailing update.  Returns launches through *n. */
+int gptb_kernel_time(gptb_handle* h, int which, double* ms, int64_t* n);
+int gptb_timing_enable(gptb_handle* h, int on);
+int gptb_timing_reset(gptb_handle* h);
+/* stream the handle launches on (cudaStream_t as void*), so callers can record events on it. */
+void* gptb_stream(gptb_handle* h);
+/* workspace cap for query batches in bytes (default 8 GiB). */
+int gptb_set_workspace_limit(gptb_handle* h, int64_t bytes);
+
+/* ---- unit-test hooks: exercise the DMMA tile engine and the small factor kernels in isolation.
+ * C (128*mt,128*nt) = A (128*mt,K) * B(128*nt,K)^T, all row-major host arrays, K multiple of 128. */
+int gptb_test_gemm_nt(gptb_handle* h, const double* A, const double* B, double* C, int mt, int nt, int K,
+                      int maskA, int maskB);
+int gptb_test_potrf_tile(gptb_handle* h, const double* A128, double* L128, double* Linv128, int* info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPTB200_H */

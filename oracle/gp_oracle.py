@@ -331,7 +331,8 @@ def synthetic_pairs(n, d=3, seed=0):
     S = rng.random((n, d))
     th = math.radians(20.0)
     R0 = np.eye(d)
-    R0[0, 0], R0[0, 1], R0[1, 0], R0[1, 1] = math.cos(th), -math.sin(th), math.sin(th), math.cos(th)
+    if d >= 2:
+        R0[0, 0], R0[0, 1], R0[1, 0], R0[1, 1] = math.cos(th), -math.sin(th), math.sin(th), math.cos(th)
     t0 = np.linspace(0.3, -0.2, d)
     T = S @ R0.T + t0 + 0.05 * np.sin(4.0 * S) + 0.01 * rng.standard_normal((n, d))
     return S, T

@@ -1,0 +1,82 @@
+"""CPU (`-m "not gpu"`): the C-ABI library loads and exports every symbol the header declares, the host-side kernel
+parsing / gradient mapping, and loud failure without a CUDA device (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gaussian_process_transportation_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "gptb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(gptb_[a-z_A-Z0-9]+)\s*\(", hdr))
+    assert declared, "no prototypes found in include/gptb200.h"
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in include/gptb200.h but not exported"
+    assert declared == set(_lib.SYMBOLS), "ctypes binding and header disagree"
+    assert _lib.load().gptb_version() >= 100
+
+
+def test_no_cuda_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from gaussian_process_transportation_b200 import _lib
+    with pytest.raises(_lib.GptbError):
+        _lib.Engine(0)
+
+
+def test_kernel_parsing_and_gradient_mapping():
+    from sklearn.gaussian_process.kernels import RBF, Matern, WhiteKernel, ConstantKernel as C
+    from gaussian_process_transportation_b200.kernel_spec import check_supported, map_gradient, read_params, UnsupportedKernel
+    k = C(0.1) * RBF(length_scale=[0.1]) + WhiteKernel(1e-4)
+    check_supported(k)
+    c, ell, s2 = read_params(k, 3)
+    assert c == 0.1 and s2 == 1e-4 and np.allclose(ell, [0.1] * 3)
+    g = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+    assert np.allclose(map_gradient(k, g, 3), [1.0, 9.0, 5.0])                      # isotropic: summed
+    k2 = C(0.1) * RBF(length_scale=[0.1, 0.2, 0.3]) + WhiteKernel(1e-4)
+    assert np.allclose(map_gradient(k2, g, 3), g)
+    k3 = C(0.1, constant_value_bounds="fixed") * RBF([0.1, 0.2, 0.3]) + WhiteKernel(1e-4, noise_level_bounds="fixed")
+    assert np.allclose(map_gradient(k3, g, 3), [2.0, 3.0, 4.0]) and k3.theta.size == 3
+    with pytest.raises(UnsupportedKernel):
+        check_supported(C(0.1) * Matern(0.1) + WhiteKernel(1e-4))
+    with pytest.raises(UnsupportedKernel):
+        check_supported(RBF(0.1))
+    with pytest.raises(ValueError):
+        read_params(C(1.0) * RBF([1.0, 2.0]) + WhiteKernel(1.0), 3)
+
+
+def test_affine_transform_matches_oracle():
+    from gaussian_process_transportation_b200 import AffineTransform
+    from oracle.gp_oracle import OracleAffine, synthetic_pairs
+    for d, scale in [(2, False), (3, False), (3, True)]:
+        S, T = synthetic_pairs(50, d, seed=3)
+        a, b = AffineTransform(do_scale=scale), OracleAffine(do_scale=scale)
+        a.fit(S, T); b.fit(S, T * (1.4 if scale else 1.0))
+        if not scale:
+            assert np.array_equal(a.rotation_matrix, b.rotation_matrix)
+            assert np.array_equal(a.predict(S), b.predict(S))
+        assert a.derivative(S).shape == (50, d, d)
+        assert abs(np.linalg.det(a.rotation_matrix) - 1.0) < 1e-12
+
+
+def test_quaternion_helpers_match_oracle():
+    from gaussian_process_transportation_b200.quaternion import from_rotation_matrix_nonorthogonal, multiply
+    from oracle.gp_oracle import quat_from_matrix_nonorthogonal, quat_mul
+    rng = np.random.default_rng(0)
+    M = np.eye(3) + 0.2 * rng.standard_normal((30, 3, 3))
+    a, b = from_rotation_matrix_nonorthogonal(M), quat_from_matrix_nonorthogonal(M)
+    s = np.sign(np.sum(a * b, axis=1))[:, None]
+    assert np.max(np.abs(a * s - b)) < 1e-12
+    q = rng.standard_normal((30, 4))
+    assert np.allclose(multiply(a, q), quat_mul(a, q))

@@ -1,0 +1,257 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI / the drop-in Python
+classes, against (a) the golden vectors produced by the unmodified reference and (b) the CPU oracle on seeded inputs.
+
+Tolerances are the north star's (BASELINE.json): posterior mean and Jacobian relative error <= 1e-9 (Frobenius norm per
+output array), std <= 1e-7 (max-abs, normalised by sqrt(c + s2) because std is ~0 near training points).
+Jacobian variance / velocity variance follow the std tolerance (they come from the same triangular products)."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+
+TOL_MEAN = 1e-9
+TOL_STD = 1e-7
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import gaussian_process_transportation_b200 as g
+    return g
+
+
+def kernel_of(g):
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+    return C(float(g["c"])) * RBF(g["ell"]) + WhiteKernel(float(g["s2"]))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# low level: tile engine and diagonal-tile factor kernels through the C-ABI test hooks
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mt,nt,K,ma,mb", [(1, 1, 128, 0, 0), (2, 3, 384, 0, 0), (2, 2, 256, 1, 2), (3, 2, 384, 2, 1)])
+def test_dmma_tile_engine(mt, nt, K, ma, mb):
+    from gaussian_process_transportation_b200 import _lib as L
+    eng = L.Engine(0)
+    rng = np.random.default_rng(mt * 7 + nt)
+    A = rng.standard_normal((mt * 128, K)); B = rng.standard_normal((nt * 128, K))
+    C = np.zeros((mt * 128, nt * 128))
+    assert eng.lib.gptb_test_gemm_nt(eng.h, L.ptr(A), L.ptr(B), L.ptr(C), mt, nt, K, ma, mb) == 0
+    for (M, mask, tiles) in [(A, ma, mt), (B, mb, nt)]:
+        for t in range(tiles):
+            if mask and t * 128 < K:
+                blk = M[t * 128:(t + 1) * 128, t * 128:(t + 1) * 128]
+                blk[:] = np.tril(blk) if mask == 1 else np.triu(blk)
+    assert rel(C, A @ B.T) < 1e-14
+
+
+def test_diag_tile_cholesky_and_inverse():
+    import ctypes
+    from gaussian_process_transportation_b200 import _lib as L
+    eng = L.Engine(0)
+    rng = np.random.default_rng(3)
+    M = rng.standard_normal((128, 128))
+    A = M @ M.T + 128 * np.eye(128)
+    Lt = np.zeros((128, 128)); Li = np.zeros((128, 128)); info = ctypes.c_int(0)
+    assert eng.lib.gptb_test_potrf_tile(eng.h, L.ptr(A), L.ptr(Lt), L.ptr(Li), ctypes.byref(info)) == 0
+    ref = np.linalg.cholesky(A)
+    assert info.value == 0
+    assert rel(np.tril(Lt), ref) < 1e-14 and rel(np.triu(Lt), ref.T) < 1e-14
+    assert rel(Li, np.linalg.inv(ref)) < 1e-13
+    A[40, 40] = -1.0     # LAPACK convention: order of the first non-positive leading minor
+    eng.lib.gptb_test_potrf_tile(eng.h, L.ptr(A), L.ptr(Lt), L.ptr(Li), ctypes.byref(info))
+    assert info.value == 41
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GaussianProcess drop-in vs goldens from the unmodified reference
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["syn_ard300.npz", "syn_iso500.npz", "syn_ard2d200.npz", "syn_ard1000.npz"])
+def test_gp_fixed_theta_vs_reference_golden(pkg, golden_dir, name):
+    g = load(golden_dir, name)
+    gp = pkg.GaussianProcess(kernel=kernel_of(g), optimizer=None)
+    gp.fit(g["X"], g["Y"])
+    sc = np.sqrt(float(g["c"]) + float(g["s2"]))
+    mean, std = gp.predict(g["xq"], return_std=True)
+    J, Jv = gp.derivative(g["xq"], return_var=True)
+    assert mean.shape == g["mean"].shape and std.shape == g["std"].shape
+    assert J.shape == g["J"].shape and Jv.shape == g["Jvar"].shape
+    assert rel(gp.gp.alpha_, g["alpha_"]) < 1e-8
+    assert rel(np.diag(gp.gp.L_), g["Ldiag"]) < 1e-12
+    assert rel(mean, g["mean"]) < TOL_MEAN
+    assert np.max(np.abs(std - g["std"])) / sc < TOL_STD
+    assert rel(J, g["J"]) < TOL_MEAN
+    assert rel(Jv, g["Jvar"]) < TOL_STD
+    assert rel(gp.predict(g["xq"]), g["mean"]) < TOL_MEAN
+    assert rel(gp.derivative(g["xq"]), g["J"]) < TOL_MEAN
+    assert rel(gp.derivative_of_variance(g["xq"]), g["dvar"]) < 1e-6
+    assert rel(np.diag(gp.K_inv), g["K_inv_diag"]) < 1e-8
+    # reference attribute surface (gaussian_process.py:38-41)
+    assert np.isclose(gp.prior_var, float(g["c"])) and np.isclose(gp.noise_var_, 1e-10 + float(g["s2"]))
+    assert np.allclose(np.atleast_1d(gp.kernel_params_[0]), g["ell"])
+
+
+@pytest.mark.parametrize("name", ["syn_ard300.npz", "syn_iso500.npz", "syn_ard2d200.npz"])
+def test_lml_and_gradient_vs_reference_golden(pkg, golden_dir, name):
+    g = load(golden_dir, name)
+    gp = pkg.GaussianProcess(kernel=kernel_of(g), optimizer=None)
+    gp.fit(g["X"], g["Y"])
+    for th, lml, grad in zip(g["thetas"], g["lmls"], g["grads"]):
+        v, gr = gp.gp.log_marginal_likelihood(th, eval_gradient=True)
+        assert abs(v - lml) <= 1e-10 * abs(lml)
+        assert rel(gr, grad) < 1e-8
+    # evaluating the LML must not disturb later predictions (the fitted factor is restored)
+    assert rel(gp.predict(g["xq"]), g["mean"]) < TOL_MEAN
+
+
+@pytest.mark.parametrize("name", ["c1_demo2d_fixed.npz", "c2_clouds3d_fixed.npz", "c2_clouds3d_scaled.npz"])
+def test_transport_flow_vs_reference_golden(pkg, golden_dir, name):
+    g = load(golden_dir, name)
+    t = pkg.GaussianProcessTransportation(kernel_transport=kernel_of(g))
+    t.method = pkg.PolicyTransportation(pkg.GaussianProcess(kernel=kernel_of(g), optimizer=None))
+    t.source_distribution, t.target_distribution = g["S"], g["T"]
+    t.training_traj, t.training_delta = g["traj_in"], g["delta_in"]
+    t.fit_transportation(do_scale=bool(g["do_scale"]))
+    t.apply_transportation()
+    sc = np.sqrt(float(g["c"]) + float(g["s2"]))
+    assert rel(t.method.affine_transform.rotation_matrix, g["R"]) < 1e-14
+    assert rel(t.training_traj, g["traj_out"]) < TOL_MEAN
+    assert np.max(np.abs(t.std - g["std"])) / sc < TOL_STD
+    assert rel(t.training_delta, g["delta_out"]) < TOL_MEAN
+    assert rel(t.var_vel_transported, g["var_vel"]) < 1e-6
+    assert t.std.shape == g["std"].shape and t.var_vel_transported.shape == g["var_vel"].shape
+    # the un-fused calls give the same answers as the fused façade pass
+    xt, sd = t.method.transport(g["traj_in"])
+    vt, vv = t.method.transport_velocity(g["traj_in"], g["delta_in"])
+    assert rel(xt, g["traj_out"]) < TOL_MEAN and rel(vt, g["delta_out"]) < TOL_MEAN
+    assert np.max(np.abs(sd - g["std"])) / sc < TOL_STD and rel(vv, g["var_vel"]) < 1e-6
+
+
+def test_optimised_fit_matches_reference_c1(pkg, golden_dir):
+    """Full L-BFGS-B fit with restarts on the 2D demo (example/2D/surface_generalization.py:67-78): same RNG seed as the golden
+    run.  LML is compared tightly, theta loosely (optimiser trajectories are rounding-sensitive)."""
+    g = load(golden_dir, "c1_demo2d_optimised.npz")
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+    k = C(constant_value=10) * RBF(4 * np.ones(2)) + WhiteKernel(0.01)
+    t = pkg.GaussianProcessTransportation(kernel_transport=k)
+    t.source_distribution, t.target_distribution = g["S"], g["T"]
+    t.training_traj, t.training_delta = g["traj_in"], g["delta_in"]
+    np.random.seed(0)
+    t.fit_transportation()
+    t.apply_transportation()
+    gp = t.method.delta_map
+    assert abs(gp.gp.log_marginal_likelihood_value_ - float(g["lml"])) < 1e-6 * abs(float(g["lml"]))
+    prm = gp.kernel.get_params()
+    assert np.allclose(prm["k1__k2__length_scale"], g["ell"], rtol=1e-3)
+    assert np.isclose(prm["k1__k1__constant_value"], float(g["c"]), rtol=1e-3)
+    assert rel(t.training_traj, g["traj_out"]) < 1e-5
+    assert rel(t.training_delta, g["delta_out"]) < 1e-4
+
+
+def test_orientation_vs_oracle_restatement(pkg, golden_dir):
+    from oracle.gp_oracle import OracleGPT
+    g = load(golden_dir, "c2_clouds3d_fixed.npz")
+    mine = pkg.GaussianProcessTransportation(kernel_transport=kernel_of(g))
+    mine.method = pkg.PolicyTransportation(pkg.GaussianProcess(kernel=kernel_of(g), optimizer=None))
+    ora = OracleGPT(kernel_of(g), optimizer=None)
+    for t in (mine, ora):
+        t.source_distribution, t.target_distribution = g["S"], g["T"]
+        t.training_traj, t.training_ori = g["traj_in"], g["ori_in"]
+        t.fit_transportation()
+        t.apply_transportation()
+    s = np.sign(np.sum(mine.training_ori * ora.training_ori, axis=1))[:, None]
+    assert np.max(np.abs(mine.training_ori * s - ora.training_ori)) < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# seeded synthetic sizes vs the CPU oracle, edge cases, size-independent properties
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,m", [(1, 2, 5), (7, 3, 1), (128, 3, 129), (129, 2, 300), (1500, 3, 2000), (640, 1, 33)])
+def test_engine_vs_oracle_shapes(n, d, m):
+    from gaussian_process_transportation_b200 import _lib as L
+    from oracle.gp_oracle import ChoGP, synthetic_pairs
+    S, T = synthetic_pairs(n, d, seed=n)
+    Y = T - S
+    ell = np.linspace(0.1, 0.2, d)
+    ora = ChoGP(0.1, ell, 1e-4).fit(S, Y)
+    eng = L.Engine(0)
+    eng.set_train(S, Y)
+    info, lml = eng.factorize(0.1, ell, 1e-4, 1e-10)
+    assert info == 0 and abs(lml - ora.lml()) <= 1e-10 * abs(ora.lml())
+    xq = np.random.default_rng(1).random((m, d))
+    o = eng.query(xq, L.MEAN | L.STD | L.JAC | L.JACVAR)
+    mean, std = ora.predict(xq, return_std=True)
+    J, Jv = ora.derivative(xq, return_var=True)
+    assert rel(o["mean"], mean) < TOL_MEAN and rel(o["jac"], J) < TOL_MEAN
+    assert np.max(np.abs(o["std"] - std)) / np.sqrt(0.1 + 1e-4) < TOL_STD
+    assert rel(o["jacvar"], Jv) < TOL_STD
+    assert eng.query(np.zeros((0, d)), L.MEAN)["mean"].shape == (0, d)
+
+
+def test_nan_rows_are_dropped_and_nonpd_raises(pkg):
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+    from oracle.gp_oracle import ChoGP, synthetic_pairs
+    S, T = synthetic_pairs(200, 3, seed=4)
+    Y = T - S
+    Y[5, 1] = np.nan
+    gp = pkg.GaussianProcess(C(0.1) * RBF([0.1, 0.1, 0.1]) + WhiteKernel(1e-4), optimizer=None)
+    gp.fit(S, Y)
+    keep = ~np.isnan(Y).any(axis=1)
+    ora = ChoGP(0.1, [0.1] * 3, 1e-4).fit(S[keep], Y[keep])
+    assert gp.n_samples == 200 and len(gp.X) == 199                       # quirk Q9
+    assert rel(gp.predict(S[:10]), ora.predict(S[:10])) < TOL_MEAN
+    # duplicated points with (almost) no noise: the factorisation must report non-PD like sklearn does
+    Sd = np.vstack([S[:50], S[:50]])
+    bad = pkg.GaussianProcess(C(1.0) * RBF(1.0) + WhiteKernel(1e-30), alpha=0.0, optimizer=None)
+    with pytest.raises(np.linalg.LinAlgError):
+        bad.fit(Sd, np.vstack([Y[:50], Y[:50]])[:, :])
+    with pytest.raises(NotImplementedError):
+        from sklearn.gaussian_process.kernels import Matern
+        pkg.GaussianProcess(C(1.0) * Matern(1.0) + WhiteKernel(1e-3))
+
+
+def test_full_size_properties_n4096():
+    """BASELINE config 3 size (N=4096): size-independent properties instead of an O(N^3) CPU oracle run.
+    (1) posterior mean at the training inputs reproduces y - (s2+jitter)*alpha exactly (K alpha = y identity);
+    (2) the variance at training inputs is c + s2 - k^T K^-1 k with K^-1 k = e_i - (s2+jitter) K^-1 e_i, i.e.
+        var_i = s2 + (s2+jitter) (1 - (s2+jitter) Kinv_ii) - jitter ... checked through the exported K^-1 diagonal;
+    (3) linearity: the mean is linear in Y."""
+    from gaussian_process_transportation_b200 import _lib as L
+    from oracle.gp_oracle import synthetic_pairs
+    n, d = 4096, 3
+    S, T = synthetic_pairs(n, d, seed=0)
+    Y = T - S
+    c, ell, s2, jit = 0.1, [0.1, 0.1, 0.1], 1e-4, 1e-10
+    eng = L.Engine(0)
+    eng.set_train(S, Y)
+    info, _ = eng.factorize(c, ell, s2, jit)
+    assert info == 0
+    alpha = eng.export_alpha()
+    idx = np.arange(0, n, 8)
+    o = eng.query(S[idx], L.MEAN | L.STD)
+    assert rel(o["mean"], Y[idx] - (s2 + jit) * alpha[idx]) < 1e-9
+    kd = np.diag(eng.export_Kinv())[idx]
+    t = s2 + jit
+    var = (c + s2) - ((c + t) - 2 * t + t * t * kd)          # k_i = K e_i - t e_i  =>  k^T K^-1 k = K_ii - 2t + t^2 Kinv_ii
+    std = np.sqrt(np.maximum(var, 0)) - np.sqrt(s2)
+    assert np.max(np.abs(o["std"][:, 0] - std)) / np.sqrt(c + s2) < TOL_STD
+    eng2 = L.Engine(0)
+    eng2.set_train(S, 2.0 * Y + 1.0)
+    eng2.factorize(c, ell, s2, jit)
+    eng3 = L.Engine(0)
+    eng3.set_train(S, np.ones_like(Y))
+    eng3.factorize(c, ell, s2, jit)
+    xq = np.random.default_rng(2).random((512, d))
+    m1 = eng.query(xq, L.MEAN)["mean"]; m2 = eng2.query(xq, L.MEAN)["mean"]; m3 = eng3.query(xq, L.MEAN)["mean"]
+    assert rel(m2, 2.0 * m1 + m3) < 1e-9
