@@ -215,16 +215,19 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lb
 // ------------------------------------------------------------------------------------------------------------
 // Panel: L[i,k] = A[i,k] * Dinv_k^T for the row tiles i > k (in place), plus the mirror L[i,k]^T into the upper half.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_panel_kernel(double* __restrict__ Lbuf, long long ld, int kt,
-                                                                     const double* __restrict__ dinv) {
-    extern __shared__ double smem[];
+__global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_panel_kernel(const __grid_constant__ CUtensorMap mapL,
+                                                                     const __grid_constant__ CUtensorMap mapD,
+                                                                     double* __restrict__ Lbuf, long long ld, int kt) {
+    extern __shared__ __align__(128) double smem[];
+    __shared__ PipeBarriers pipe;
+    pipe_init(&pipe);
     const int ti = kt + 1 + blockIdx.x;
     double acc[8][4][2];
     acc_clear(acc);
-    // k-space of this product is the 128 columns of block column kt: shift bases so that k-tile 0 is that block
-    Operand A{Lbuf + (long long)ti * TS * ld + (long long)kt * TS, ld, MASK_NONE, -1};
-    Operand B{dinv + (long long)kt * TS * TS, TS, MASK_NONE, -1};   // Dinv rows n, k <= n (zeros stored above)
-    gemm_nt_tile(A, B, 0, 1, acc, smem);
+    // k-space of this product is the 128 columns of block column kt: offset k so that k-tile 0 is that block
+    Operand A{&mapL, ti * TS, kt * TS, MASK_NONE, -1};
+    Operand B{&mapD, kt * TS, 0, MASK_NONE, -1};   // Dinv rows n, k <= n (zeros stored above)
+    gemm_nt_tile(A, B, 0, 1, acc, smem, &pipe);
     double* out = Lbuf + (long long)ti * TS * ld + (long long)kt * TS;          // lower: rows ti, cols kt
     double* outT = Lbuf + (long long)kt * TS * ld + (long long)ti * TS;         // mirror: rows kt, cols ti
     acc_foreach(acc, [&](int r, int c, double v0, double v1) {
@@ -239,17 +242,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_panel_kernel(double* __
 // SYRK on the DMMA engine.  blockIdx.x enumerates the lower triangle of the trailing tile grid, heaviest rows first
 // is irrelevant here (all tiles cost the same).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_trailing_kernel(double* __restrict__ Lbuf, long long ld, int k0, int k1,
+__global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_trailing_kernel(const __grid_constant__ CUtensorMap mapL,
+                                                                        double* __restrict__ Lbuf, long long ld, int k0, int k1,
                                                                         int first_tile) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(128) double smem[];
+    __shared__ PipeBarriers pipe;
+    pipe_init(&pipe);
     int a, b;
     tri_decode(blockIdx.x, a, b);
     const int ti = first_tile + a, tj = first_tile + b;
     double acc[8][4][2];
     acc_clear(acc);
-    Operand A{Lbuf + (long long)ti * TS * ld, ld, MASK_NONE, -1};
-    Operand B{Lbuf + (long long)tj * TS * ld, ld, MASK_NONE, -1};
-    gemm_nt_tile(A, B, k0, k1, acc, smem);
+    Operand A{&mapL, ti * TS, 0, MASK_NONE, -1};
+    Operand B{&mapL, tj * TS, 0, MASK_NONE, -1};
+    gemm_nt_tile(A, B, k0, k1, acc, smem, &pipe);
     double* out = Lbuf + (long long)ti * TS * ld + (long long)tj * TS;
     acc_foreach(acc, [&](int r, int c, double v0, double v1) {
         double2* p = reinterpret_cast<double2*>(out + (long long)r * ld + c);
@@ -359,9 +365,12 @@ __global__ void __launch_bounds__(256) trtri_init_kernel(double* __restrict__ Mi
 
 // Level with half-size s tiles: diagonal super-blocks [2qs, 2qs+s) = "A" and [2qs+s, min(2qs+2s,T)) = "C".
 // Product 1 (transposed temp):  W[n][m] = sum_{k in A, k >= n} Minv^T[n][k] * L[m][k],   n in A (rows), m in C (cols)
-__global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_level_p1_kernel(const double* __restrict__ Lbuf, const double* __restrict__ Minv,
+__global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_level_p1_kernel(const __grid_constant__ CUtensorMap mapL,
+                                                                        const __grid_constant__ CUtensorMap mapM,
                                                                         double* __restrict__ W, long long ld, int T, int s) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(128) double smem[];
+    __shared__ PipeBarriers pipe;
+    pipe_init(&pipe);
     // decode blockIdx.x -> (pair q, tile n in A, tile m in C); enumerate with per-pair stride s*s (skip out-of-range)
     const int per = s * s;
     const int q = blockIdx.x / per, rem = blockIdx.x % per;
@@ -371,9 +380,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_level_p1_kernel(const d
     const int a_end = 2 * q * s + s;             // k-tiles tn .. a_end-1
     double acc[8][4][2];
     acc_clear(acc);
-    Operand A{Minv + (long long)tn * TS * ld, ld, MASK_UPPER, tn};   // mirror rows n: Minv^T[n][k], k >= n
-    Operand B{Lbuf + (long long)tm * TS * ld, ld, MASK_NONE, -1};    // L rows m (below the diagonal for k in A)
-    gemm_nt_tile(A, B, tn, a_end, acc, smem);
+    Operand A{&mapM, tn * TS, 0, MASK_UPPER, tn};   // mirror rows n: Minv^T[n][k], k >= n
+    Operand B{&mapL, tm * TS, 0, MASK_NONE, -1};    // L rows m (below the diagonal for k in A)
+    gemm_nt_tile(A, B, tn, a_end, acc, smem, &pipe);
     double* out = W + (long long)tn * TS * ld + (long long)tm * TS;
     acc_foreach(acc, [&](int r, int c, double v0, double v1) {
         *reinterpret_cast<double2*>(out + (long long)r * ld + c) = make_double2(v0, v1);
@@ -381,9 +390,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_level_p1_kernel(const d
 }
 
 // Product 2:  Minv[m][n] = - sum_{k in C, k <= m} Minv[m][k] * W[n][k],  m in C (rows), n in A (cols); plus mirror.
-__global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_level_p2_kernel(double* __restrict__ Minv, const double* __restrict__ W,
-                                                                        long long ld, int T, int s) {
-    extern __shared__ double smem[];
+__global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_level_p2_kernel(const __grid_constant__ CUtensorMap mapM,
+                                                                        const __grid_constant__ CUtensorMap mapW,
+                                                                        double* __restrict__ Minv, long long ld, int T, int s) {
+    extern __shared__ __align__(128) double smem[];
+    __shared__ PipeBarriers pipe;
+    pipe_init(&pipe);
     const int per = s * s;
     const int q = blockIdx.x / per, rem = blockIdx.x % per;
     const int tm = 2 * q * s + s + rem / s;      // C tile (row of Minv)
@@ -392,9 +404,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_level_p2_kernel(double*
     const int c_begin = 2 * q * s + s;           // k-tiles c_begin .. tm
     double acc[8][4][2];
     acc_clear(acc);
-    Operand A{Minv + (long long)tm * TS * ld, ld, MASK_LOWER, tm};   // Minv rows m, k <= m
-    Operand B{W + (long long)tn * TS * ld, ld, MASK_NONE, -1};       // W rows n, cols k in C
-    gemm_nt_tile(A, B, c_begin, tm + 1, acc, smem);
+    Operand A{&mapM, tm * TS, 0, MASK_LOWER, tm};   // Minv rows m, k <= m
+    Operand B{&mapW, tn * TS, 0, MASK_NONE, -1};    // W rows n, cols k in C
+    gemm_nt_tile(A, B, c_begin, tm + 1, acc, smem, &pipe);
     double* out = Minv + (long long)tm * TS * ld + (long long)tn * TS;
     double* outT = Minv + (long long)tn * TS * ld + (long long)tm * TS;
     acc_foreach(acc, [&](int r, int c, double v0, double v1) {
@@ -405,16 +417,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_level_p2_kernel(double*
 }
 
 // K^-1 = L^-T L^-1:  Kinv[i][j] = sum_{k >= max(i,j)} Minv^T[i][k] Minv^T[j][k]; lower tiles (ti >= tj) + mirror.
-__global__ void __launch_bounds__(GEMM_THREADS, 1) kinv_kernel(const double* __restrict__ Minv, double* __restrict__ Kinv, long long ld,
-                                                              int T) {
-    extern __shared__ double smem[];
+__global__ void __launch_bounds__(GEMM_THREADS, 1) kinv_kernel(const __grid_constant__ CUtensorMap mapM, double* __restrict__ Kinv,
+                                                              long long ld, int T) {
+    extern __shared__ __align__(128) double smem[];
+    __shared__ PipeBarriers pipe;
+    pipe_init(&pipe);
     int ti, tj;
     tri_decode(blockIdx.x, ti, tj);
     double acc[8][4][2];
     acc_clear(acc);
-    Operand A{Minv + (long long)ti * TS * ld, ld, MASK_UPPER, ti};
-    Operand B{Minv + (long long)tj * TS * ld, ld, MASK_UPPER, tj};   // only bites when tj == ti
-    gemm_nt_tile(A, B, ti, T, acc, smem);
+    Operand A{&mapM, ti * TS, 0, MASK_UPPER, ti};
+    Operand B{&mapM, tj * TS, 0, MASK_UPPER, tj};   // only bites when tj == ti
+    gemm_nt_tile(A, B, ti, T, acc, smem, &pipe);
     double* out = Kinv + (long long)ti * TS * ld + (long long)tj * TS;
     double* outT = Kinv + (long long)tj * TS * ld + (long long)ti * TS;
     const bool diag = (ti == tj);

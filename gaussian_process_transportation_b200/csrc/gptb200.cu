@@ -16,6 +16,33 @@ namespace {
 
 struct EvPair { cudaEvent_t a, b; };
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        cudaDriverEntryPointQueryResult q;
+        void* p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 3-D TMA view (4, rows, K/4) of a row-major FP64 matrix (rows x K, leading dimension ld): box (4, 128, BK/4) lands in
+// shared memory as [k/4][row][k%4], the conflict-free fragment layout of gemm_engine.cuh.
+bool make_operand_map(CUtensorMap* m, const double* base, long long rows, long long K, long long ld) {
+    EncodeTiledFn enc = get_encoder();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {4, (cuuint64_t)rows, (cuuint64_t)(K / 4)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 8, 32};
+    cuuint32_t box[3] = {4, (cuuint32_t)TS, (cuuint32_t)(BK / 4)};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 struct gptb_handle {
@@ -28,6 +55,7 @@ struct gptb_handle {
     double *Lbuf = nullptr, *Dinv = nullptr, *Minv = nullptr, *Wbuf = nullptr, *gradpart = nullptr, *scal = nullptr;
     double* header = nullptr;
     int* info = nullptr;
+    CUtensorMap mapL, mapD, mapM, mapW;      // TMA views of Lbuf, Dinv, Minv, Wbuf
     KParams kp{};
     Affine af{};
     bool have_train = false, have_factor = false, have_alpha = false, have_minv = false, have_kinv = false;
@@ -55,6 +83,11 @@ struct gptb_handle {
     do {                                                                                              \
         cudaError_t _e = (call);                                                                      \
         if (_e != cudaSuccess) GPTB_FAIL(h, -2, "CUDA error %s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define MAKE_MAP(h, m, base, rows, K, ld)                                                              \
+    do {                                                                                               \
+        if (!make_operand_map((m), (base), (rows), (K), (ld))) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed at %s:%d", __FILE__, __LINE__); \
     } while (0)
 
 #define LAUNCH_CHECK(h)                                                                               \
@@ -189,6 +222,8 @@ static int alloc_model(gptb_handle* h, long long N, int d, int p, bool train) {
             CU(h, cudaMalloc(&h->tmp2, sizeof(double) * p * Npad));
             CU(h, cudaMalloc(&h->Lbuf, sizeof(double) * Npad * Npad));
             CU(h, cudaMalloc(&h->Dinv, sizeof(double) * Npad * TS));
+            MAKE_MAP(h, &h->mapL, h->Lbuf, Npad, Npad, Npad);
+            MAKE_MAP(h, &h->mapD, h->Dinv, Npad, TS, TS);
         }
     }
     h->N = N;
@@ -258,10 +293,10 @@ static int factorize_device(gptb_handle* h) {
         LAUNCH_CHECK(h);
         const int r = T - kt - 1;
         if (r > 0) {
-            potrf_panel_kernel<<<r, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->Lbuf, ld, kt, h->Dinv);
+            potrf_panel_kernel<<<r, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->mapD, h->Lbuf, ld, kt);
             LAUNCH_CHECK(h);
             tic(h, 2);
-            potrf_trailing_kernel<<<(unsigned)((long long)r * (r + 1) / 2), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->Lbuf, ld, kt, kt + 1, kt + 1);
+            potrf_trailing_kernel<<<(unsigned)((long long)r * (r + 1) / 2), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->Lbuf, ld, kt, kt + 1, kt + 1);
             toc(h, 2);
             LAUNCH_CHECK(h);
         }
@@ -323,7 +358,10 @@ extern "C" int gptb_factorize(gptb_handle* h, double c, const double* ell, doubl
 }
 
 static int ensure_wbuf(gptb_handle* h) {
-    if (!h->Wbuf) CU(h, cudaMalloc(&h->Wbuf, sizeof(double) * h->Npad * h->Npad));
+    if (!h->Wbuf) {
+        CU(h, cudaMalloc(&h->Wbuf, sizeof(double) * h->Npad * h->Npad));
+        MAKE_MAP(h, &h->mapW, h->Wbuf, h->Npad, h->Npad, h->Npad);
+    }
     return 0;
 }
 
@@ -332,7 +370,10 @@ static int build_minv(gptb_handle* h) {
     if (!h->have_factor) GPTB_FAIL(h, -1, "no factorisation available");
     const int T = h->T;
     const long long ld = h->Npad;
-    if (!h->Minv) CU(h, cudaMalloc(&h->Minv, sizeof(double) * h->Npad * h->Npad));
+    if (!h->Minv) {
+        CU(h, cudaMalloc(&h->Minv, sizeof(double) * h->Npad * h->Npad));
+        MAKE_MAP(h, &h->mapM, h->Minv, h->Npad, h->Npad, h->Npad);
+    }
     int rc = ensure_wbuf(h);
     if (rc) return rc;
     h->have_kinv = false;
@@ -341,9 +382,9 @@ static int build_minv(gptb_handle* h) {
     for (int s = 1; s < T; s *= 2) {
         int pairs = (T + 2 * s - 1) / (2 * s);
         unsigned grid = (unsigned)((long long)pairs * s * s);
-        trtri_level_p1_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->Lbuf, h->Minv, h->Wbuf, ld, T, s);
+        trtri_level_p1_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->mapM, h->Wbuf, ld, T, s);
         LAUNCH_CHECK(h);
-        trtri_level_p2_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->Minv, h->Wbuf, ld, T, s);
+        trtri_level_p2_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapM, h->mapW, h->Minv, ld, T, s);
         LAUNCH_CHECK(h);
     }
     h->have_minv = true;
@@ -355,7 +396,7 @@ static int build_kinv(gptb_handle* h) {
     int rc = build_minv(h);
     if (rc) return rc;
     const int T = h->T;
-    kinv_kernel<<<(unsigned)((long long)T * (T + 1) / 2), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->Minv, h->Wbuf, h->Npad, T);
+    kinv_kernel<<<(unsigned)((long long)T * (T + 1) / 2), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapM, h->Wbuf, h->Npad, T);
     LAUNCH_CHECK(h);
     h->have_kinv = true;
     return 0;
@@ -420,7 +461,7 @@ extern "C" int gptb_set_affine(gptb_handle* h, const double* R, double s, const 
 template <int D, int P>
 static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_dev, int B, int Bpad, unsigned flags, int nrhs,
                        unsigned genflags, const QueryOut& out, long long q_off, long long Mtot, double* rhs, double* part,
-                       double* macc, double* xr, int nsplit) {
+                       double* macc, double* xr, int nsplit, const CUtensorMap* mapR) {
     const int T = h->T;
     const long long rows_total = (long long)nrhs * Bpad;
     Affine af = h->af;
@@ -433,7 +474,7 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
     if (nrhs > 0) {
         const int rowtiles = (int)(rows_total / TS);
         tic(h, 0);
-        trmm_sumsq_kernel<<<(unsigned)((long long)rowtiles * T), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(rhs, h->Minv, h->Npad, T, rowtiles, rows_total, part);
+        trmm_sumsq_kernel<<<(unsigned)((long long)rowtiles * T), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(*mapR, h->mapM, T, rowtiles, rows_total, part);
         toc(h, 0);
         LAUNCH_CHECK(h);
     }
@@ -443,7 +484,7 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
 }
 
 typedef int (*chunk_fn)(gptb_handle*, const double*, const double*, int, int, unsigned, int, unsigned, const QueryOut&, long long,
-                        long long, double*, double*, double*, double*, int);
+                        long long, double*, double*, double*, double*, int, const CUtensorMap*);
 
 static chunk_fn pick_chunk_fn(int d, int p) {
     static const chunk_fn table[4][4] = {
@@ -522,10 +563,22 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     double* xr = reinterpret_cast<double*>(base + o_xr);
     QueryOut out{mean_dev, std_dev, jac_dev, jacvar_dev, xhat_dev, vhat_dev, vvar_dev, jphi_dev, dvar_dev};
     chunk_fn fn = pick_chunk_fn(d, p);
+    CUtensorMap mapR_full, mapR_tail;
+    int Bpad_mapped = -1;
     for (long long q0 = 0; q0 < M; q0 += Bfirst) {
         int B = (int)((M - q0 < Bfirst) ? (M - q0) : Bfirst);
         int Bpad = (B + TS - 1) / TS * TS;
-        int rc = fn(h, x_dev + q0 * d, vel_dev ? vel_dev + q0 * d : nullptr, B, Bpad, flags, nrhs, genflags, out, q0, M, rhs, part, macc, xr, nsplit);
+        const CUtensorMap* mapR = nullptr;
+        if (nrhs > 0) {
+            // the right-hand-side rows of this batch: (nrhs * Bpad) x Npad, row-major in the workspace
+            CUtensorMap* m = (Bpad == Bfirst) ? &mapR_full : &mapR_tail;
+            if (Bpad != Bpad_mapped) {
+                MAKE_MAP(h, m, rhs, (long long)nrhs * Bpad, h->Npad, h->Npad);
+                Bpad_mapped = Bpad;
+            }
+            mapR = m;
+        }
+        int rc = fn(h, x_dev + q0 * d, vel_dev ? vel_dev + q0 * d : nullptr, B, Bpad, flags, nrhs, genflags, out, q0, M, rhs, part, macc, xr, nsplit, mapR);
         if (rc) return rc;
     }
     return 0;
@@ -638,7 +691,10 @@ extern "C" int gptb_state_alloc(gptb_handle* h, int64_t N, int d, int p, int wit
     if (!h) return -1;
     int rc = alloc_model(h, N, d, p, false);
     if (rc) return rc;
-    if (with_variance && !h->Minv) CU(h, cudaMalloc(&h->Minv, sizeof(double) * h->Npad * h->Npad));
+    if (with_variance && !h->Minv) {
+        CU(h, cudaMalloc(&h->Minv, sizeof(double) * h->Npad * h->Npad));
+        MAKE_MAP(h, &h->mapM, h->Minv, h->Npad, h->Npad, h->Npad);
+    }
     return 0;
 }
 
@@ -676,15 +732,18 @@ extern "C" int gptb_state_commit(gptb_handle* h) {
 // ---------------------------------------------------------------------------------------------------------------
 // unit-test hooks
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS, 1) test_gemm_kernel(const double* A, const double* B, double* C, int nt, int K, int maskA,
-                                                                   int maskB) {
-    extern __shared__ double smem[];
+__global__ void __launch_bounds__(GEMM_THREADS, 1) test_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                   const __grid_constant__ CUtensorMap mapB, double* C, int nt, int K,
+                                                                   int maskA, int maskB) {
+    extern __shared__ __align__(128) double smem[];
+    __shared__ PipeBarriers pipe;
+    pipe_init(&pipe);
     const int tm = blockIdx.x / nt, tn = blockIdx.x % nt;
     double acc[8][4][2];
     acc_clear(acc);
-    Operand a{A + (long long)tm * TS * K, K, maskA, tm};
-    Operand b{B + (long long)tn * TS * K, K, maskB, tn};
-    gemm_nt_tile(a, b, 0, K / TS, acc, smem);
+    Operand a{&mapA, tm * TS, 0, maskA, tm};
+    Operand b{&mapB, tn * TS, 0, maskB, tn};
+    gemm_nt_tile(a, b, 0, K / TS, acc, smem, &pipe);
     double* out = C + (long long)tm * TS * ((long long)nt * TS) + (long long)tn * TS;
     acc_foreach(acc, [&](int r, int c, double v0, double v1) {
         out[(long long)r * nt * TS + c] = v0;
@@ -704,7 +763,10 @@ extern "C" int gptb_test_gemm_nt(gptb_handle* h, const double* A, const double* 
     // stream-ordered copies: the handle's stream is non-blocking, a legacy-stream cudaMemcpy would not order with it
     CU(h, cudaMemcpyAsync(dA, A, sa, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(dB, B, sb, cudaMemcpyHostToDevice, h->stream));
-    test_gemm_kernel<<<mt * nt, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(dA, dB, dC, nt, K, maskA, maskB);
+    CUtensorMap mapA, mapB;
+    MAKE_MAP(h, &mapA, dA, (long long)mt * TS, K, K);
+    MAKE_MAP(h, &mapB, dB, (long long)nt * TS, K, K);
+    test_gemm_kernel<<<mt * nt, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(mapA, mapB, dC, nt, K, maskA, maskB);
     LAUNCH_CHECK(h);
     CU(h, cudaMemcpyAsync(C, dC, sc, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));

@@ -134,17 +134,20 @@ __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ x
 // explicit inverse factor so every flop is a DMMA tile; W is never written to memory.
 // Algorithmic work per 128x128 output tile with ti: 2*128*128*128*(ti+1) flops.  Heaviest tiles are scheduled first.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS, 1) trmm_sumsq_kernel(const double* __restrict__ rhs, const double* __restrict__ Minv,
-                                                                    long long ld, int T, int rowtiles, long long rows_total,
-                                                                    double* __restrict__ part) {
-    extern __shared__ double smem[];
+__global__ void __launch_bounds__(GEMM_THREADS, 1) trmm_sumsq_kernel(const __grid_constant__ CUtensorMap mapR,
+                                                                    const __grid_constant__ CUtensorMap mapM, int T, int rowtiles,
+                                                                    long long rows_total, double* __restrict__ part) {
+    extern __shared__ __align__(128) double smem[];
+    __shared__ PipeBarriers pipe;
+    pipe_init(&pipe);
     const int ti = T - 1 - (int)(blockIdx.x / rowtiles);
     const int rt = (int)(blockIdx.x % rowtiles);
     double acc[8][4][2];
     acc_clear(acc);
-    Operand A{rhs + (long long)rt * TS * ld, ld, MASK_NONE, -1};
-    Operand B{Minv + (long long)ti * TS * ld, ld, MASK_LOWER, ti};
-    gemm_nt_tile(A, B, 0, ti + 1, acc, smem);
+    Operand A{&mapR, rt * TS, 0, MASK_NONE, -1};
+    Operand B{&mapM, ti * TS, 0, MASK_LOWER, ti};
+    gemm_nt_tile(A, B, 0, ti + 1, acc, smem, &pipe);
+    if (!is_consumer()) return;
     // row sums of squares: thread owns rows wm*64+mi*8+g; reduce over its 8 columns, the 4 lanes t, then the 4 wn warps
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3, wm = warp >> 2, wn = warp & 3;
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trmm_sumsq_kernel(const doubl
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         if (t == 0) red[wn * TS + wm * 64 + mi * 8 + g] = s;
     }
-    __syncthreads();
+    consumer_sync();
     if (threadIdx.x < TS) {
         int r = threadIdx.x;
         double s = (red[r] + red[TS + r]) + (red[2 * TS + r] + red[3 * TS + r]);
