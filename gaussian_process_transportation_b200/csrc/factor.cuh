@@ -78,148 +78,212 @@ __global__ void __launch_bounds__(256) gram_lower_kernel(const double* __restric
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Diagonal tile: in-shared-memory blocked Cholesky (16-wide left-looking panels) and triangular inverse.
+// Diagonal tile (128 x 128): Cholesky factor and its explicit inverse, entirely in one CTA's shared memory.
+// This kernel is the serial spine of the blocked factorisation, so it is built for latency:
+//   * 32 x 32 diagonal blocks are factored and inverted by ONE warp in registers (lane i owns row i; pivots,
+//     column scalings and rank-1 updates travel by warp shuffles -- no barriers inside a block);
+//   * everything between blocks (panel solve as a product with the block inverse, trailing update, assembly of the
+//     off-diagonal blocks of the inverse) is a small DMMA product on shared-memory operands by all 8 warps.
 // Writes L (lower) + L^T (upper) back into the factor buffer's diagonal tile and Dinv = L_kk^-1 (dense, zeros above
 // the diagonal) into dinv.  info: first non-positive pivot (1-based global order), LAPACK dpotrf convention.
+// Shared layout: S[128][132] (leading dimension = 4 mod 16 makes both [row][k] and [k][row] DMMA fragment reads
+// conflict-free), Zd[4][32][36] block inverses, Tm[32][132] scratch.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int DLD = TS + 1;
-constexpr int DIAG_SMEM_BYTES = (TS * DLD + TS) * 8;
+constexpr int DLD = TS + 4;          // 132
+constexpr int ZLD = 36;
+constexpr int DB = 32;               // inner block
+constexpr int DIAG_SMEM_BYTES = (TS * DLD + 4 * DB * ZLD + DB * DLD) * 8;   // 205,824 B
 
-__device__ __forceinline__ void chol_tile_smem(double* S, int tid, int nthreads, int gbase, int* info) {
-    // S[r*DLD + c], lower triangle in/out
-    for (int j0 = 0; j0 < TS; j0 += 16) {
-        // (1) left-looking update of panel columns j0..j0+15 (rows j0..127) with columns 0..j0-1
-        if (j0 > 0) {
-            int cnt = (TS - j0) * 16;
-            for (int e = tid; e < cnt; e += nthreads) {
-                int r = j0 + (e >> 4), c = j0 + (e & 15);
-                if (c <= r) {
-                    const double* pr = S + r * DLD;
-                    const double* pc = S + c * DLD;
-                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                    for (int m = 0; m < j0; m += 4) {
-                        s0 = fma(pr[m], pc[m], s0);
-                        s1 = fma(pr[m + 1], pc[m + 1], s1);
-                        s2 = fma(pr[m + 2], pc[m + 2], s2);
-                        s3 = fma(pr[m + 3], pc[m + 3], s3);
-                    }
-                    S[r * DLD + c] -= (s0 + s1) + (s2 + s3);
+// C[M x N] = beta*C + alpha * A * B^T on shared-memory operands, 8 warps.  Element (m,k) of A is A[m*lda+k] (or
+// A[k*lda+m] when A_COL); element (n,k) of B is B[n*ldb+k] (or B[k*ldb+n] when B_COL).  M, N multiples of 8, K of 4.
+// Work unit: 8 rows x up to 32 columns (4 accumulator fragments) per warp.  lower_only skips 8x8 blocks above the diagonal.
+// A warp reads every A fragment of its row strip before it stores, so C may alias A's rows (in-place panel solve).
+template <bool A_COL, bool B_COL>
+__device__ __forceinline__ void smem_gemm(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int N,
+                                          int K, double alpha, double beta, bool lower_only) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int rbs = M >> 3, cgs = (N + 31) >> 5;
+    for (int task = warp; task < rbs * cgs; task += 8) {
+        const int rb = task / cgs, cg = task % cgs;
+        const int r0 = rb * 8, c0 = cg * 32;
+        int nb = min(4, (N - c0) >> 3);
+        if (lower_only) nb = min(nb, rb - cg * 4 + 1);
+        if (nb <= 0) continue;
+        double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+        for (int k0 = 0; k0 < K; k0 += 4) {
+            const double a = A_COL ? A[(k0 + t) * lda + r0 + g] : A[(r0 + g) * lda + k0 + t];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < nb) {
+                    const int n = c0 + j * 8 + g;
+                    const double b = B_COL ? B[(k0 + t) * ldb + n] : B[n * ldb + k0 + t];
+                    dmma884(acc[j][0], acc[j][1], a, b);
                 }
             }
         }
-        __syncthreads();
-        // (2) warp 0 factors the 16x16 diagonal block
-        if (tid < 32) {
-            for (int j = 0; j < 16; ++j) {
-                int jj = j0 + j;
-                double dgl = S[jj * DLD + jj];
-                if (tid == 0) {
-                    if (!(dgl > 0.0)) {
-                        if (atomicCAS(info, 0, gbase + jj + 1) == 0) {}
-                    }
-                }
-                double piv = (dgl > 0.0) ? sqrt(dgl) : 1.0;
-                __syncwarp();
-                if (tid == 0) S[jj * DLD + jj] = piv;
-                if (tid > j && tid < 16) S[(j0 + tid) * DLD + jj] /= piv;
-                __syncwarp();
-                // update remaining lower part of the 16x16 block: pairs (i,c), j < c <= i <= 15
-                for (int e = tid; e < 256; e += 32) {
-                    int i = e >> 4, c = e & 15;
-                    if (c > j && c <= i) S[(j0 + i) * DLD + j0 + c] -= S[(j0 + i) * DLD + jj] * S[(j0 + c) * DLD + jj];
-                }
-                __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < nb) {
+                double* dst = C + (r0 + g) * ldc + c0 + j * 8 + 2 * t;
+                double o0 = alpha * acc[j][0], o1 = alpha * acc[j][1];
+                if (beta != 0.0) { o0 += dst[0]; o1 += dst[1]; }
+                dst[0] = o0;
+                dst[1] = o1;
             }
         }
-        __syncthreads();
-        // (3) rows below the block: X = A * L11^-T, one thread per row
-        {
-            int r = j0 + 16 + tid;
-            if (r < TS) {
-                double x[16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    double s = S[r * DLD + j0 + c];
-#pragma unroll
-                    for (int m = 0; m < 16; ++m)
-                        if (m < c) s = fma(-x[m], S[(j0 + c) * DLD + j0 + m], s);
-                    x[c] = s / S[(j0 + c) * DLD + j0 + c];
-                }
-#pragma unroll
-                for (int c = 0; c < 16; ++c) S[r * DLD + j0 + c] = x[c];
-            }
-        }
-        __syncthreads();
     }
 }
 
-// Z = L^-1 for the lower-triangular L in S (lower part). Z is built transposed in the strict upper part of S:
-// S[c*DLD + r] = Z[r][c] for r > c; zd[r] = Z[r][r].  Thread c (< 128) owns column c.
-__device__ __forceinline__ void trinv_tile_smem(double* S, double* zd, int tid) {
-    if (tid < TS) zd[tid] = 1.0 / S[tid * DLD + tid];
-    __syncthreads();
-    if (tid < TS) {
-        const int c = tid;
-        double* zrow = S + c * DLD;   // Z[k][c] lives at zrow[k] for k > c
-        const double zcc = zd[c];
-        for (int r = 1; r < TS; ++r) {
-            // all threads walk the same (r,k) so the L reads broadcast; threads with c >= r idle
-            if (c < r) {
-                const double* lr = S + r * DLD;
-                double s0 = lr[c] * zcc, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                int k = c + 1;
-                for (; k + 3 < r; k += 4) {
-                    s0 = fma(lr[k], zrow[k], s0);
-                    s1 = fma(lr[k + 1], zrow[k + 1], s1);
-                    s2 = fma(lr[k + 2], zrow[k + 2], s2);
-                    s3 = fma(lr[k + 3], zrow[k + 3], s3);
-                }
-                for (; k < r; ++k) s0 = fma(lr[k], zrow[k], s0);
-                zrow[r] = -((s0 + s1) + (s2 + s3)) * zd[r];
-            }
-            // zrow[r] is only read by the same thread later: no barrier needed
+// One warp: in-register Cholesky of a 32x32 block (lane i holds row i in a[0..31], lower part meaningful) followed by
+// the inverse of the factor.  On return a[] holds row i of L (entries above the diagonal are unspecified), x[] holds
+// COLUMN `lane` of L^-1 (x[r] = Linv[r][lane], zero for r < lane).  Returns the 1-based index of the first
+// non-positive pivot in the block, 0 if none.
+__device__ __forceinline__ int warp_potrf_trtri32(double (&a)[DB], double (&x)[DB], int lane) {
+    const unsigned full = 0xffffffffu;
+    int bad = 0;
+    double rinv_mine = 1.0;
+#pragma unroll
+    for (int j = 0; j < DB; ++j) {
+        const double d = __shfl_sync(full, a[j], j);
+        if (!(d > 0.0) && bad == 0) bad = j + 1;
+        const double piv = (d > 0.0) ? sqrt(d) : 1.0;
+        const double rinv = (d > 0.0) ? rsqrt(d) : 1.0;        // independent of the sqrt: halves the pivot latency
+        if (lane == j) rinv_mine = rinv;
+        const double l = (lane == j) ? piv : a[j] * rinv;     // column j of L (lanes > j); LAPACK dpotf2 scales by 1/ajj too
+        a[j] = l;
+#pragma unroll
+        for (int k = j + 1; k < DB; ++k) {
+            const double lk = __shfl_sync(full, l, k);
+            a[k] = fma(-l, lk, a[k]);                          // rank-1 update (only i >= k is used later)
         }
     }
-    __syncthreads();
+    // inverse: lane c solves L x = e_c by forward substitution; L[r][k] is broadcast from lane r
+#pragma unroll
+    for (int r = 0; r < DB; ++r) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < r; ++k) {
+            const double lrk = __shfl_sync(full, a[k], r);
+            if (k & 1) s1 = fma(lrk, x[k], s1); else s0 = fma(lrk, x[k], s0);
+        }
+        const double ri = __shfl_sync(full, rinv_mine, r);
+        const double rhs = (r == lane) ? 1.0 : 0.0;
+        x[r] = (r < lane) ? 0.0 : (rhs - (s0 + s1)) * ri;
+    }
+    return bad;
 }
 
-__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lbuf, long long ld, int kt, double* __restrict__ dinv,
-                                                         int* info) {
-    extern __shared__ double sm[];
-    double* S = sm;
-    double* zd = sm + TS * DLD;
-    const int tid = threadIdx.x;
+// Forward substitution is fused here: when rhs != nullptr the kernel also emits z_k = L_kk^-1 y_k (y_k = rows of the
+// running right-hand side, already updated by the panels of the previous steps) into sol.
+__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ Lbuf, long long ld, int kt, double* __restrict__ dinv,
+                                                            int* info, const double* __restrict__ rhs, double* __restrict__ sol,
+                                                            int Npad, int p) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double ys[MAXP][TS];
+    if (rhs != nullptr)
+        for (int e = threadIdx.x; e < p * TS; e += 256) ys[e / TS][e % TS] = rhs[(long long)(e / TS) * Npad + kt * TS + (e % TS)];
+    double* S = sm;                         // [128][DLD]
+    double* Zd = sm + TS * DLD;             // [4][32][ZLD]
+    double* Tm = Zd + 4 * DB * ZLD;         // [32][DLD]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* tile = Lbuf + (long long)kt * TS * ld + kt * TS;
-    for (int e = tid; e < TS * TS; e += 256) {
-        int r = e >> 7, c = e & 127;
-        S[r * DLD + c] = tile[(long long)r * ld + c];
+    for (int e = tid; e < TS * TS / 2; e += 256) {
+        int r = e >> 6, c2 = (e & 63) << 1;
+        double2 v = *reinterpret_cast<const double2*>(tile + (long long)r * ld + c2);
+        S[r * DLD + c2] = v.x;
+        S[r * DLD + c2 + 1] = v.y;
     }
     __syncthreads();
-    chol_tile_smem(S, tid, 256, kt * TS, info);
-    // write L (lower) and L^T (upper) back
+    // ---- blocked Cholesky, 32-wide block columns -----------------------------------------------------------------
+    for (int b = 0; b < TS / DB; ++b) {
+        const int j0 = b * DB;
+        if (warp == 0) {
+            double a[DB], x[DB];
+#pragma unroll
+            for (int c = 0; c < DB; ++c) a[c] = S[(j0 + lane) * DLD + j0 + c];
+            const int bad = warp_potrf_trtri32(a, x, lane);
+            if (bad && lane == 0) atomicCAS(info, 0, kt * TS + j0 + bad);
+#pragma unroll
+            for (int c = 0; c < DB; ++c) {
+                if (c <= lane) S[(j0 + lane) * DLD + j0 + c] = a[c];
+                Zd[(b * DB + c) * ZLD + lane] = x[c];          // x[r] = Linv[r][lane] -> row r, column lane
+            }
+        }
+        __syncthreads();
+        const int rem = TS - j0 - DB;
+        if (rem > 0) {
+            // panel: rows below the block times the block inverse (in place)
+            smem_gemm<false, false>(S + (j0 + DB) * DLD + j0, DLD, S + (j0 + DB) * DLD + j0, DLD, Zd + b * DB * ZLD, ZLD, rem, DB, DB,
+                                    1.0, 0.0, false);
+            __syncthreads();
+            // trailing update of the remaining lower triangle
+            smem_gemm<false, false>(S + (j0 + DB) * DLD + j0 + DB, DLD, S + (j0 + DB) * DLD + j0, DLD, S + (j0 + DB) * DLD + j0, DLD,
+                                    rem, rem, DB, -1.0, 1.0, true);
+            __syncthreads();
+        }
+    }
+    // ---- write L (lower) and its mirror (upper) back ---------------------------------------------------------------
     for (int e = tid; e < TS * TS; e += 256) {
         int r = e >> 7, c = e & 127;
-        double v = (c <= r) ? S[r * DLD + c] : S[c * DLD + r];
-        tile[(long long)r * ld + c] = v;
+        tile[(long long)r * ld + c] = (c <= r) ? S[r * DLD + c] : S[c * DLD + r];
     }
     __syncthreads();
-    trinv_tile_smem(S, zd, tid);
+    // ---- inverse: off-diagonal 32-blocks, block row by block row.  (Linv_ij)^T is kept in S's upper block (j,i). ----
+    for (int i = 1; i < TS / DB; ++i) {
+        // Tm[:, 32j..32j+31] = L_ij Linv_jj + sum_{k=j+1}^{i-1} L_ik Linv_kj        for every j < i
+        for (int j = 0; j < i; ++j) {
+            smem_gemm<false, true>(Tm + j * DB, DLD, S + (i * DB) * DLD + j * DB, DLD, Zd + j * DB * ZLD, ZLD, DB, DB, DB, 1.0, 0.0, false);
+        }
+        __syncthreads();
+        for (int j = 0; j + 1 < i; ++j) {
+            smem_gemm<false, false>(Tm + j * DB, DLD, S + (i * DB) * DLD + (j + 1) * DB, DLD, S + (j * DB) * DLD + (j + 1) * DB, DLD, DB, DB,
+                                    (i - j - 1) * DB, 1.0, 1.0, false);
+        }
+        __syncthreads();
+        // (Linv_ij)^T[n][m] = - sum_kk Tm[kk][32j+n] * Linv_ii[m][kk]   for all j < i at once (rows n = 0 .. 32i-1)
+        smem_gemm<true, false>(S + i * DB, DLD, Tm, DLD, Zd + i * DB * ZLD, ZLD, i * DB, DB, DB, -1.0, 0.0, false);
+        __syncthreads();
+    }
     double* dk = dinv + (long long)kt * TS * TS;
     for (int e = tid; e < TS * TS; e += 256) {
         int r = e >> 7, c = e & 127;
-        double v = (c < r) ? S[c * DLD + r] : ((c == r) ? zd[r] : 0.0);
+        int bi = r >> 5, bj = c >> 5;
+        double v = 0.0;
+        if (bi == bj) v = (c <= r) ? Zd[(bi * DB + (r & 31)) * ZLD + (c & 31)] : 0.0;
+        else if (bi > bj) v = S[c * DLD + r];
         dk[r * TS + c] = v;
+    }
+    if (rhs != nullptr && tid < TS) {
+        const int r = tid, bi = r >> 5, rl = r & 31;
+        double z[MAXP] = {0.0, 0.0, 0.0, 0.0};
+        for (int c = 0; c < bi * DB; ++c) {
+            const double v = S[c * DLD + r];
+            for (int q = 0; q < p; ++q) z[q] = fma(v, ys[q][c], z[q]);
+        }
+        for (int cc = 0; cc <= rl; ++cc) {
+            const double v = Zd[(bi * DB + rl) * ZLD + cc];
+            for (int q = 0; q < p; ++q) z[q] = fma(v, ys[q][bi * DB + cc], z[q]);
+        }
+        for (int q = 0; q < p; ++q) sol[(long long)q * Npad + kt * TS + r] = z[q];
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // Panel: L[i,k] = A[i,k] * Dinv_k^T for the row tiles i > k (in place), plus the mirror L[i,k]^T into the upper half.
+// Fused forward substitution: y_i -= L[i,k] z_k with the freshly computed tile still in registers (rhs may be null).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_panel_kernel(const __grid_constant__ CUtensorMap mapL,
                                                                      const __grid_constant__ CUtensorMap mapD,
-                                                                     double* __restrict__ Lbuf, long long ld, int kt) {
+                                                                     double* __restrict__ Lbuf, long long ld, int kt,
+                                                                     double* __restrict__ rhs, const double* __restrict__ sol, int Npad,
+                                                                     int p) {
     extern __shared__ __align__(128) double smem[];
     __shared__ PipeBarriers pipe;
+    __shared__ double zs[MAXP][TS];
+    __shared__ double red[MAXP][4][TS];
+    if (rhs != nullptr)
+        for (int e = threadIdx.x; e < p * TS; e += GEMM_THREADS) zs[e / TS][e % TS] = sol[(long long)(e / TS) * Npad + kt * TS + (e % TS)];
     pipe_init(&pipe);
     const int ti = kt + 1 + blockIdx.x;
     double acc[8][4][2];
@@ -228,6 +292,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_panel_kernel(const __gr
     Operand A{&mapL, ti * TS, kt * TS, MASK_NONE, -1};
     Operand B{&mapD, kt * TS, 0, MASK_NONE, -1};   // Dinv rows n, k <= n (zeros stored above)
     gemm_nt_tile(A, B, 0, 1, acc, smem, &pipe);
+    if (!is_consumer()) return;
     double* out = Lbuf + (long long)ti * TS * ld + (long long)kt * TS;          // lower: rows ti, cols kt
     double* outT = Lbuf + (long long)kt * TS * ld + (long long)ti * TS;         // mirror: rows kt, cols ti
     acc_foreach(acc, [&](int r, int c, double v0, double v1) {
@@ -235,92 +300,154 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_panel_kernel(const __gr
         outT[(long long)c * ld + r] = v0;
         outT[(long long)(c + 1) * ld + r] = v1;
     });
+    if (rhs == nullptr) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3, wm = warp >> 2, wn = warp & 3;
+    for (int q = 0; q < p; ++q) {
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const int c = wn * 32 + ni * 8 + 2 * t;
+                sacc = fma(acc[mi][ni][0], zs[q][c], sacc);
+                sacc = fma(acc[mi][ni][1], zs[q][c + 1], sacc);
+            }
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+            if (t == 0) red[q][wn][wm * 64 + mi * 8 + g] = sacc;
+        }
+    }
+    consumer_sync();
+    if (threadIdx.x < TS) {
+        const int r = threadIdx.x;
+        for (int q = 0; q < p; ++q)
+            rhs[(long long)q * Npad + ti * TS + r] -= (red[q][0][r] + red[q][1][r]) + (red[q][2][r] + red[q][3][r]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Trailing update: A[i,j] -= sum_{kk in [k0,k1)} L[i,kk] L[j,kk]^T for k1 <= j <= i < T (lower tiles), i.e. a rank-(128*(k1-k0))
-// SYRK on the DMMA engine.  blockIdx.x enumerates the lower triangle of the trailing tile grid, heaviest rows first
-// is irrelevant here (all tiles cost the same).
+// Trailing update: A[i,j] -= sum_{kk in [k0,k1)} L[i,kk] L[j,kk]^T (a rank-(128*(k1-k0)) SYRK on the DMMA engine), as a
+// persistent job loop so that the read-modify-write of tile t overlaps the operand stream of tile t+1.
+//   mode 0: the lower triangle of tiles (i,j), base <= j <= i < T          (njobs = r(r+1)/2, r = T - base)
+//   mode 1: the single tile column j = base, rows base <= i < T            (njobs = T - base)   -- the look-ahead column
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_trailing_kernel(const __grid_constant__ CUtensorMap mapL,
                                                                         double* __restrict__ Lbuf, long long ld, int k0, int k1,
-                                                                        int first_tile) {
+                                                                        int base, int mode, int njobs) {
     extern __shared__ __align__(128) double smem[];
     __shared__ PipeBarriers pipe;
     pipe_init(&pipe);
-    int a, b;
-    tri_decode(blockIdx.x, a, b);
-    const int ti = first_tile + a, tj = first_tile + b;
-    double acc[8][4][2];
-    acc_clear(acc);
-    Operand A{&mapL, ti * TS, 0, MASK_NONE, -1};
-    Operand B{&mapL, tj * TS, 0, MASK_NONE, -1};
-    gemm_nt_tile(A, B, k0, k1, acc, smem, &pipe);
-    double* out = Lbuf + (long long)ti * TS * ld + (long long)tj * TS;
-    acc_foreach(acc, [&](int r, int c, double v0, double v1) {
-        double2* p = reinterpret_cast<double2*>(out + (long long)r * ld + c);
-        double2 o = *p;
-        o.x -= v0;
-        o.y -= v1;
-        *p = o;
-    });
+    auto tile_of = [&](int job, int& ti, int& tj) {
+        if (mode == 0) {
+            int a, b;
+            tri_decode(job, a, b);
+            ti = base + a;
+            tj = base + b;
+        } else {
+            ti = base + job;
+            tj = base;
+        }
+    };
+    auto jobfn = [&](int job, Operand& A, Operand& B, int& kb, int& ke) {
+        int ti, tj;
+        tile_of(job, ti, tj);
+        A = Operand{&mapL, ti * TS, 0, MASK_NONE, -1};
+        B = Operand{&mapL, tj * TS, 0, MASK_NONE, -1};
+        kb = k0;
+        ke = k1;
+    };
+    // epilogue: old tile values arrive through the ring (box = this warp's 32 columns as [c/4][row][c%4]); the new
+    // values leave as fire-and-forget global stores, so the DMMA pipe restarts on the next tile without a load stall
+    auto epifn = [&](int job, const Operand& A, const Operand& B, double (&acc)[8][4][2], const double* box) {
+        double* out = Lbuf + (long long)A.row0 * ld + (long long)B.row0;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int g = lane >> 2, t = lane & 3, wm = warp >> 2, wn = warp & 3;
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const int r = wm * 64 + mi * 8 + g;
+                const int kg = ni * 2 + (t >> 1), off = (2 * t) & 3;
+                const double2 old = *reinterpret_cast<const double2*>(box + (((kg * TS) + r) << 2) + off);
+                *reinterpret_cast<double2*>(out + (long long)r * ld + wn * 32 + ni * 8 + 2 * t) =
+                    make_double2(old.x - acc[mi][ni][0], old.y - acc[mi][ni][1]);
+            }
+    };
+    gemm_nt_jobs<true>(blockIdx.x, gridDim.x, njobs, jobfn, epifn, smem, &pipe, &mapL);
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Blocked triangular solve steps for alpha = L^-T L^-1 Y (few right-hand sides, memory-bound).
-// Forward  (transposed = 0), step k: z_k = Dinv_k y_k ; y_i -= L[i,k] z_k for i > k     (rows of the lower half)
-// Backward (transposed = 1), step k: a_k = Dinv_k^T z_k ; z_j -= L[k,j]^T a_k for j < k (rows of the upper mirror)
-// rhs is SoA [p][Npad], updated in place; sol receives the solved block.  CTA b handles one other row tile
-// (plus, for b == 0, publishing the solved block).  Every CTA recomputes the 128x128 block product (L2-resident).
+// Back substitution alpha = L^-T z (the forward half z = L^-1 y is fused into the factorisation above), block by block
+// from the last tile:  step k:  alpha_k = Dinv_k^T z_k
+//                               z_j -= L[k,j]^T alpha_k  for j < k   (one CTA per tile j; reads the 128x128 tile of the
+//                               upper mirror = rows of tile j, columns of tile k, K-contiguous).
+// Few right-hand sides: memory-bound (each step touches k tiles of 128 KB once).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) trsv_step_kernel(const double* __restrict__ Lbuf, long long ld, const double* __restrict__ dinv,
-                                                        double* __restrict__ rhs, double* __restrict__ sol, int Npad, int p, int kt,
-                                                        int transposed) {
-    __shared__ double yk[MAXP][TS];
-    __shared__ double zk[MAXP][TS];
-    const int tid = threadIdx.x;
-    for (int q = 0; q < p; ++q) yk[q][tid] = rhs[(long long)q * Npad + kt * TS + tid];
-    __syncthreads();
+// One launch per step: every CTA first forms alpha_k = Dinv_k^T z_k (redundantly; the 128 KB block is L2-resident and
+// the 256 threads issue all of its loads up front), CTA 0 publishes it, then CTA j applies its tile's update.
+__global__ void __launch_bounds__(256) trsv_back_step_kernel(const double* __restrict__ Lbuf, long long ld, const double* __restrict__ dinv,
+                                                             double* __restrict__ rhs, double* __restrict__ sol, int Npad, int p, int kt) {
+    __shared__ double zs[MAXP][TS];
+    __shared__ double part[8][MAXP][TS];
+    __shared__ double al[MAXP][TS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < p * TS; e += 256) zs[e / TS][e % TS] = rhs[(long long)(e / TS) * Npad + kt * TS + (e % TS)];
     const double* dk = dinv + (long long)kt * TS * TS;
-    double z[MAXP];
-    for (int q = 0; q < MAXP; ++q) z[q] = 0.0;
-    if (!transposed) {
-        // z[r] = sum_{c<=r} Dinv[r][c] y[c]
-        for (int c = 0; c <= tid; ++c) {
-            double dv = dk[tid * TS + c];
-            for (int q = 0; q < p; ++q) z[q] = fma(dv, yk[q][c], z[q]);
-        }
-    } else {
-        // z[c] = sum_{r>=c} Dinv[r][c] y[r]   (coalesced over tid = c)
-        for (int r = tid; r < TS; ++r) {
-            double dv = dk[r * TS + tid];
-            for (int q = 0; q < p; ++q) z[q] = fma(dv, yk[q][r], z[q]);
-        }
+    // alpha[c] = sum_r Dinv[r][c] z[r]: warp w takes rows 16w..16w+15, lane takes columns 4*lane..4*lane+3
+    double2 d0[16], d1[16];
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+        const double* rp = dk + (warp * 16 + rr) * TS + lane * 4;
+        d0[rr] = *reinterpret_cast<const double2*>(rp);
+        d1[rr] = *reinterpret_cast<const double2*>(rp + 2);
     }
-    for (int q = 0; q < p; ++q) zk[q][tid] = z[q];
     __syncthreads();
-    if (blockIdx.x == 0)
-        for (int q = 0; q < p; ++q) sol[(long long)q * Npad + kt * TS + tid] = z[q];
-    // update one other row tile
-    int other;
-    if (!transposed) {
-        other = kt + 1 + blockIdx.x;
-        if (other >= Npad / TS) return;
-    } else {
-        other = kt - 1 - blockIdx.x;
-        if (other < 0) return;
+    for (int q = 0; q < p; ++q) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+            const double zv = zs[q][warp * 16 + rr];
+            a0 = fma(d0[rr].x, zv, a0);
+            a1 = fma(d0[rr].y, zv, a1);
+            a2 = fma(d1[rr].x, zv, a2);
+            a3 = fma(d1[rr].y, zv, a3);
+        }
+        part[warp][q][lane * 4 + 0] = a0;
+        part[warp][q][lane * 4 + 1] = a1;
+        part[warp][q][lane * 4 + 2] = a2;
+        part[warp][q][lane * 4 + 3] = a3;
     }
-    const double* rowp = Lbuf + ((long long)other * TS + tid) * ld + (long long)kt * TS;
-    double s[MAXP];
-    for (int q = 0; q < MAXP; ++q) s[q] = 0.0;
-    for (int c = 0; c < TS; c += 2) {
-        double2 lv = *reinterpret_cast<const double2*>(rowp + c);
+    __syncthreads();
+    for (int e = tid; e < p * TS; e += 256) {
+        const int q = e / TS, c = e % TS;
+        double sacc = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sacc += part[w][q][c];
+        al[q][c] = sacc;
+        if (blockIdx.x == 0) sol[(long long)q * Npad + kt * TS + c] = sacc;
+    }
+    __syncthreads();
+    const int tj = blockIdx.x;                        // tiles above the diagonal block row: j < kt
+    if (tj >= kt) return;
+    double a[MAXP][4];
+    for (int q = 0; q < MAXP; ++q)
+        for (int e = 0; e < 4; ++e) a[q][e] = (q < p) ? al[q][lane * 4 + e] : 0.0;
+    for (int rr = 0; rr < 16; ++rr) {
+        const int r = warp * 16 + rr;
+        const double* rowp = Lbuf + ((long long)tj * TS + r) * ld + (long long)kt * TS + lane * 4;   // mirror: L[k,j]^T rows
+        const double2 u0 = *reinterpret_cast<const double2*>(rowp);
+        const double2 u1 = *reinterpret_cast<const double2*>(rowp + 2);
         for (int q = 0; q < p; ++q) {
-            s[q] = fma(lv.x, zk[q][c], s[q]);
-            s[q] = fma(lv.y, zk[q][c + 1], s[q]);
+            double sacc = u0.x * a[q][0];
+            sacc = fma(u0.y, a[q][1], sacc);
+            sacc = fma(u1.x, a[q][2], sacc);
+            sacc = fma(u1.y, a[q][3], sacc);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
+            if (lane == 0) rhs[(long long)q * Npad + tj * TS + r] -= sacc;
         }
     }
-    for (int q = 0; q < p; ++q) rhs[(long long)q * Npad + other * TS + tid] -= s[q];
 }
 
 // ------------------------------------------------------------------------------------------------------------

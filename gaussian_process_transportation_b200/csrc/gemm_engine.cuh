@@ -93,10 +93,138 @@ __device__ __forceinline__ void pipe_init(PipeBarriers* pb) {
     __syncthreads();
 }
 
-// acc[mi][ni][0..1] <-> C[wm*64 + mi*8 + g][wn*32 + ni*8 + 2t + {0,1}],  g = lane>>2, t = lane&3,
-// wm = warp>>2, wn = warp&3 (consumer warps 0..7).  Accumulates (does not clear) into acc.  kt range is in 128-wide
-// k-tiles.  Must be called by all GEMM_THREADS threads, at most once per kernel (barrier phases start at 0).
-// On return the consumer warps have passed a consumer_sync(): shared memory may be reused by the epilogue.
+// One k-slab of DMMA work for a consumer warp.  s = absolute slab index (k = s*BK).
+__device__ __forceinline__ void consume_slab(const Operand& A, const Operand& B, const double* sA, const double* sB, int s,
+                                             double (&acc)[8][4][2], int wm, int wn, int g, int t) {
+    const int kt = s / SLABS_PER_TILE, sl = s % SLABS_PER_TILE;
+    const bool mA = (A.mask != MASK_NONE) && (kt == A.diag_kt);
+    const bool mB = (B.mask != MASK_NONE) && (kt == B.diag_kt);
+    const double* pa = sA + ((wm * 64 + g) << 2) + t;
+    const double* pbf = sB + ((wn * 32 + g) << 2) + t;
+#pragma unroll
+    for (int kg = 0; kg < BK / 4; ++kg) {
+        double a[8], b[4];
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) a[mi] = pa[(kg * TS + mi * 8) << 2];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = pbf[(kg * TS + ni * 8) << 2];
+        if (mA | mB) {          // block-uniform branch: only on slabs that cross a diagonal tile
+            const int kl = sl * BK + kg * 4 + t;
+            if (mA) {
+#pragma unroll
+                for (int mi = 0; mi < 8; ++mi) {
+                    int r = wm * 64 + mi * 8 + g;
+                    bool keep = (A.mask == MASK_LOWER) ? (kl <= r) : (kl >= r);
+                    a[mi] = keep ? a[mi] : 0.0;
+                }
+            }
+            if (mB) {
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    int r = wn * 32 + ni * 8 + g;
+                    bool keep = (B.mask == MASK_LOWER) ? (kl <= r) : (kl >= r);
+                    b[ni] = keep ? b[ni] : 0.0;
+                }
+            }
+        }
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+}
+
+__device__ __forceinline__ void acc_clear(double (&acc)[8][4][2]) {
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+}
+
+// Persistent job loop: this CTA runs jobs job0, job0+stride, ... < njobs.  jobfn(job, A, B, kt_begin, kt_end) describes a
+// 128x128 output tile; epifn(job, A, B, acc) is called by the consumer threads with the finished accumulators
+// (acc[mi][ni][0..1] <-> C[wm*64 + mi*8 + g][wn*32 + ni*8 + 2t + {0,1}], g = lane>>2, t = lane&3, wm = warp>>2,
+// wn = warp&3).  The producer warp keeps streaming the next jobs' slabs through the ring while the consumers run
+// their epilogue, so per-tile prologue/epilogue latency is hidden.  Must be called by all GEMM_THREADS threads, once.
+//
+// CPREF = true additionally streams the job's 128x128 OUTPUT tile (rows A.row0, columns B.row0.. of the matrix behind
+// cmap) through the same ring as two extra entries right behind the job's operand slabs, so a read-modify-write
+// epilogue finds the old values in shared memory instead of stalling on global loads.  Entry e holds columns
+// [64e, 64e+64) as two operand-style boxes of 32 columns ([c/4][row][c%4]); consumer warp (wm, wn) owns box wn and is
+// handed its box pointer: epifn(job, A, B, acc, box).
+template <bool CPREF, typename JobFn, typename EpiFn>
+__device__ __forceinline__ void gemm_nt_jobs(int job0, int stride, int njobs, JobFn jobfn, EpiFn epifn, double* smem,
+                                             PipeBarriers* pb, const CUtensorMap* cmap = nullptr) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    int gs = 0;   // slabs issued / consumed so far by this CTA (identical sequence on both sides)
+    if (warp == CONSUMER_THREADS / 32) {
+        // ---------------- TMA producer: one elected lane ----------------
+        if (lane == 0) {
+            for (int job = job0; job < njobs; job += stride) {
+                Operand A, B;
+                int kb, ke;
+                jobfn(job, A, B, kb, ke);
+                const int nslab = (ke - kb) * SLABS_PER_TILE, s0 = kb * SLABS_PER_TILE;
+                for (int it = 0; it < nslab; ++it, ++gs) {
+                    const int st = gs % NSTAGE;
+                    if (gs >= NSTAGE) mbar_wait(&pb->empty[st], ((gs / NSTAGE) - 1) & 1);
+                    double* sA = smem + st * 2 * SLAB_DOUBLES;
+                    double* sB = sA + SLAB_DOUBLES;
+                    const int kel = (s0 + it) * BK;
+                    mbar_expect_tx(&pb->full[st], 2 * SLAB_DOUBLES * 8);
+                    tma_load_3d(sA, A.map, 0, A.row0, (A.k0 + kel) >> 2, &pb->full[st]);
+                    tma_load_3d(sB, B.map, 0, B.row0, (B.k0 + kel) >> 2, &pb->full[st]);
+                }
+                if constexpr (CPREF) {
+                    for (int e = 0; e < 2; ++e, ++gs) {
+                        const int st = gs % NSTAGE;
+                        if (gs >= NSTAGE) mbar_wait(&pb->empty[st], ((gs / NSTAGE) - 1) & 1);
+                        double* sA = smem + st * 2 * SLAB_DOUBLES;
+                        mbar_expect_tx(&pb->full[st], 2 * SLAB_DOUBLES * 8);
+                        tma_load_3d(sA, cmap, 0, A.row0, (B.row0 + 64 * e) >> 2, &pb->full[st]);
+                        tma_load_3d(sA + SLAB_DOUBLES, cmap, 0, A.row0, (B.row0 + 64 * e + 32) >> 2, &pb->full[st]);
+                    }
+                }
+            }
+        }
+        return;
+    }
+    // ---------------- consumers: LDS + DMMA ----------------
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    for (int job = job0; job < njobs; job += stride) {
+        Operand A, B;
+        int kb, ke;
+        jobfn(job, A, B, kb, ke);
+        const int nslab = (ke - kb) * SLABS_PER_TILE, s0 = kb * SLABS_PER_TILE;
+        double acc[8][4][2];
+        acc_clear(acc);
+        for (int it = 0; it < nslab; ++it, ++gs) {
+            const int st = gs % NSTAGE;
+            mbar_wait(&pb->full[st], (gs / NSTAGE) & 1);
+            const double* sA = smem + st * 2 * SLAB_DOUBLES;
+            consume_slab(A, B, sA, sA + SLAB_DOUBLES, s0 + it, acc, wm, wn, g, t);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pb->empty[st]);      // this warp is done reading stage st
+        }
+        if constexpr (CPREF) {
+            for (int e = 0; e < 2; ++e, ++gs) {
+                const int st = gs % NSTAGE;
+                mbar_wait(&pb->full[st], (gs / NSTAGE) & 1);
+                if ((wn >> 1) == e) epifn(job, A, B, acc, smem + st * 2 * SLAB_DOUBLES + (wn & 1) * SLAB_DOUBLES);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&pb->empty[st]);
+            }
+        } else {
+            epifn(job, A, B, acc, (const double*)nullptr);
+        }
+    }
+}
+
+// Single-tile form: accumulates (does not clear) into acc.  kt range is in 128-wide k-tiles.  Must be called by all
+// GEMM_THREADS threads, at most once per kernel (barrier phases start at 0).  On return the consumer warps have passed a
+// consumer_sync(): shared memory may be reused by the epilogue.
 __device__ __forceinline__ void gemm_nt_tile(const Operand& A, const Operand& B, int kt_begin, int kt_end,
                                              double (&acc)[8][4][2], double* smem, PipeBarriers* pb) {
     const int tid = threadIdx.x;
@@ -104,9 +232,7 @@ __device__ __forceinline__ void gemm_nt_tile(const Operand& A, const Operand& B,
     const int nslab = (kt_end - kt_begin) * SLABS_PER_TILE;
     const int s0 = kt_begin * SLABS_PER_TILE;
     if (nslab <= 0) return;
-
     if (warp == CONSUMER_THREADS / 32) {
-        // ---------------- TMA producer: one elected lane ----------------
         if (lane == 0) {
             for (int it = 0; it < nslab; ++it) {
                 const int st = it % NSTAGE;
@@ -121,65 +247,20 @@ __device__ __forceinline__ void gemm_nt_tile(const Operand& A, const Operand& B,
         }
         return;
     }
-    // ---------------- consumers: LDS + DMMA ----------------
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp >> 2, wn = warp & 3;
     for (int it = 0; it < nslab; ++it) {
         const int st = it % NSTAGE;
         mbar_wait(&pb->full[st], (it / NSTAGE) & 1);
         const double* sA = smem + st * 2 * SLAB_DOUBLES;
-        const double* sB = sA + SLAB_DOUBLES;
-        const int s = s0 + it;
-        const int kt = s / SLABS_PER_TILE, sl = s % SLABS_PER_TILE;
-        const bool mA = (A.mask != MASK_NONE) && (kt == A.diag_kt);
-        const bool mB = (B.mask != MASK_NONE) && (kt == B.diag_kt);
-        const double* pa = sA + ((wm * 64 + g) << 2) + t;
-        const double* pbf = sB + ((wn * 32 + g) << 2) + t;
-#pragma unroll
-        for (int kg = 0; kg < BK / 4; ++kg) {
-            double a[8], b[4];
-#pragma unroll
-            for (int mi = 0; mi < 8; ++mi) a[mi] = pa[(kg * TS + mi * 8) << 2];
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = pbf[(kg * TS + ni * 8) << 2];
-            if (mA | mB) {          // block-uniform branch: only on slabs that cross a diagonal tile
-                const int kl = sl * BK + kg * 4 + t;
-                if (mA) {
-#pragma unroll
-                    for (int mi = 0; mi < 8; ++mi) {
-                        int r = wm * 64 + mi * 8 + g;
-                        bool keep = (A.mask == MASK_LOWER) ? (kl <= r) : (kl >= r);
-                        a[mi] = keep ? a[mi] : 0.0;
-                    }
-                }
-                if (mB) {
-#pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) {
-                        int r = wn * 32 + ni * 8 + g;
-                        bool keep = (B.mask == MASK_LOWER) ? (kl <= r) : (kl >= r);
-                        b[ni] = keep ? b[ni] : 0.0;
-                    }
-                }
-            }
-#pragma unroll
-            for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-        }
+        consume_slab(A, B, sA, sA + SLAB_DOUBLES, s0 + it, acc, wm, wn, g, t);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&pb->empty[st]);      // this warp is done reading stage st
+        if (lane == 0) mbar_arrive(&pb->empty[st]);
     }
     consumer_sync();
 }
 
 __device__ __forceinline__ bool is_consumer() { return threadIdx.x < CONSUMER_THREADS; }
-
-__device__ __forceinline__ void acc_clear(double (&acc)[8][4][2]) {
-#pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
-}
 
 // visit every accumulator pair: f(row, col, v0 /*col*/, v1 /*col+1*/) with row/col local to the 128x128 tile
 template <typename F>

@@ -48,6 +48,8 @@ bool make_operand_map(CUtensorMap* m, const double* base, long long rows, long l
 struct gptb_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux = nullptr;               // high-priority stream for the look-ahead diagonal tile
+    std::vector<cudaEvent_t> ev_diag, ev_col; // per-step dependencies between the two streams
     std::string err;
     long long N = 0, Npad = 0;
     int T = 0, d = 0, p = 0;
@@ -141,7 +143,10 @@ extern "C" int gptb_create(int device, gptb_handle** out) {
     gptb_handle* h = new gptb_handle();
     h->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return -2; }
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return -2; }
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete h; return -2; }
+    if (cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete h; return -2; }
     if (cudaMalloc(&h->info, sizeof(int)) != cudaSuccess || cudaMalloc(&h->scal, 64 * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->header, 32 * sizeof(double)) != cudaSuccess) {
         delete h;
@@ -169,6 +174,9 @@ extern "C" void gptb_destroy(gptb_handle* h) {
     cudaFree(h->header);
     for (auto& v : h->ev)
         for (auto& e : v) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto e : h->ev_diag) cudaEventDestroy(e);
+    for (auto e : h->ev_col) cudaEventDestroy(e);
+    cudaStreamDestroy(h->aux);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -276,11 +284,26 @@ static int launch_scale(gptb_handle* h) {
     return 0;
 }
 
-// Gram + blocked right-looking Cholesky.  Returns LAPACK-style info through the handle's device flag.
+// Gram + blocked right-looking Cholesky with one step of look-ahead, forward substitution fused in.
+//   main stream : panel(k) -> trailing column k+1 -> [event] -> rest of trailing(k)            (wide kernels)
+//   aux  stream : [wait column event] -> diagonal tile k+1 (factor + inverse + z_{k+1}) -> [event]   (one CTA)
+// so the serial diagonal-tile kernel runs underneath the bulk of the previous trailing update.  The persistent
+// trailing kernel is launched on at most (#SM - 1) CTAs to keep one SM free for that diagonal-tile CTA.
 static int factorize_device(gptb_handle* h) {
     const int T = h->T;
     const long long ld = h->Npad;
+    const int Npad = (int)h->Npad, p = h->p;
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+    while ((int)h->ev_diag.size() < T + 1) {
+        cudaEvent_t a, b;
+        CU(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->ev_diag.push_back(a);
+        h->ev_col.push_back(b);
+    }
     CU(h, cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
+    CU(h, cudaMemcpyAsync(h->tmp1, h->Y, sizeof(double) * p * h->Npad, cudaMemcpyDeviceToDevice, h->stream));
     int rc = launch_scale(h);
     if (rc) return rc;
     const unsigned ntri = (unsigned)((long long)T * (T + 1) / 2);
@@ -288,15 +311,31 @@ static int factorize_device(gptb_handle* h) {
         gram_lower_kernel<decltype(D)::value><<<ntri, 256, 0, h->stream>>>(h->Xs, h->Lbuf, (int)h->N, (int)h->Npad, h->kp);
     });
     LAUNCH_CHECK(h);
+    CU(h, cudaEventRecord(h->ev_col[T], h->stream));                 // "column 0 is ready"
+    CU(h, cudaStreamWaitEvent(h->aux, h->ev_col[T], 0));
+    potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->aux>>>(h->Lbuf, ld, 0, h->Dinv, h->info, h->tmp1, h->tmp2, Npad, p);
+    LAUNCH_CHECK(h);
+    CU(h, cudaEventRecord(h->ev_diag[0], h->aux));
     for (int kt = 0; kt < T; ++kt) {
-        potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->stream>>>(h->Lbuf, ld, kt, h->Dinv, h->info);
-        LAUNCH_CHECK(h);
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_diag[kt], 0));
         const int r = T - kt - 1;
-        if (r > 0) {
-            potrf_panel_kernel<<<r, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->mapD, h->Lbuf, ld, kt);
-            LAUNCH_CHECK(h);
+        if (r <= 0) break;
+        potrf_panel_kernel<<<r, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->mapD, h->Lbuf, ld, kt, h->tmp1, h->tmp2, Npad, p);
+        LAUNCH_CHECK(h);
+        // look-ahead column: tiles (i, kt+1), i >= kt+1
+        potrf_trailing_kernel<<<r, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->Lbuf, ld, kt, kt + 1, kt + 1, 1, r);
+        LAUNCH_CHECK(h);
+        CU(h, cudaEventRecord(h->ev_col[kt], h->stream));
+        CU(h, cudaStreamWaitEvent(h->aux, h->ev_col[kt], 0));
+        potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->aux>>>(h->Lbuf, ld, kt + 1, h->Dinv, h->info, h->tmp1, h->tmp2, Npad, p);
+        LAUNCH_CHECK(h);
+        CU(h, cudaEventRecord(h->ev_diag[kt + 1], h->aux));
+        if (r > 1) {
+            const int r2 = r - 1;
+            const int njobs = r2 * (r2 + 1) / 2;
+            const int grid = njobs < nsm - 1 ? njobs : nsm - 1;
             tic(h, 2);
-            potrf_trailing_kernel<<<(unsigned)((long long)r * (r + 1) / 2), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->Lbuf, ld, kt, kt + 1, kt + 1);
+            potrf_trailing_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->Lbuf, ld, kt, kt + 1, kt + 2, 0, njobs);
             toc(h, 2);
             LAUNCH_CHECK(h);
         }
@@ -311,19 +350,12 @@ static int factorize_device(gptb_handle* h) {
     return 0;
 }
 
+// alpha = L^-T z, z = L^-1 Y already produced block by block inside factorize_device (tmp2).
 static int solve_alpha(gptb_handle* h) {
     const int T = h->T;
     const long long ld = h->Npad;
-    const size_t bytes = sizeof(double) * h->p * h->Npad;
-    CU(h, cudaMemcpyAsync(h->tmp1, h->Y, bytes, cudaMemcpyDeviceToDevice, h->stream));
-    for (int kt = 0; kt < T; ++kt) {
-        int grid = T - kt - 1 > 0 ? T - kt - 1 : 1;
-        trsv_step_kernel<<<grid, 128, 0, h->stream>>>(h->Lbuf, ld, h->Dinv, h->tmp1, h->tmp2, (int)h->Npad, h->p, kt, 0);
-        LAUNCH_CHECK(h);
-    }
     for (int kt = T - 1; kt >= 0; --kt) {
-        int grid = kt > 0 ? kt : 1;
-        trsv_step_kernel<<<grid, 128, 0, h->stream>>>(h->Lbuf, ld, h->Dinv, h->tmp2, h->alpha, (int)h->Npad, h->p, kt, 1);
+        trsv_back_step_kernel<<<kt > 0 ? kt : 1, 256, 0, h->stream>>>(h->Lbuf, ld, h->Dinv, h->tmp2, h->alpha, (int)h->Npad, h->p, kt);
         LAUNCH_CHECK(h);
     }
     return 0;
@@ -782,7 +814,7 @@ extern "C" int gptb_test_potrf_tile(gptb_handle* h, const double* A128, double* 
     CU(h, cudaMalloc(&dI, sizeof(double) * TS * TS));
     CU(h, cudaMemcpyAsync(dA, A128, sizeof(double) * TS * TS, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
-    potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->stream>>>(dA, TS, 0, dI, h->info);
+    potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->stream>>>(dA, TS, 0, dI, h->info, nullptr, nullptr, TS, 0);
     LAUNCH_CHECK(h);
     CU(h, cudaMemcpyAsync(L128, dA, sizeof(double) * TS * TS, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(Linv128, dI, sizeof(double) * TS * TS, cudaMemcpyDeviceToHost, h->stream));
