@@ -241,6 +241,9 @@ def main():
     else:
         aff_pack = np.zeros(d * d + 1 + 2 * d)
     if world > 1:
+        warm = torch.zeros(1, device=dev)
+        dist.all_reduce(warm)                       # NCCL communicator set-up is not part of the model broadcast
+        torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         broadcast_model(eng, src=0)
         ap_t = torch.from_numpy(aff_pack).to(dev)
@@ -330,8 +333,16 @@ def main():
         flops_per_launch = q_per_launch * Npad * (Npad + 128.0)
         avg_launch_ms = trmm_ms / max(trmm_n, 1)
         achieved = flops_per_launch / (avg_launch_ms * 1e-3) * 1e-12
+        traffic = None
+        try:   # DRAM bytes per launch from the committed ncu capture, only when it is the same launch shape
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_trmm_traffic.json")))
+            if tr["N"] == N and abs(tr["queries_per_launch"] - q_per_launch) < 1:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": "trmm_sumsq_kernel (FP64 DMMA mma.sync.m8n8k4)", "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                    "algorithmic_flops_per_launch": flops_per_launch, "launch_ms": avg_launch_ms,
                     "peak_source": "cuBLAS FP64 GEMM 6144^3 measured live in this run (MEASURED_PEAKS.json has no FP64 entry); "
                                    "DMMA/DFMA pipe peak 37.0 TFLOP/s (profiles/r01_fp64_peaks.json)",
                     "algorithmic_flops_per_query": Npad * (Npad + 128.0), "share_of_step": trmm_ms / ms_total,

@@ -27,6 +27,7 @@ SYMBOLS = {
     "gptb_set_affine": (C.c_int, [C.c_void_p, _dp, C.c_double, _dp, _dp]),
     "gptb_query": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_uint32, _dp] + [_dp] * 9),
     "gptb_query_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p] + [C.c_void_p] * 9),
+    "gptb_query_cov": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp, _dp]),
     "gptb_export_L": (C.c_int, [C.c_void_p, _dp]),
     "gptb_export_alpha": (C.c_int, [C.c_void_p, _dp]),
     "gptb_export_Kinv": (C.c_int, [C.c_void_p, _dp]),
@@ -182,6 +183,17 @@ class Engine:
                                  ptr(g("xhat")), ptr(g("vhat")), ptr(g("vvar")), ptr(g("jphi")), ptr(g("dvar")))
         self._check(rc, "gptb_query")
         return o
+
+    def query_cov(self, x):
+        """Posterior mean (M,p) and joint covariance (M,M) on the device (k(x,x) + s2 I - K* K^-1 K*^T)."""
+        x = as_f64(x)
+        if x.ndim != 2 or x.shape[1] != self.d:
+            raise ValueError(f"query points must have shape (M, {self.d}), got {x.shape}")
+        M = x.shape[0]
+        mean, cov = np.empty((M, self.p)), np.empty((M, M))
+        if M:
+            self._check(self.lib.gptb_query_cov(self.h, ptr(x), M, ptr(mean), ptr(cov)), "gptb_query_cov")
+        return mean, cov
 
     def query_dev(self, x_ptr, M, flags, vel_ptr=0, mean=0, std=0, jac=0, jacvar=0, xhat=0, vhat=0, vvar=0, jphi=0, dvar=0):
         rc = self.lib.gptb_query_dev(self.h, x_ptr, M, int(flags), vel_ptr or None, mean or None, std or None, jac or None, jacvar or None,

@@ -129,6 +129,11 @@ static int set_kernel_attrs(gptb_handle* h) {
     CU(h, cudaFuncSetAttribute(trtri_level_p2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(kinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(trmm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(trmm_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(cov_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(cov_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(cov_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(cov_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     return 0;
 }
 
@@ -662,6 +667,85 @@ extern "C" int gptb_query(gptb_handle* h, const double* x, int64_t M, uint32_t f
     for (int i = 2; i < 11; ++i)
         if (segs[i].hout) CU(h, cudaMemcpyAsync(segs[i].hout, dp(i), segs[i].per * M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// joint covariance
+// ---------------------------------------------------------------------------------------------------------------
+template <int D, int P>
+static int cov_generate(gptb_handle* h, const double* x_dev, int M, int Mpad, double* rhs, double* xr, double* macc, double* mean_dev) {
+    Affine af = h->af;
+    af.on = 0;
+    dim3 grid(Mpad / QPB, 1);
+    kstar_kernel<D, P><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, M, Mpad, h->kp, af, 1u, rhs, xr, macc, 1);
+    LAUNCH_CHECK(h);
+    QueryOut out{mean_dev, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    finalize_kernel<D, P><<<(M + 127) / 128, 128, 0, h->stream>>>(macc, 1, nullptr, h->T, M, Mpad, Mpad, xr, nullptr, h->kp, h->af, GPTB_MEAN, out, 0, M);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+typedef int (*covgen_fn)(gptb_handle*, const double*, int, int, double*, double*, double*, double*);
+static covgen_fn pick_covgen(int d, int p) {
+    static const covgen_fn table[4][4] = {
+        {cov_generate<1, 1>, cov_generate<1, 2>, cov_generate<1, 3>, cov_generate<1, 4>},
+        {cov_generate<2, 1>, cov_generate<2, 2>, cov_generate<2, 3>, cov_generate<2, 4>},
+        {cov_generate<3, 1>, cov_generate<3, 2>, cov_generate<3, 3>, cov_generate<3, 4>},
+        {cov_generate<4, 1>, cov_generate<4, 2>, cov_generate<4, 3>, cov_generate<4, 4>}};
+    return table[d - 1][p - 1];
+}
+
+extern "C" int gptb_query_cov(gptb_handle* h, const double* x, int64_t M, double* mean, double* cov) {
+    if (!h || M < 0) return -1;
+    if (M == 0) return 0;
+    if (!x || !mean || !cov) return -1;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->have_alpha) GPTB_FAIL(h, -1, "gptb_query_cov: model is not fitted");
+    if (M > 32768) GPTB_FAIL(h, -1, "gptb_query_cov: M=%lld exceeds the 32768-point limit of the joint covariance", (long long)M);
+    int rc = build_minv(h);
+    if (rc) return rc;
+    const int d = h->d, p = h->p, T = h->T;
+    const int Mpad = (int)((M + TS - 1) / TS * TS);
+    const long long Npad = h->Npad;
+    double *xd = nullptr, *rhs = nullptr, *W = nullptr, *xr = nullptr, *macc = nullptr, *mean_d = nullptr, *cov_d = nullptr;
+    auto cleanup = [&]() {
+        for (double* q : {xd, rhs, W, xr, macc, mean_d, cov_d})
+            if (q) cudaFree(q);
+    };
+#define CUX(call)                                                                                           \
+    do {                                                                                                    \
+        cudaError_t _e = (call);                                                                            \
+        if (_e != cudaSuccess) { cleanup(); GPTB_FAIL(h, -2, "CUDA error %s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); } \
+    } while (0)
+    CUX(cudaMalloc(&xd, sizeof(double) * M * d));
+    CUX(cudaMalloc(&rhs, sizeof(double) * Mpad * Npad));
+    CUX(cudaMalloc(&W, sizeof(double) * Mpad * Npad));
+    CUX(cudaMalloc(&xr, sizeof(double) * Mpad * d));
+    CUX(cudaMalloc(&macc, sizeof(double) * Mpad * (p + p * d)));
+    CUX(cudaMalloc(&mean_d, sizeof(double) * M * p));
+    CUX(cudaMalloc(&cov_d, sizeof(double) * M * M));
+    CUX(cudaMemcpyAsync(xd, x, sizeof(double) * M * d, cudaMemcpyHostToDevice, h->stream));
+    rc = pick_covgen(d, p)(h, xd, (int)M, Mpad, rhs, xr, macc, mean_d);
+    if (rc) { cleanup(); return rc; }
+    CUtensorMap mapR, mapW;
+    if (!make_operand_map(&mapR, rhs, Mpad, Npad, Npad) || !make_operand_map(&mapW, W, Mpad, Npad, Npad)) {
+        cleanup();
+        GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed");
+    }
+    const int mt = Mpad / TS;
+    trmm_store_kernel<<<(unsigned)(mt * T), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(mapR, h->mapM, T, mt, W, Npad);
+    h->launches++;
+    dispatch_d(d, [&](auto D) {
+        cov_kernel<decltype(D)::value><<<(unsigned)(mt * mt), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(mapW, T, mt, xr, h->kp, (int)M, cov_d);
+    });
+    h->launches++;
+    CUX(cudaGetLastError());
+    CUX(cudaMemcpyAsync(mean, mean_d, sizeof(double) * M * p, cudaMemcpyDeviceToHost, h->stream));
+    CUX(cudaMemcpyAsync(cov, cov_d, sizeof(double) * M * M, cudaMemcpyDeviceToHost, h->stream));
+    CUX(cudaStreamSynchronize(h->stream));
+#undef CUX
+    cleanup();
     return 0;
 }
 

@@ -15,6 +15,8 @@ struct Affine {
 
 constexpr int QPW = 4;          // queries per warp
 constexpr int QPB = 32;         // queries per CTA (8 warps)
+constexpr int TRMM_GR = 12;     // L2 blocking of the variance triangular multiply: row tiles per group
+constexpr int TRMM_GI = 12;     //                                                   inverse-factor row tiles per group
 
 // ------------------------------------------------------------------------------------------------------------
 // Generator: for a batch of queries, regenerate k(x*, X) on the fly (never read from HBM), reduce it against alpha
@@ -140,8 +142,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trmm_sumsq_kernel(const __gri
     extern __shared__ __align__(128) double smem[];
     __shared__ PipeBarriers pipe;
     pipe_init(&pipe);
-    const int ti = T - 1 - (int)(blockIdx.x / rowtiles);
-    const int rt = (int)(blockIdx.x % rowtiles);
+    // Tile order = L2 blocking: CTAs that run concurrently (consecutive blockIdx) form groups of TRMM_GR row tiles x
+    // TRMM_GI inverse-factor row tiles, so every operand slab fetched from HBM is reused ~12x out of L2 instead of
+    // being re-read per tile (35.7 GB -> a few GB per launch at N=4096, profiles/r01_trmm_*).  ti-blocks run from the
+    // heaviest (longest k-range) to the lightest.
+    int ti, rt;
+    {
+        const long long idx = blockIdx.x;
+        const long long per_tib = (long long)rowtiles * TRMM_GI;
+        const int tib = (int)(idx / per_tib);
+        const long long rem = idx - (long long)tib * per_tib;
+        const int ti_cnt = min(TRMM_GI, T - tib * TRMM_GI);
+        const int rb = (int)(rem / ((long long)TRMM_GR * ti_cnt));
+        const int rem2 = (int)(rem - (long long)rb * TRMM_GR * ti_cnt);
+        rt = rb * TRMM_GR + rem2 / ti_cnt;
+        ti = T - 1 - (tib * TRMM_GI + rem2 % ti_cnt);
+    }
     double acc[8][4][2];
     acc_clear(acc);
     Operand A{&mapR, rt * TS, 0, MASK_NONE, -1};
@@ -170,6 +186,72 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trmm_sumsq_kernel(const __gri
         double s = (red[r] + red[TS + r]) + (red[2 * TS + r] + red[3 * TS + r]);
         part[(long long)ti * rows_total + (long long)rt * TS + r] = s;
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Joint posterior covariance (GaussianProcess.predict(return_cov=True) / samples(); gaussian_process.py:50-60,
+// sklearn:_gpr.py:470-475): W = RHS * Linv^T is materialised once (same tile engine, store epilogue), then
+//   cov[a][b] = k(x_a, x_b) + s2*[a==b] - sum_k W[a][k] W[b][k].
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 1) trmm_store_kernel(const __grid_constant__ CUtensorMap mapR,
+                                                                    const __grid_constant__ CUtensorMap mapM, int T, int rowtiles,
+                                                                    double* __restrict__ W, long long ld) {
+    extern __shared__ __align__(128) double smem[];
+    __shared__ PipeBarriers pipe;
+    pipe_init(&pipe);
+    const int ti = T - 1 - (int)(blockIdx.x / rowtiles);
+    const int rt = (int)(blockIdx.x % rowtiles);
+    double acc[8][4][2];
+    acc_clear(acc);
+    Operand A{&mapR, rt * TS, 0, MASK_NONE, -1};
+    Operand B{&mapM, ti * TS, 0, MASK_LOWER, ti};
+    gemm_nt_tile(A, B, 0, ti + 1, acc, smem, &pipe);
+    double* out = W + (long long)rt * TS * ld + (long long)ti * TS;
+    acc_foreach(acc, [&](int r, int c, double v0, double v1) {
+        *reinterpret_cast<double2*>(out + (long long)r * ld + c) = make_double2(v0, v1);
+    });
+}
+
+template <int D>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) cov_kernel(const __grid_constant__ CUtensorMap mapW, int T, int mtiles,
+                                                             const double* __restrict__ xr, KParams kp, int M,
+                                                             double* __restrict__ cov) {
+    extern __shared__ __align__(128) double smem[];
+    __shared__ PipeBarriers pipe;
+    __shared__ double xa[D][TS], xb[D][TS];
+    const int ta = blockIdx.x / mtiles, tb = blockIdx.x % mtiles;
+    for (int e = threadIdx.x; e < D * TS; e += GEMM_THREADS) {
+        const int a = e / TS, r = e % TS;
+        const int qa = ta * TS + r, qb = tb * TS + r;
+        xa[a][r] = (qa < M) ? xr[(long long)qa * D + a] / kp.ell[a] : 0.0;
+        xb[a][r] = (qb < M) ? xr[(long long)qb * D + a] / kp.ell[a] : 0.0;
+    }
+    pipe_init(&pipe);
+    double acc[8][4][2];
+    acc_clear(acc);
+    Operand A{&mapW, ta * TS, 0, MASK_NONE, -1};
+    Operand B{&mapW, tb * TS, 0, MASK_NONE, -1};
+    gemm_nt_tile(A, B, 0, T, acc, smem, &pipe);
+    acc_foreach(acc, [&](int r, int c, double v0, double v1) {
+        const int qa = ta * TS + r;
+        if (qa >= M) return;
+        double v[2] = {v0, v1};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int qb = tb * TS + c + j;
+            if (qb < M) {
+                double s = 0.0;
+#pragma unroll
+                for (int a = 0; a < D; ++a) {
+                    const double df = xa[a][r] - xb[a][c + j];
+                    s += df * df;
+                }
+                double kss = kp.c * exp(-0.5 * s);
+                if (qa == qb) kss += kp.s2;
+                cov[(long long)qa * M + qb] = kss - v[j];
+            }
+        }
+    });
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -206,15 +206,39 @@ class GaussianProcess:
         return self._engine.query(x, flags, vel)
 
     def predict(self, x, return_std=False, return_cov=False):
+        squeeze = self.n_outputs == 1                                     # sklearn squeezes single-target outputs (_gpr.py:452-456,495-499)
         if return_std == True:                                            # noqa: E712  (reference semantics)
             o = self._query(x, _lib.MEAN | _lib.STD)
+            if squeeze:
+                return o["mean"][:, 0], o["std"][:, 0]
             return o["mean"], o["std"]
         if return_cov == True:                                            # noqa: E712
-            raise NotImplementedError("predict(return_cov=True) is not on the B200 path yet (SURVEY.md section 8 row f2)")
-        return self._query(x, _lib.MEAN)["mean"]
+            mean, cov = self._joint(x)
+            if squeeze:
+                return mean[:, 0], cov
+            # sklearn:_gpr.py:470-478 -- the covariance is replicated over the outputs
+            return mean, np.repeat(cov[:, :, np.newaxis], self.n_outputs, axis=2)
+        mean = self._query(x, _lib.MEAN)["mean"]
+        return mean[:, 0] if squeeze else mean
+
+    def _joint(self, x):
+        self._ensure_fitted_factor()
+        x = np.asarray(x, dtype=np.float64)
+        return self._engine.query_cov(x)
 
     def samples(self, x):
-        raise NotImplementedError("samples() needs the joint posterior covariance (SURVEY.md section 8 row f2)")
+        """10 joint posterior samples, seed 0, layout (10, M, n_outputs) (gaussian_process.py:57-60 over sklearn's sample_y,
+        _gpr.py:502-539).  Mean and covariance come from the GPU; the draw itself is numpy's RandomState(0) multivariate
+        normal exactly as sklearn calls it, so the samples match the reference's stream."""
+        mean, cov = self._joint(x)
+        rng = check_random_state(0)
+        n_samples = 10
+        if self.n_outputs == 1:
+            y = rng.multivariate_normal(mean[:, 0], cov, n_samples).T                     # (M, 10), as sklearn returns it
+            return np.transpose(y, (2, 0, 1))     # the reference transposes three axes here and fails for one output; so do we
+        cols = [rng.multivariate_normal(mean[:, t], cov, n_samples).T[:, np.newaxis] for t in range(self.n_outputs)]
+        y = np.hstack(cols)                                                                # (M, p, 10)
+        return np.transpose(y, (2, 0, 1))
 
     def derivative(self, x, return_var=False):
         """Jacobian of the posterior mean, layout (M, n_outputs, n_features) (quirk Q4), and optionally the variance of

@@ -86,6 +86,11 @@ int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, uint32_t flag
                    double* mean_dev, double* std_dev, double* jac_dev, double* jacvar_dev,
                    double* xhat_dev, double* vhat_dev, double* vvar_dev, double* jphi_dev, double* dvar_dev);
 
+/* ---- joint posterior on M points: mean (M,p) and covariance (M,M) = k(x,x) + s2 I - K* K^-1 K*^T, the quantity behind
+ * GaussianProcess.predict(return_cov=True) and samples() (gaussian_process.py:50-60; sklearn:_gpr.py:470-475, 502-539).
+ * The covariance is output-independent (the host replicates it over p as sklearn does). */
+int gptb_query_cov(gptb_handle* h, const double* x, int64_t M, double* mean, double* cov);
+
 /* ---- read-back of fitted state (GaussianProcess attributes `gp.L_`, `gp.alpha_`, `K_inv`; gaussian_process.py:42-43).
  * L is (N,N) lower (upper part zero), alpha is (N,p), Kinv is (N,N) symmetric. */
 int gptb_export_L(gptb_handle* h, double* L);

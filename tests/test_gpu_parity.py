@@ -255,3 +255,40 @@ def test_full_size_properties_n4096():
     xq = np.random.default_rng(2).random((512, d))
     m1 = eng.query(xq, L.MEAN)["mean"]; m2 = eng2.query(xq, L.MEAN)["mean"]; m3 = eng3.query(xq, L.MEAN)["mean"]
     assert rel(m2, 2.0 * m1 + m3) < 1e-9
+
+
+def test_joint_covariance_and_samples_vs_oracle(pkg, golden_dir):
+    """predict(return_cov=True) and samples() against the oracle over the real sklearn regressor."""
+    from oracle.gp_oracle import SkGaussianProcess
+    g = load(golden_dir, "syn_ard300.npz")
+    mine = pkg.GaussianProcess(kernel=kernel_of(g), optimizer=None)
+    ora = SkGaussianProcess(kernel_of(g), optimizer=None)
+    mine.fit(g["X"], g["Y"]); ora.fit(g["X"], g["Y"])
+    xq = g["xq"][:50]
+    m1, c1 = mine.predict(xq, return_cov=True)
+    m2, c2 = ora.predict(xq, return_cov=True)
+    assert m1.shape == m2.shape and c1.shape == c2.shape == (50, 50, 3)
+    assert rel(m1, m2) < TOL_MEAN
+    assert np.max(np.abs(c1 - c2)) / (float(g["c"]) + float(g["s2"])) < TOL_STD
+    s1, s2 = mine.samples(xq), ora.samples(xq)
+    assert s1.shape == s2.shape == (10, 50, 3)
+    # same RandomState stream; the SVD-based draw amplifies covariance rounding by ~sqrt(cond), hence the looser bound
+    assert np.max(np.abs(s1 - s2)) < 1e-6
+
+
+def test_single_output_shapes_match_sklearn(pkg):
+    """p = 1: sklearn squeezes mean/std to 1-D (sklearn:_gpr.py:452-456,495-499); the drop-in must too."""
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+    from oracle.gp_oracle import SkGaussianProcess, synthetic_pairs
+    S, T = synthetic_pairs(150, 2, seed=9)
+    y = (T - S)[:, :1]
+    k = C(0.5) * RBF(0.3) + WhiteKernel(1e-3)
+    mine, ora = pkg.GaussianProcess(k, optimizer=None), SkGaussianProcess(k, optimizer=None)
+    mine.fit(S, y); ora.fit(S, y)
+    xq = S[:20] + 0.01
+    a, b = mine.predict(xq, return_std=True), ora.predict(xq, return_std=True)
+    assert a[0].shape == b[0].shape == (20,) and a[1].shape == b[1].shape == (20,)
+    assert rel(a[0], b[0]) < TOL_MEAN and np.max(np.abs(a[1] - b[1])) < TOL_STD
+    assert mine.predict(xq).shape == ora.predict(xq).shape
+    Ja, Jb = mine.derivative(xq), ora.derivative(xq)
+    assert Ja.shape == Jb.shape and rel(Ja, Jb) < TOL_MEAN
