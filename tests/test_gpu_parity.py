@@ -292,3 +292,23 @@ def test_single_output_shapes_match_sklearn(pkg):
     assert mine.predict(xq).shape == ora.predict(xq).shape
     Ja, Jb = mine.derivative(xq), ora.derivative(xq)
     assert Ja.shape == Jb.shape and rel(Ja, Jb) < TOL_MEAN
+
+
+def test_optimised_fit_matches_reference_c2(pkg, golden_dir):
+    """Config 2: the shipped 834-point clouds with the default kernel, full L-BFGS-B + 5 restarts, same RNG seed as the
+    golden run of the unmodified reference (154 LML evaluations there).  Noise ends at its lower bound in both."""
+    g = load(golden_dir, "c2_clouds3d_optimised.npz")
+    t = pkg.GaussianProcessTransportation()
+    t.source_distribution, t.target_distribution = g["S"], g["T"]
+    t.training_traj, t.training_delta = g["traj_in"], g["delta_in"]
+    np.random.seed(0)
+    t.fit_transportation()
+    t.apply_transportation()
+    gp = t.method.delta_map
+    assert abs(gp.gp.log_marginal_likelihood_value_ - float(g["lml"])) < 1e-6 * abs(float(g["lml"]))
+    prm = gp.kernel.get_params()
+    assert np.allclose(np.atleast_1d(prm["k1__k2__length_scale"]), g["ell"], rtol=1e-3)
+    assert np.isclose(prm["k1__k1__constant_value"], float(g["c"]), rtol=1e-3)
+    assert rel(t.training_traj, g["traj_out"]) < 1e-5
+    assert rel(t.training_delta, g["delta_out"]) < 1e-4
+    assert np.max(np.abs(t.std - g["std"])) / np.sqrt(float(g["c"]) + float(g["s2"])) < 1e-4
