@@ -505,7 +505,10 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
     af.on = (flags & GPTB_AFFINE_IN) ? h->af.on : 0;
     dim3 grid(Bpad / QPB, nsplit);
     tic(h, 1);
-    kstar_kernel<D, P><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, B, Bpad, h->kp, af, genflags, rhs, xr, macc, nsplit);
+    if (genflags)
+        kstar_kernel<D, P, true><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, B, Bpad, h->kp, af, genflags, rhs, xr, macc, nsplit);
+    else
+        kstar_kernel<D, P, false><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, B, Bpad, h->kp, af, 0u, rhs, xr, macc, nsplit);
     toc(h, 1);
     LAUNCH_CHECK(h);
     if (nrhs > 0) {
@@ -678,7 +681,7 @@ static int cov_generate(gptb_handle* h, const double* x_dev, int M, int Mpad, do
     Affine af = h->af;
     af.on = 0;
     dim3 grid(Mpad / QPB, 1);
-    kstar_kernel<D, P><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, M, Mpad, h->kp, af, 1u, rhs, xr, macc, 1);
+    kstar_kernel<D, P, true><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, M, Mpad, h->kp, af, 1u, rhs, xr, macc, 1);
     LAUNCH_CHECK(h);
     QueryOut out{mean_dev, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     finalize_kernel<D, P><<<(M + 127) / 128, 128, 0, h->stream>>>(macc, 1, nullptr, h->T, M, Mpad, Mpad, xr, nullptr, h->kp, h->af, GPTB_MEAN, out, 0, M);

@@ -13,10 +13,44 @@ struct Affine {
     double Tbar[MAXD];
 };
 
-constexpr int QPW = 4;          // queries per warp
-constexpr int QPB = 32;         // queries per CTA (8 warps)
+constexpr int QPW = 1;          // queries per warp
+constexpr int QPB = 8;          // queries per CTA (8 warps)
 constexpr int TRMM_GR = 12;     // L2 blocking of the variance triangular multiply: row tiles per group
 constexpr int TRMM_GI = 12;     //                                                   inverse-factor row tiles per group
+
+// ------------------------------------------------------------------------------------------------------------
+// exp(x) for x <= 0 (the RBF profile), FP64, ~1 ulp: x = m*(ln2/16) + r with m = 16 n + j, |r| <= ln2/32, so that
+// exp(x) = 2^n * 2^(j/16) * exp(r) needs only a degree-7 polynomial (remainder 1.2e-18) evaluated in Estrin form
+// (dependency depth 3) plus one table multiply.  12 FP64 issue slots instead of libdevice's ~21
+// (profiles/r01_fp64_peaks.json), and no special-case branches: arguments below -700 return 0.
+// The 16-entry table lives in shared memory (lanes with different j hit different banks).
+// ------------------------------------------------------------------------------------------------------------
+__constant__ double c_exp2_16[16] = {
+    0x1.0000000000000p+0, 0x1.0b5586cf9890fp+0, 0x1.172b83c7d517bp+0, 0x1.2387a6e756238p+0, 0x1.306fe0a31b715p+0, 0x1.3dea64c123422p+0,
+    0x1.4bfdad5362a27p+0, 0x1.5ab07dd485429p+0, 0x1.6a09e667f3bcdp+0, 0x1.7a11473eb0187p+0, 0x1.8ace5422aa0dbp+0, 0x1.9c49182a3f090p+0,
+    0x1.ae89f995ad3adp+0, 0x1.c199bdd85529cp+0, 0x1.d5818dcfba487p+0, 0x1.ea4afa2a490dap+0};
+
+__device__ __forceinline__ double exp_neg(double x, const double* tab) {
+    const double MAGIC = 6755399441055744.0;               // 1.5 * 2^52: the integer lands in the low mantissa word
+    const double t = fma(x, 0x1.71547652b82fep+4, MAGIC);   // x * 16/ln2
+    const int m = __double2loint(t);
+    const double mf = t - MAGIC;
+    double r = fma(mf, -0x1.62e42fee00000p-5, x);           // ln2/16 high part (32 significant bits: m*hi is exact)
+    r = fma(mf, -0x1.a39ef35793c76p-37, r);
+    const double r2 = r * r;
+    const double p01 = 1.0 + r;
+    const double p23 = fma(r, 1.0 / 6.0, 0.5);
+    const double p45 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    const double p67 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
+    const double r4 = r2 * r2;
+    const double lo = fma(r2, p23, p01);
+    const double hi = fma(r2, p67, p45);
+    double pv = fma(r4, hi, lo) * tab[m & 15];
+    // scale by 2^n through the exponent field (n <= 0 here; result stays normal for x >= -700)
+    const int n = m >> 4;
+    pv = __hiloint2double(__double2hiint(pv) + (n << 20), __double2loint(pv));
+    return (x < -700.0) ? 0.0 : pv;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // Generator: for a batch of queries, regenerate k(x*, X) on the fly (never read from HBM), reduce it against alpha
@@ -30,12 +64,15 @@ constexpr int TRMM_GI = 12;     //                                              
 // split when the batch alone cannot fill 148 SMs, partial sums are reduced in a fixed order by finalize.
 // Roofline: FP64 pipe (DFMA issue) -- ~21 DFMA slots for exp + 3D+2 for the distance + P(1+D) accumulate per pair.
 // ------------------------------------------------------------------------------------------------------------
-template <int D, int P>
+template <int D, int P, bool STORE>
 __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ xq, const double* __restrict__ Xs,
                                                     const double* __restrict__ alpha, int N, int Npad, int B, int Bpad,
                                                     KParams kp, Affine af, unsigned flags, double* __restrict__ rhs,
                                                     double* __restrict__ xr, double* __restrict__ macc, int nsplit) {
     constexpr int NACC = P + P * D;
+    __shared__ double etab[16];
+    if (threadIdx.x < 16) etab[threadIdx.x] = c_exp2_16[threadIdx.x];
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q0 = blockIdx.x * QPB + warp * QPW;
     double xs[QPW][D];
@@ -71,7 +108,7 @@ __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ x
 #pragma unroll
         for (int v = 0; v < NACC; ++v) acc[qq][v] = 0.0;
 
-    const bool st_k = flags & 1u, st_g = flags & 2u, st_kg = flags & 4u;
+    const bool st_k = STORE && (flags & 1u), st_g = STORE && (flags & 2u), st_kg = STORE && (flags & 4u);
     const int per = ((Npad / 32 + nsplit - 1) / nsplit) * 32;
     const int nbeg = blockIdx.y * per;
     const int nend = min(Npad, nbeg + per);
@@ -90,15 +127,15 @@ __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ x
                 df[a] = xs[qq][a] - xn[a];
                 s += df[a] * df[a];
             }
-            double k = (inb && valid[qq]) ? kp.c * exp(-0.5 * s) : 0.0;
+            double k = (inb && valid[qq]) ? kp.c * exp_neg(-0.5 * s, etab) : 0.0;
             const long long row = (long long)(q0 + qq) * Npad + n;
-            if (st_k) rhs[row] = k;
+            if (STORE && st_k) rhs[row] = k;
 #pragma unroll
             for (int o = 0; o < P; ++o) acc[qq][o] = fma(k, al[o], acc[qq][o]);
 #pragma unroll
             for (int a = 0; a < D; ++a) {
                 double u = -k * df[a];                 // k * (X_a - x_a)/ell_a
-                if (st_g | st_kg) {
+                if (STORE && (st_g | st_kg)) {
                     double gval = u * kp.inv_ell[a];
                     if (st_g) rhs[(long long)(1 + a) * Bpad * Npad + row] = gval;
                     if (st_kg) rhs[(long long)(1 + D + a) * Bpad * Npad + row] = k + gval;

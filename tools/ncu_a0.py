@@ -1,9 +1,13 @@
 """Driver for ncu captures of the Gram build and the mean/Jacobian generator (A0 mode) (developer tool)."""
-import os, sys
+import os
+import sys
+
 import numpy as np
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gaussian_process_transportation_b200 import _lib as L
 from oracle.gp_oracle import synthetic_pairs
+
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
 S, T = synthetic_pairs(N, 3, seed=0)
