@@ -21,6 +21,7 @@ SYMBOLS = {
     "gptb_last_error": (C.c_char_p, [C.c_void_p]),
     "gptb_version": (C.c_int, []),
     "gptb_set_train": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_int, C.c_int]),
+    "gptb_set_kernel_kind": (C.c_int, [C.c_void_p, C.c_int]),
     "gptb_factorize": (C.c_int, [C.c_void_p, C.c_double, _dp, C.c_double, C.c_double, _dp]),
     "gptb_lml": (C.c_int, [C.c_void_p, C.c_double, _dp, C.c_double, C.c_double, C.c_int, _dp, _dp]),
     "gptb_prepare_variance": (C.c_int, [C.c_void_p]),
@@ -122,6 +123,9 @@ class Engine:
         self.N, self.d = X.shape
         self.p = Y.shape[1]
         self._check(self.lib.gptb_set_train(self.h, ptr(X), ptr(Y), self.N, self.d, self.p), "gptb_set_train")
+
+    def set_kernel_kind(self, kind):
+        self._check(self.lib.gptb_set_kernel_kind(self.h, int(kind)), "gptb_set_kernel_kind")
 
     def _ell(self, ell):
         e = np.atleast_1d(np.asarray(ell, dtype=np.float64)).ravel()

@@ -14,11 +14,37 @@ namespace gptb {
 constexpr int MAXD = 4;
 constexpr int MAXP = 4;
 
+// Radial profile of the stationary part: RBF (sklearn:kernels.py:1558-1587) or Matern nu = 1.5 / 2.5
+// (sklearn:kernels.py Matern.__call__), all as functions of s = sum_a ((x_a - y_a)/ell_a)^2.
+enum { KIND_RBF = 0, KIND_MATERN15 = 1, KIND_MATERN25 = 2 };
+
 struct KParams {
     double c, s2, jitter;
     double ell[MAXD];
     double inv_ell[MAXD];
+    int kind;
 };
+
+// profile(s) with k = c * profile; EXPF is the exponential to use for a non-positive argument
+template <typename EXPF>
+__device__ __forceinline__ double kernel_profile(double s, int kind, EXPF expf_neg) {
+    if (kind == KIND_RBF) return expf_neg(-0.5 * s);
+    const double r = sqrt(s);
+    if (kind == KIND_MATERN15) {
+        const double t = 1.7320508075688772 * r;          // sqrt(3) * dist
+        return (1.0 + t) * expf_neg(-t);
+    }
+    const double t = 2.23606797749979 * r;                // sqrt(5) * dist
+    return (1.0 + t + t * t / 3.0) * expf_neg(-t);
+}
+
+// d profile / d log ell_a = grad_factor(s) * d2_a  with d2_a = ((x_a - y_a)/ell_a)^2   (sklearn Matern/RBF eval_gradient)
+__device__ __forceinline__ double kernel_grad_factor(double s, int kind) {
+    if (kind == KIND_RBF) return exp(-0.5 * s);
+    if (kind == KIND_MATERN15) return 3.0 * exp(-sqrt(3.0 * s));
+    const double t = sqrt(5.0 * s);
+    return 5.0 / 3.0 * (t + 1.0) * exp(-t);
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // Xs[a][n] = X[a][n] / ell[a]   (sklearn divides the inputs by the length-scale before differencing,
@@ -67,7 +93,7 @@ __global__ void __launch_bounds__(256) gram_lower_kernel(const double* __restric
                 double df = xi[a][r] - xj[a][q];
                 s += df * df;
             }
-            double v = kp.c * exp(-0.5 * s);
+            double v = kp.c * kernel_profile(s, kp.kind, [](double z) { return exp(z); });
             if (gi == gj) v += diag_add;
             if (gi >= N || gj >= N) v = (gi == gj) ? 1.0 : 0.0;
             out[q] = v;
@@ -620,10 +646,10 @@ __global__ void __launch_bounds__(256) lml_grad_kernel(const double* __restrict_
                     d2[a] = df * df;
                     s += d2[a];
                 }
-                double kr = kp.c * exp(-0.5 * s) * w;
-                gc += kr;
+                gc += kp.c * kernel_profile(s, kp.kind, [](double z) { return exp(z); }) * w;
+                const double kg = kp.c * kernel_grad_factor(s, kp.kind) * w;
 #pragma unroll
-                for (int a = 0; a < D; ++a) gl[a] = fma(kr, d2[a], gl[a]);
+                for (int a = 0; a < D; ++a) gl[a] = fma(kg, d2[a], gl[a]);
                 if (gi == gj) gs += w;
             }
         }

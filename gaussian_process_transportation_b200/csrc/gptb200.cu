@@ -244,6 +244,14 @@ static int alloc_model(gptb_handle* h, long long N, int d, int p, bool train) {
     return 0;
 }
 
+extern "C" int gptb_set_kernel_kind(gptb_handle* h, int kind) {
+    if (!h) return -1;
+    if (kind < 0 || kind > 2) GPTB_FAIL(h, -1, "unknown kernel kind %d", kind);
+    if (kind != h->kp.kind) h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = false;
+    h->kp.kind = kind;
+    return 0;
+}
+
 extern "C" int gptb_set_train(gptb_handle* h, const double* X, const double* Y, int64_t N, int d, int p) {
     if (!h || !X || !Y) return -1;
     int rc = alloc_model(h, N, d, p, true);
@@ -801,6 +809,7 @@ static int write_header(gptb_handle* h) {
     hd[0] = (double)h->N; hd[1] = h->d; hd[2] = h->p; hd[3] = h->kp.c; hd[4] = h->kp.s2; hd[5] = h->kp.jitter;
     for (int a = 0; a < MAXD; ++a) hd[6 + a] = h->kp.ell[a];
     hd[10] = h->have_minv ? 1.0 : 0.0;
+    hd[11] = (double)h->kp.kind;
     CU(h, cudaMemcpyAsync(h->header, hd, sizeof(hd), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
@@ -838,6 +847,7 @@ extern "C" int gptb_state_commit(gptb_handle* h) {
     double hd[32];
     CU(h, cudaMemcpy(hd, h->header, sizeof(hd), cudaMemcpyDeviceToHost));
     if ((long long)hd[0] != h->N || (int)hd[1] != h->d || (int)hd[2] != h->p) GPTB_FAIL(h, -1, "state header does not match the allocated shape");
+    h->kp.kind = (int)hd[11];
     int rc = set_params(h, hd[3], &hd[6], hd[4], hd[5]);
     if (rc) return rc;
     if ((rc = launch_scale(h))) return rc;

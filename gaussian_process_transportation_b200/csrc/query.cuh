@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ x
                 df[a] = xs[qq][a] - xn[a];
                 s += df[a] * df[a];
             }
-            double k = (inb && valid[qq]) ? kp.c * exp_neg(-0.5 * s, etab) : 0.0;
+            double k = (inb && valid[qq]) ? kp.c * kernel_profile(s, kp.kind, [&](double z) { return exp_neg(z, etab); }) : 0.0;
             const long long row = (long long)(q0 + qq) * Npad + n;
             if (STORE && st_k) rhs[row] = k;
 #pragma unroll
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) cov_kernel(const __grid_const
                     const double df = xa[a][r] - xb[a][c + j];
                     s += df * df;
                 }
-                double kss = kp.c * exp(-0.5 * s);
+                double kss = kp.c * kernel_profile(s, kp.kind, [](double z) { return exp(z); });
                 if (qa == qb) kss += kp.s2;
                 cov[(long long)qa * M + qb] = kss - v[j];
             }

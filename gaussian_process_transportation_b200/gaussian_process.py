@@ -16,7 +16,7 @@ from sklearn.base import clone
 from sklearn.utils import check_random_state
 
 from . import _lib
-from .kernel_spec import check_supported, map_gradient, read_params
+from .kernel_spec import check_supported, kernel_kind, map_gradient, read_params
 
 GPR_CHOLESKY_LOWER = True
 
@@ -116,6 +116,7 @@ class GaussianProcess:
                 "The number of targets seen in `y` is different from the parameter `n_targets`. "
                 f"Got {self.Y.shape[1]} != {gp.n_targets}.")
         eng = self._engine
+        eng.set_kernel_kind(kernel_kind(gp.kernel))
         eng.set_train(self.X, self.Y)
         gp.kernel_ = clone(gp.kernel)
         rng = check_random_state(None)                   # the global numpy RNG, as in the reference (quirk Q10)

@@ -8,7 +8,7 @@ sklearn's kernel classes are used here purely as that container (theta / bounds 
 from __future__ import annotations
 
 import numpy as np
-from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Product, Sum, WhiteKernel
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern, Product, Sum, WhiteKernel
 
 
 class UnsupportedKernel(NotImplementedError):
@@ -16,13 +16,22 @@ class UnsupportedKernel(NotImplementedError):
 
 
 def check_supported(kernel):
-    # exact types: sklearn's Matern / RationalQuadratic subclass RBF-like bases but have different radial profiles
+    # exact types: sklearn's Matern subclasses RBF but has a different radial profile
     ok = (type(kernel) is Sum and type(kernel.k1) is Product and type(kernel.k1.k1) is ConstantKernel
-          and type(kernel.k1.k2) is RBF and type(kernel.k2) is WhiteKernel)
+          and type(kernel.k2) is WhiteKernel
+          and (type(kernel.k1.k2) is RBF or (type(kernel.k1.k2) is Matern and kernel.k1.k2.nu in (1.5, 2.5))))
     if not ok:
         raise UnsupportedKernel(
-            "gaussian_process_transportation_b200 implements ConstantKernel * RBF + WhiteKernel only "
+            "gaussian_process_transportation_b200 implements ConstantKernel * {RBF | Matern(nu=1.5|2.5)} + WhiteKernel only "
             f"(got {kernel!r}); there is no CPU fallback for other kernels")
+
+
+def kernel_kind(kernel):
+    """Engine code of the stationary factor's radial profile: 0 RBF, 1 Matern-1.5, 2 Matern-2.5."""
+    k = kernel.k1.k2
+    if type(k) is RBF:
+        return 0
+    return 1 if k.nu == 1.5 else 2
 
 
 def read_params(kernel, d):

@@ -51,6 +51,12 @@ int  gptb_version(void);
  * X is (N,d), Y is (N,p).  Limits: 1 <= d <= 4, 1 <= p <= 4. */
 int gptb_set_train(gptb_handle* h, const double* X, const double* Y, int64_t N, int d, int p);
 
+/* ---- radial profile of the stationary factor: 0 = RBF (default), 1 = Matern nu=1.5, 2 = Matern nu=2.5
+ * (sklearn:kernels.py Matern.__call__; the dynamics GPs of the reference's demos use C*Matern(nu=2.5)+White,
+ * example/2D/surface_generalization.py:49).  Applies to every later factorize / lml / query call.
+ * Note: `derivative` keeps the reference's closed form dk = k (X - x)/ell^2 for every profile (gaussian_process.py:82-87). */
+int gptb_set_kernel_kind(gptb_handle* h, int kind);
+
 /* ---- fit at fixed hyper-parameters: Gram build, L = chol(c R + (s2+jitter) I), alpha = L^-T L^-1 Y.
  * Replaces sklearn:_gpr.py:347-367.  On return *lml (may be NULL) holds the log marginal likelihood
  * (sklearn:_gpr.py:613-617).  Non-PD => returns the failing order (>0). */

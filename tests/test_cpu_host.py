@@ -48,8 +48,12 @@ def test_kernel_parsing_and_gradient_mapping():
     assert np.allclose(map_gradient(k2, g, 3), g)
     k3 = C(0.1, constant_value_bounds="fixed") * RBF([0.1, 0.2, 0.3]) + WhiteKernel(1e-4, noise_level_bounds="fixed")
     assert np.allclose(map_gradient(k3, g, 3), [2.0, 3.0, 4.0]) and k3.theta.size == 3
+    from gaussian_process_transportation_b200.kernel_spec import kernel_kind
+    assert kernel_kind(k) == 0
+    assert kernel_kind(C(0.1) * Matern(0.1, nu=1.5) + WhiteKernel(1e-4)) == 1
+    assert kernel_kind(C(0.1) * Matern([0.1, 0.2], nu=2.5) + WhiteKernel(1e-4)) == 2
     with pytest.raises(UnsupportedKernel):
-        check_supported(C(0.1) * Matern(0.1) + WhiteKernel(1e-4))
+        check_supported(C(0.1) * Matern(0.1, nu=0.5) + WhiteKernel(1e-4))
     with pytest.raises(UnsupportedKernel):
         check_supported(RBF(0.1))
     with pytest.raises(ValueError):

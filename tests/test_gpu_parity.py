@@ -218,7 +218,7 @@ def test_nan_rows_are_dropped_and_nonpd_raises(pkg):
         bad.fit(Sd, np.vstack([Y[:50], Y[:50]])[:, :])
     with pytest.raises(NotImplementedError):
         from sklearn.gaussian_process.kernels import Matern
-        pkg.GaussianProcess(C(1.0) * Matern(1.0) + WhiteKernel(1e-3))
+        pkg.GaussianProcess(C(1.0) * Matern(1.0, nu=0.5) + WhiteKernel(1e-3))
 
 
 def test_full_size_properties_n4096():
@@ -312,3 +312,41 @@ def test_optimised_fit_matches_reference_c2(pkg, golden_dir):
     assert rel(t.training_traj, g["traj_out"]) < 1e-5
     assert rel(t.training_delta, g["delta_out"]) < 1e-4
     assert np.max(np.abs(t.std - g["std"])) / np.sqrt(float(g["c"]) + float(g["s2"])) < 1e-4
+
+
+@pytest.mark.parametrize("nu,d", [(2.5, 2), (1.5, 3)])
+def test_matern_policy_gp_vs_oracle(pkg, nu, d):
+    """the dynamics GPs of the reference demos are C*Matern(nu=2.5)+White
+    (example/2D/surface_generalization.py:49-54) queried on dense grids.  Oracle = the reference wrapper restated over the real
+    sklearn regressor (any kernel).  `derivative` keeps the reference's RBF-form expression for every profile."""
+    from sklearn.gaussian_process.kernels import Matern, WhiteKernel, ConstantKernel as C
+    from oracle.gp_oracle import SkGaussianProcess, synthetic_pairs
+    S, T = synthetic_pairs(400, d, seed=11)
+    Y = T - S
+    k = C(np.sqrt(0.1)) * Matern(np.linspace(0.3, 0.5, d), nu=nu) + WhiteKernel(0.01)
+    mine, ora = pkg.GaussianProcess(k, optimizer=None), SkGaussianProcess(k, optimizer=None)
+    mine.fit(S, Y); ora.fit(S, Y)
+    g = np.linspace(-0.1, 1.1, 12)
+    xq = np.stack(np.meshgrid(*([g] * d)), -1).reshape(-1, d)[:1500]
+    m1, s1 = mine.predict(xq, return_std=True); m2, s2 = ora.predict(xq, return_std=True)
+    assert rel(m1, m2) < TOL_MEAN
+    assert np.max(np.abs(s1 - s2)) / np.sqrt(np.sqrt(0.1) + 0.01) < TOL_STD
+    J1, V1 = mine.derivative(xq[:200], return_var=True); J2, V2 = ora.derivative(xq[:200], return_var=True)
+    assert rel(J1, J2) < TOL_MEAN and rel(V1, V2) < TOL_STD
+    th = mine.gp.kernel_.theta + 0.3
+    v1, g1 = mine.gp.log_marginal_likelihood(th, eval_gradient=True)
+    v2, g2 = ora.gp.log_marginal_likelihood(th, eval_gradient=True)
+    assert abs(v1 - v2) <= 1e-10 * abs(v2) and rel(g1, g2) < 1e-8
+
+
+def test_matern_optimised_fit_matches_sklearn(pkg):
+    from sklearn.gaussian_process.kernels import Matern, WhiteKernel, ConstantKernel as C
+    from oracle.gp_oracle import SkGaussianProcess, synthetic_pairs
+    S, T = synthetic_pairs(120, 2, seed=5)
+    Y = T - S
+    k = C(np.sqrt(0.1)) * Matern(np.ones(2), nu=2.5) + WhiteKernel(0.01)
+    mine, ora = pkg.GaussianProcess(k, n_restarts_optimizer=2), SkGaussianProcess(k, n_restarts_optimizer=2)
+    np.random.seed(3); mine.fit(S, Y)
+    np.random.seed(3); ora.fit(S, Y)
+    assert abs(mine.gp.log_marginal_likelihood_value_ - ora.gp.log_marginal_likelihood_value_) < 1e-6 * abs(ora.gp.log_marginal_likelihood_value_)
+    assert rel(mine.predict(S[:30] + 0.02), ora.predict(S[:30] + 0.02)) < 1e-5
