@@ -24,6 +24,7 @@ SYMBOLS = {
     "gptb_set_kernel_kind": (C.c_int, [C.c_void_p, C.c_int]),
     "gptb_factorize": (C.c_int, [C.c_void_p, C.c_double, _dp, C.c_double, C.c_double, _dp]),
     "gptb_lml": (C.c_int, [C.c_void_p, C.c_double, _dp, C.c_double, C.c_double, C.c_int, _dp, _dp]),
+    "gptb_set_variance_mode": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "gptb_prepare_variance": (C.c_int, [C.c_void_p]),
     "gptb_set_affine": (C.c_int, [C.c_void_p, _dp, C.c_double, _dp, _dp]),
     "gptb_query": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_uint32, _dp] + [_dp] * 9),
@@ -151,6 +152,10 @@ class Engine:
         rc = self.lib.gptb_lml(self.h, float(c), ptr(e), float(s2), float(jitter), int(bool(want_grad)), C.byref(out), ptr(g))
         self._check(rc, "gptb_lml")
         return rc, out.value, g
+
+    def set_variance_mode(self, mode, slices=6):
+        """0 = FP64 DMMA (default); 1 = INT8-sliced tcgen05 path with `slices` digit planes (5..7)."""
+        self._check(self.lib.gptb_set_variance_mode(self.h, int(mode), int(slices)), "gptb_set_variance_mode")
 
     def prepare_variance(self):
         self._check(self.lib.gptb_prepare_variance(self.h), "gptb_prepare_variance")

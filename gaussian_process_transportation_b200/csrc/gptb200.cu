@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "query.cuh"
+#include "ozaki.cuh"
 
 using namespace gptb;
 
@@ -43,6 +44,19 @@ bool make_operand_map(CUtensorMap* m, const double* base, long long rows, long l
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 3-D TMA view (k bytes, rows, plane) of int8 digit planes [S][rows][ncols]; box (64, box_rows, S), 64-byte swizzle
+// (the K-major shared-memory layout tcgen05.mma expects).
+bool make_plane_map(CUtensorMap* m, const int8_t* base, long long rows, long long ncols, int S, int box_rows) {
+    EncodeTiledFn enc = get_encoder();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)ncols, (cuuint64_t)rows, (cuuint64_t)S};
+    cuuint64_t strides[2] = {(cuuint64_t)ncols, (cuuint64_t)rows * (cuuint64_t)ncols};
+    cuuint32_t box[3] = {(cuuint32_t)oz::OKB, (cuuint32_t)box_rows, (cuuint32_t)S};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 struct gptb_handle {
@@ -58,6 +72,12 @@ struct gptb_handle {
     double* header = nullptr;
     int* info = nullptr;
     CUtensorMap mapL, mapD, mapM, mapW;      // TMA views of Lbuf, Dinv, Minv, Wbuf
+    // INT8-sliced variance path (ozaki.cuh): digit planes of the inverse factor + per-row scales
+    int var_mode = 0, var_slices = 6;
+    int8_t* Bplanes = nullptr;
+    double* scaleB = nullptr;
+    CUtensorMap mapBq;
+    bool have_bplanes = false;
     KParams kp{};
     Affine af{};
     bool have_train = false, have_factor = false, have_alpha = false, have_minv = false, have_kinv = false;
@@ -118,7 +138,11 @@ static void free_model(gptb_handle* h) {
         if (*pp) cudaFree(*pp);
         *pp = nullptr;
     }
-    h->have_train = h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = false;
+    if (h->Bplanes) cudaFree(h->Bplanes);
+    if (h->scaleB) cudaFree(h->scaleB);
+    h->Bplanes = nullptr;
+    h->scaleB = nullptr;
+    h->have_train = h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = h->have_bplanes = false;
 }
 
 static int set_kernel_attrs(gptb_handle* h) {
@@ -129,6 +153,9 @@ static int set_kernel_attrs(gptb_handle* h) {
     CU(h, cudaFuncSetAttribute(trtri_level_p2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(kinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(trmm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<5>::SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<6>::SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<7>::SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(trmm_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(cov_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(cov_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -241,6 +268,16 @@ static int alloc_model(gptb_handle* h, long long N, int d, int p, bool train) {
     }
     h->N = N;
     h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = false;
+    return 0;
+}
+
+extern "C" int gptb_set_variance_mode(gptb_handle* h, int mode, int slices) {
+    if (!h) return -1;
+    if (mode < 0 || mode > 1) GPTB_FAIL(h, -1, "unknown variance mode %d", mode);
+    if (mode == 1 && (slices < 5 || slices > 7)) GPTB_FAIL(h, -1, "the INT8-sliced variance path supports 5, 6 or 7 digit planes (got %d)", slices);
+    if (mode == 1 && slices != h->var_slices) h->have_bplanes = false;
+    h->var_mode = mode;
+    if (mode == 1) h->var_slices = slices;
     return 0;
 }
 
@@ -422,6 +459,7 @@ static int build_minv(gptb_handle* h) {
     int rc = ensure_wbuf(h);
     if (rc) return rc;
     h->have_kinv = false;
+    h->have_bplanes = false;
     trtri_init_kernel<<<T, 256, 0, h->stream>>>(h->Minv, ld, h->Dinv);
     LAUNCH_CHECK(h);
     for (int s = 1; s < T; s *= 2) {
@@ -433,6 +471,32 @@ static int build_minv(gptb_handle* h) {
         LAUNCH_CHECK(h);
     }
     h->have_minv = true;
+    return 0;
+}
+
+template <typename F>
+static void dispatch_slices(int S, F f) {
+    if (S == 5) f(std::integral_constant<int, 5>{});
+    else if (S == 6) f(std::integral_constant<int, 6>{});
+    else f(std::integral_constant<int, 7>{});
+}
+
+// digit planes of the inverse factor for the INT8-sliced variance path
+static int build_bplanes(gptb_handle* h) {
+    if (h->have_bplanes) return 0;
+    int rc = build_minv(h);
+    if (rc) return rc;
+    const long long Npad = h->Npad;
+    const int S = h->var_slices;
+    if (h->Bplanes) { cudaFree(h->Bplanes); h->Bplanes = nullptr; }
+    CU(h, cudaMalloc(&h->Bplanes, (size_t)S * Npad * Npad));
+    if (!h->scaleB) CU(h, cudaMalloc(&h->scaleB, sizeof(double) * Npad));
+    dispatch_slices(S, [&](auto SS) {
+        oz::slice_rows_kernel<decltype(SS)::value><<<(unsigned)Npad, 256, 0, h->stream>>>(h->Minv, Npad, Npad, (int)Npad, 1, h->Bplanes, Npad * Npad, h->scaleB);
+    });
+    LAUNCH_CHECK(h);
+    if (!make_plane_map(&h->mapBq, h->Bplanes, Npad, Npad, S, oz::ON)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
+    h->have_bplanes = true;
     return 0;
 }
 
@@ -506,7 +570,7 @@ extern "C" int gptb_set_affine(gptb_handle* h, const double* R, double s, const 
 template <int D, int P>
 static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_dev, int B, int Bpad, unsigned flags, int nrhs,
                        unsigned genflags, const QueryOut& out, long long q_off, long long Mtot, double* rhs, double* part,
-                       double* macc, double* xr, int nsplit, const CUtensorMap* mapR) {
+                       double* macc, double* xr, int nsplit, const CUtensorMap* mapR, void* oz_planes, double* oz_scale) {
     const int T = h->T;
     const long long rows_total = (long long)nrhs * Bpad;
     Affine af = h->af;
@@ -519,20 +583,40 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
         kstar_kernel<D, P, false><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, B, Bpad, h->kp, af, 0u, rhs, xr, macc, nsplit);
     toc(h, 1);
     LAUNCH_CHECK(h);
-    if (nrhs > 0) {
+    int Tpart = T;
+    if (nrhs > 0 && h->var_mode == 1) {
+        // INT8-sliced path: split the right-hand-side rows into digit planes, then S(S+1)/2 exact int8 GEMMs per tile
+        const int S = h->var_slices;
+        const int rowtiles = (int)(rows_total / TS);
+        const int T64 = (int)(h->Npad / oz::ON);
+        int8_t* Aplanes = reinterpret_cast<int8_t*>(oz_planes);
+        CUtensorMap mapAq;
+        if (!make_plane_map(&mapAq, Aplanes, rows_total, h->Npad, S, oz::OM)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
+        tic(h, 0);
+        dispatch_slices(S, [&](auto SS) {
+            constexpr int SV = decltype(SS)::value;
+            oz::slice_rows_kernel<SV><<<(unsigned)rows_total, 256, 0, h->stream>>>(rhs, h->Npad, rows_total, (int)h->Npad, 0, Aplanes, rows_total * h->Npad, oz_scale);
+            oz::ozaki_trmm_kernel<SV><<<(unsigned)((long long)rowtiles * T64), oz::OTHREADS, oz::Cfg<SV>::SMEM_BYTES, h->stream>>>(
+                mapAq, h->mapBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part);
+        });
+        toc(h, 0);
+        h->launches++;
+        LAUNCH_CHECK(h);
+        Tpart = T64;
+    } else if (nrhs > 0) {
         const int rowtiles = (int)(rows_total / TS);
         tic(h, 0);
         trmm_sumsq_kernel<<<(unsigned)((long long)rowtiles * T), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(*mapR, h->mapM, T, rowtiles, rows_total, part);
         toc(h, 0);
         LAUNCH_CHECK(h);
     }
-    finalize_kernel<D, P><<<(B + 127) / 128, 128, 0, h->stream>>>(macc, nsplit, part, T, B, Bpad, rows_total, xr, vel_dev, h->kp, h->af, flags, out, q_off, Mtot);
+    finalize_kernel<D, P><<<(B + 127) / 128, 128, 0, h->stream>>>(macc, nsplit, part, Tpart, B, Bpad, rows_total, xr, vel_dev, h->kp, h->af, flags, out, q_off, Mtot);
     LAUNCH_CHECK(h);
     return 0;
 }
 
 typedef int (*chunk_fn)(gptb_handle*, const double*, const double*, int, int, unsigned, int, unsigned, const QueryOut&, long long,
-                        long long, double*, double*, double*, double*, int, const CUtensorMap*);
+                        long long, double*, double*, double*, double*, int, const CUtensorMap*, void*, double*);
 
 static chunk_fn pick_chunk_fn(int d, int p) {
     static const chunk_fn table[4][4] = {
@@ -567,14 +651,15 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     if (flags & (GPTB_STD | GPTB_DVAR)) { nrhs = 1; genflags |= 1u; }
     if (flags & (GPTB_JACVAR | GPTB_DVAR)) { nrhs = 1 + d; genflags |= 2u; }
     if (flags & GPTB_DVAR) { nrhs = 1 + 2 * d; genflags |= 4u | 1u; }
+    const bool ozaki = (nrhs > 0 && h->var_mode == 1);
     if (nrhs > 0) {
-        int rc = build_minv(h);
+        int rc = ozaki ? build_bplanes(h) : build_minv(h);
         if (rc) return rc;
     }
     // batch size: bounded by the workspace for the right-hand-side rows (nrhs * Bpad * Npad doubles)
     long long Bmax;
     if (nrhs > 0) {
-        Bmax = h->ws_limit / (long long)(sizeof(double) * nrhs * h->Npad);
+        Bmax = h->ws_limit / (long long)((sizeof(double) + (ozaki ? h->var_slices : 0)) * nrhs * h->Npad);
         Bmax = Bmax / TS * TS;
         if (Bmax < TS) Bmax = TS;
         if (Bmax > 65536) Bmax = 65536;
@@ -593,7 +678,9 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     size_t need = 0;
     auto carve = [&](size_t doubles) { size_t off = need; need += (doubles * sizeof(double) + 255) / 256 * 256; return off; };
     size_t o_rhs = carve((size_t)nrhs * Bfirst * h->Npad);
-    size_t o_part = carve((size_t)(nrhs > 0 ? T : 0) * nrhs * Bfirst);
+    size_t o_part = carve((size_t)(nrhs > 0 ? (ozaki ? 2 * T : T) : 0) * nrhs * Bfirst);
+    size_t o_ozp = carve(ozaki ? ((size_t)h->var_slices * nrhs * Bfirst * h->Npad + 7) / 8 : 0);
+    size_t o_ozs = carve(ozaki ? (size_t)nrhs * Bfirst : 0);
     size_t o_macc = carve((size_t)nsplit * Bfirst * NACC);
     size_t o_xr = carve((size_t)Bfirst * d);
     if (need > h->ws_bytes) {
@@ -609,6 +696,8 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     double* part = reinterpret_cast<double*>(base + o_part);
     double* macc = reinterpret_cast<double*>(base + o_macc);
     double* xr = reinterpret_cast<double*>(base + o_xr);
+    void* oz_planes = base + o_ozp;
+    double* oz_scale = reinterpret_cast<double*>(base + o_ozs);
     QueryOut out{mean_dev, std_dev, jac_dev, jacvar_dev, xhat_dev, vhat_dev, vvar_dev, jphi_dev, dvar_dev};
     chunk_fn fn = pick_chunk_fn(d, p);
     CUtensorMap mapR_full, mapR_tail;
@@ -626,7 +715,7 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
             }
             mapR = m;
         }
-        int rc = fn(h, x_dev + q0 * d, vel_dev ? vel_dev + q0 * d : nullptr, B, Bpad, flags, nrhs, genflags, out, q0, M, rhs, part, macc, xr, nsplit, mapR);
+        int rc = fn(h, x_dev + q0 * d, vel_dev ? vel_dev + q0 * d : nullptr, B, Bpad, flags, nrhs, genflags, out, q0, M, rhs, part, macc, xr, nsplit, mapR, oz_planes, oz_scale);
         if (rc) return rc;
     }
     return 0;

@@ -72,7 +72,8 @@ class _Regressor:
 
 
 class GaussianProcess:
-    def __init__(self, kernel, alpha=1e-10, optimizer='fmin_l_bfgs_b', n_restarts_optimizer=5, n_targets=None, device=None):
+    def __init__(self, kernel, alpha=1e-10, optimizer='fmin_l_bfgs_b', n_restarts_optimizer=5, n_targets=None, device=None,
+                 variance_mode=None):
         check_supported(kernel)
         if optimizer is None:
             n_restarts_optimizer = 0                     # gaussian_process.py:18-21 (sklearn default)
@@ -80,6 +81,10 @@ class GaussianProcess:
         self.kernel = kernel
         self.alpha = alpha
         self._device = device
+        # how |L^-1 k*|^2 is evaluated: "fp64" (DMMA, default) or "int8x5|6|7" (INT8-sliced tcgen05 path, include/gptb200.h);
+        # the environment variable GPTB_VARIANCE_MODE sets the default for objects that do not say
+        import os as _os
+        self._variance_mode = variance_mode or _os.environ.get("GPTB_VARIANCE_MODE", "fp64")
         self._engine_obj = None
         self._factor_theta = None
         self._K_inv = None
@@ -93,6 +98,11 @@ class GaussianProcess:
                 import os
                 dev = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("GPTB_DEVICE") is None else int(os.environ["GPTB_DEVICE"])
             self._engine_obj = _lib.Engine(dev)
+            vm = str(self._variance_mode).lower()
+            if vm.startswith("int8x"):
+                self._engine_obj.set_variance_mode(1, int(vm[5:]))
+            elif vm != "fp64":
+                raise ValueError(f"unknown variance_mode {self._variance_mode!r} (use 'fp64' or 'int8x5'..'int8x7')")
         return self._engine_obj
 
     # -- fit -------------------------------------------------------------------------------------------------------

@@ -71,6 +71,12 @@ int gptb_factorize(gptb_handle* h, double c, const double* ell, double s2, doubl
 int gptb_lml(gptb_handle* h, double c, const double* ell, double s2, double jitter, int want_grad,
              double* lml, double* grad);
 
+/* ---- how the variance products |L^-1 k*|^2 are evaluated: mode 0 (default) = FP64 DMMA tile engine; mode 1 = INT8-sliced
+ * ("Ozaki") evaluation on tcgen05 tensor cores with `slices` in {5,6,7} 7-bit digit planes per operand (exact int32
+ * accumulation of the digit products, FP64 recombination).  6 planes reproduce the FP64 std to ~1e-9 of sqrt(c+s2)
+ * (tolerance 1e-7), 7 to ~1e-11; the posterior mean and Jacobian are unaffected. */
+int gptb_set_variance_mode(gptb_handle* h, int mode, int slices);
+
 /* ---- explicit inverse factor for the variance queries (built lazily by gptb_query when needed). */
 int gptb_prepare_variance(gptb_handle* h);
 

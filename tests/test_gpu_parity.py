@@ -350,3 +350,58 @@ def test_matern_optimised_fit_matches_sklearn(pkg):
     np.random.seed(3); ora.fit(S, Y)
     assert abs(mine.gp.log_marginal_likelihood_value_ - ora.gp.log_marginal_likelihood_value_) < 1e-6 * abs(ora.gp.log_marginal_likelihood_value_)
     assert rel(mine.predict(S[:30] + 0.02), ora.predict(S[:30] + 0.02)) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# INT8-sliced (tcgen05) variance path: same tolerances as the FP64 path
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["syn_ard300.npz", "syn_ard1000.npz", "syn_iso500.npz"])
+def test_int8_sliced_variance_vs_reference_golden(pkg, golden_dir, name):
+    g = load(golden_dir, name)
+    gp = pkg.GaussianProcess(kernel=kernel_of(g), optimizer=None, variance_mode="int8x6")
+    gp.fit(g["X"], g["Y"])
+    sc = np.sqrt(float(g["c"]) + float(g["s2"]))
+    mean, std = gp.predict(g["xq"], return_std=True)
+    J, Jv = gp.derivative(g["xq"], return_var=True)
+    assert rel(mean, g["mean"]) < TOL_MEAN and rel(J, g["J"]) < TOL_MEAN
+    assert np.max(np.abs(std - g["std"])) / sc < TOL_STD
+    assert rel(Jv, g["Jvar"]) < TOL_STD
+    assert rel(gp.derivative_of_variance(g["xq"]), g["dvar"]) < 1e-5
+
+
+def test_int8_sliced_transport_flow_and_slices(pkg, golden_dir):
+    g = load(golden_dir, "c2_clouds3d_fixed.npz")
+    sc = np.sqrt(float(g["c"]) + float(g["s2"]))
+    errs = {}
+    for mode in ("int8x6", "int8x7"):
+        t = pkg.GaussianProcessTransportation(kernel_transport=kernel_of(g))
+        t.method = pkg.PolicyTransportation(pkg.GaussianProcess(kernel=kernel_of(g), optimizer=None, variance_mode=mode))
+        t.source_distribution, t.target_distribution = g["S"], g["T"]
+        t.training_traj, t.training_delta = g["traj_in"], g["delta_in"]
+        t.fit_transportation()
+        t.apply_transportation()
+        assert rel(t.training_traj, g["traj_out"]) < TOL_MEAN and rel(t.training_delta, g["delta_out"]) < TOL_MEAN
+        errs[mode] = np.max(np.abs(t.std - g["std"])) / sc
+        assert errs[mode] < TOL_STD
+        assert rel(t.var_vel_transported, g["var_vel"]) < 1e-6
+    assert errs["int8x7"] <= errs["int8x6"] * 1.5 + 1e-12
+
+
+def test_int8_sliced_full_size_n4096():
+    """N = 4096 (BASELINE config 3): the sliced path against the FP64 DMMA path of the same engine on 8192 queries, incl. points
+    next to training inputs where the variance nearly cancels."""
+    from gaussian_process_transportation_b200 import _lib as L
+    from oracle.gp_oracle import synthetic_pairs
+    S, T = synthetic_pairs(4096, 3, seed=0)
+    eng = L.Engine(0)
+    eng.set_train(S, T - S)
+    assert eng.factorize(0.1, [0.1] * 3, 1e-4, 1e-10)[0] == 0
+    rng = np.random.default_rng(5)
+    xq = np.vstack([-0.1 + 1.2 * rng.random((6144, 3)), S[:2048] + 1e-4])
+    ref = eng.query(xq, L.MEAN | L.STD | L.JAC)
+    eng.set_variance_mode(1, 6)
+    o = eng.query(xq, L.MEAN | L.STD | L.JAC)
+    assert np.array_equal(o["mean"], ref["mean"]) and np.array_equal(o["jac"], ref["jac"])
+    assert np.max(np.abs(o["std"] - ref["std"])) / np.sqrt(0.1 + 1e-4) < 2e-8
+    with pytest.raises(L.GptbError):
+        eng.set_variance_mode(1, 4)
