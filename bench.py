@@ -107,6 +107,28 @@ def measure_dgemm_peak(torch, dev, n=6144):
     return 2.0 * n ** 3 / best * 1e-9
 
 
+def measure_int8_peak(torch, dev, n=8192):
+    """Library int8 tensor-core GEMM rate on this GPU (cuBLASLt through torch._int_mm), best of 5; falls back to
+    2 x the measured bf16 rate of MEASURED_PEAKS.json (int8 dense = 2 x bf16 dense on B200) when that path is unavailable."""
+    try:
+        a = torch.randint(-64, 64, (n, n), dtype=torch.int8, device=dev)
+        b = torch.randint(-64, 64, (n, n), dtype=torch.int8, device=dev)
+        torch._int_mm(a, b)
+        torch.cuda.synchronize(dev)
+        best = 1e30
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch._int_mm(a, b); e1.record(); torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / best * 1e-9, f"cuBLASLt int8 GEMM {n}^3 (torch._int_mm) measured live in this run"
+    except Exception as exc:  # pragma: no cover
+        try:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            return 2.0 * pk["bf16_tflops"], "2 x MEASURED_PEAKS.json bf16_tflops (int8 dense = 2 x bf16 dense); torch._int_mm unavailable: " + str(exc)[:80]
+        except Exception:
+            return 2.0 * 1590.0, "2 x fallback bf16 peak (1.59 PFLOP/s)"
+
+
 def cpu_baseline_sample(N, n_queries, threads_note=True):
     """The CPU path (oracle port over the real sklearn regressor) on a bounded sample: fit(optimizer=None) at N, then mode A
     = predict(return_std) + derivative() on `n_queries` points, chunked like BASELINE.md section 3."""
@@ -198,6 +220,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--queries", type=int, default=0, help="override queries per step per GPU")
+    ap.add_argument("--variance", default="int8x6", choices=["fp64", "int8x5", "int8x6", "int8x7"],
+                    help="evaluation of the predictive-variance products: FP64 DMMA tile engine, or the INT8-sliced tcgen05 path "
+                         "(exact int32 digit-plane GEMMs, FP64 recombination; 6 planes keep std within ~2e-9 of the FP64 path)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -223,6 +248,8 @@ def main():
     K = args.steps
 
     eng = L.Engine(local_rank)
+    if args.variance != "fp64":
+        eng.set_variance_mode(1, int(args.variance[5:]))
     S, T, xq = make_inputs(N, M, rank)
     fit_ms = prep_ms = bcast_ms = None
     if rank == 0:
@@ -300,6 +327,18 @@ def main():
     eng.timing(False); eng.timing_reset()
     launches = eng.launch_count() - launches0
     value = world * M * K / (ms_total * 1e-3)
+    other = None
+    if args.variance != "fp64":
+        # the same step with the variance products on the FP64 DMMA tile engine (the exact path), for reference
+        eng.set_variance_mode(0)
+        step_dev()
+        eng.timing(True); eng.timing_reset()
+        Ko = max(1, min(K, 2))
+        ms_o = timed(step_dev, Ko)
+        o_ms, o_n = eng.kernel_time(0)
+        eng.timing(False); eng.timing_reset()
+        other = {"ms": ms_o, "steps": Ko, "trmm_ms": o_ms, "trmm_n": o_n}
+        eng.set_variance_mode(1, int(args.variance[5:]))
 
     # ---- end to end through the host-pointer C ABI with pinned buffers ------------------------------------------
     xh = torch.from_numpy(xq).pin_memory()
@@ -325,28 +364,52 @@ def main():
     d2h = M * (p + p + p * d) * 8
 
     if rank == 0:
-        peak = measure_dgemm_peak(torch, dev)
+        dgemm_peak = measure_dgemm_peak(torch, dev)
         Npad = (N + 127) // 128 * 128
-        # algorithmic flops of the triangular multiply per launch: sum over row tiles of 2*128*128*128*(ti+1)
+        int8 = args.variance != "fp64"
         launches_per_step = max(1, trmm_n // max(K, 1))
         q_per_launch = M / launches_per_step
-        flops_per_launch = q_per_launch * Npad * (Npad + 128.0)
         avg_launch_ms = trmm_ms / max(trmm_n, 1)
-        achieved = flops_per_launch / (avg_launch_ms * 1e-3) * 1e-12
-        traffic = None
-        try:   # DRAM bytes per launch from the committed ncu capture, only when it is the same launch shape
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_trmm_traffic.json")))
-            if tr["N"] == N and abs(tr["queries_per_launch"] - q_per_launch) < 1:
-                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-        except Exception:
-            pass
-        roofline = {"bound": "tensor", "kernel": "trmm_sumsq_kernel (FP64 DMMA mma.sync.m8n8k4)", "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
-                    "algorithmic_flops_per_launch": flops_per_launch, "launch_ms": avg_launch_ms,
-                    "peak_source": "cuBLAS FP64 GEMM 6144^3 measured live in this run (MEASURED_PEAKS.json has no FP64 entry); "
-                                   "DMMA/DFMA pipe peak 37.0 TFLOP/s (profiles/r01_fp64_peaks.json)",
-                    "algorithmic_flops_per_query": Npad * (Npad + 128.0), "share_of_step": trmm_ms / ms_total,
-                    "generator_share_of_step": gen_ms / ms_total}
+        if int8:
+            # dominant kernel: ozaki_trmm_kernel -- S(S+1)/2 exact int8 GEMMs over the lower triangle, 64-row tiles
+            S_ = int(args.variance[5:])
+            pairs = S_ * (S_ + 1) // 2
+            ops_per_launch = 2.0 * pairs * q_per_launch * Npad * (Npad + 64.0) / 2.0
+            achieved = ops_per_launch / (avg_launch_ms * 1e-3) * 1e-12
+            int8_peak, int8_src = measure_int8_peak(torch, dev)
+            roofline = {"bound": "tensor", "kernel": f"ozaki_trmm_kernel<{S_}> (tcgen05.mma kind::i8, TMEM accumulators, {pairs} digit-plane products)",
+                        "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": achieved / int8_peak, "traffic": None,
+                        "peak_source": int8_src, "algorithmic_ops_per_launch": ops_per_launch, "launch_ms": avg_launch_ms,
+                        "fp64_equivalent_tflops": q_per_launch * Npad * (Npad + 64.0) / (avg_launch_ms * 1e-3) * 1e-12,
+                        "fp64_dgemm_peak_tflops": dgemm_peak, "share_of_step": trmm_ms / ms_total,
+                        "generator_share_of_step": gen_ms / ms_total}
+            if other:
+                fl = (M / max(1, other["trmm_n"] // other["steps"])) * Npad * (Npad + 128.0)
+                ach = fl / (other["trmm_ms"] / max(other["trmm_n"], 1) * 1e-3) * 1e-12
+                other_out = {"value": world * M * other["steps"] / (other["ms"] * 1e-3), "unit": "query-points/s",
+                             "ms_per_step": other["ms"] / other["steps"],
+                             "roofline": {"bound": "tensor", "kernel": "trmm_sumsq_kernel (FP64 DMMA mma.sync.m8n8k4)", "achieved": ach,
+                                          "peak": dgemm_peak, "unit": "TFLOP/s", "frac": ach / dgemm_peak}}
+            else:
+                other_out = None
+        else:
+            flops_per_launch = q_per_launch * Npad * (Npad + 128.0)
+            achieved = flops_per_launch / (avg_launch_ms * 1e-3) * 1e-12
+            traffic = None
+            try:   # DRAM bytes per launch from the committed ncu capture, only when it is the same launch shape
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r01_trmm_traffic.json")))
+                if tr["N"] == N and abs(tr["queries_per_launch"] - q_per_launch) < 1:
+                    traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            except Exception:
+                pass
+            roofline = {"bound": "tensor", "kernel": "trmm_sumsq_kernel (FP64 DMMA mma.sync.m8n8k4)", "achieved": achieved, "peak": dgemm_peak,
+                        "unit": "TFLOP/s", "frac": achieved / dgemm_peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                        "algorithmic_flops_per_launch": flops_per_launch, "launch_ms": avg_launch_ms,
+                        "peak_source": "cuBLAS FP64 GEMM 6144^3 measured live in this run (MEASURED_PEAKS.json has no FP64 entry); "
+                                       "DMMA/DFMA pipe peak 37.0 TFLOP/s (profiles/r01_fp64_peaks.json)",
+                        "algorithmic_flops_per_query": Npad * (Npad + 128.0), "share_of_step": trmm_ms / ms_total,
+                        "generator_share_of_step": gen_ms / ms_total}
+            other_out = None
         cpu = None
         if not args.no_cpu_baseline:
             nq = {4096: 4096, 16384: 1024}.get(N, 8192)
@@ -358,21 +421,23 @@ def main():
             m, s, J = cb["outs"][0]
             rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
             parity = {"mean_rel": rel(o["mean"], m), "jac_rel": rel(o["jac"], J),
-                      "std_abs_over_sqrt_prior": float(np.max(np.abs(o["std"] - s)) / np.sqrt(KERNEL["c"] + KERNEL["s2"]))}
+                      "std_abs_over_sqrt_prior": float(np.max(np.abs(o["std"] - s)) / np.sqrt(KERNEL["c"] + KERNEL["s2"])),
+                      "tolerance": {"mean_rel": 1e-9, "jac_rel": 1e-9, "std_abs_over_sqrt_prior": 1e-7}, "variance_mode": args.variance}
             cpu = {"value": cb["qps"], "unit": "query-points/s", "cores": cb["cores"], "kind": "port",
                    "sample": f"oracle port (sklearn GaussianProcessRegressor + restated reference wrapper) on {nq} of the workload's "
                              f"queries, predict(return_std)+derivative(), chunks of 2048; host has {cb['host_cpus']} cpus",
                    "fit_ms": cb["fit_ms"], "parity_vs_gpu": parity}
+        dtype = "f64" if not int8 else f"f64 (mean/Jacobian/fit in FP64; variance products as {args.variance[5:]}x7-bit int8 digit planes, exact int32 accumulation, FP64 recombination)"
         line = {"metric": METRIC, "value": value, "unit": "query-points/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
                 "data": "synthetic",
                 "config": {"workload": wl["name"], "N": N, "queries_per_step_per_gpu": M, "mode": "A (mean+std+Jacobian)",
-                           "kernel": "C(0.1)*RBF([0.1]*3)+White(1e-4)", "parallelism": f"query-sharded x{world}",
+                           "kernel": "C(0.1)*RBF([0.1]*3)+White(1e-4)", "parallelism": f"query-sharded x{world}", "variance": args.variance,
                            "l2_policy": "inputs larger than L2: each step streams a >=2 GiB k* workspace"},
                 "fit_ms": fit_ms, "prepare_variance_ms": prep_ms, "bcast_ms": bcast_ms,
                 "e2e": {"value": e2e_value, "unit": "query-points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / Ke, "steps": Ke},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "gpu_launches": int(launches), "roofline": roofline, "fp64_dmma_variance": other_out, "cpu_baseline": cpu,
                 "clocks": sampler.summary() if sampler else None}
         print(json.dumps(line))
     if world > 1:

@@ -90,7 +90,7 @@ struct gptb_handle {
     size_t stage_bytes = 0;
     long long launches = 0;
     bool timing = false;
-    std::vector<EvPair> ev[3];
+    std::vector<EvPair> ev[4];
 };
 
 #define GPTB_FAIL(h, code, ...)                               \
@@ -179,7 +179,7 @@ extern "C" int gptb_create(int device, gptb_handle** out) {
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete h; return -2; }
     if (cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete h; return -2; }
-    if (cudaMalloc(&h->info, sizeof(int)) != cudaSuccess || cudaMalloc(&h->scal, 64 * sizeof(double)) != cudaSuccess ||
+    if (cudaMalloc(&h->info, 4 * sizeof(int)) != cudaSuccess || cudaMalloc(&h->scal, 64 * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->header, 32 * sizeof(double)) != cudaSuccess) {
         delete h;
         return -2;
@@ -232,7 +232,7 @@ extern "C" int gptb_timing_reset(gptb_handle* h) {
     return 0;
 }
 extern "C" int gptb_kernel_time(gptb_handle* h, int which, double* ms, int64_t* n) {
-    if (!h || which < 0 || which > 2) return -1;
+    if (!h || which < 0 || which > 3) return -1;
     CU(h, cudaStreamSynchronize(h->stream));
     double tot = 0.0;
     for (auto& e : h->ev[which]) {
@@ -592,12 +592,20 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
         int8_t* Aplanes = reinterpret_cast<int8_t*>(oz_planes);
         CUtensorMap mapAq;
         if (!make_plane_map(&mapAq, Aplanes, rows_total, h->Npad, S, oz::OM)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
+        tic(h, 3);
+        dispatch_slices(S, [&](auto SS) {
+            oz::slice_rows_kernel<decltype(SS)::value><<<(unsigned)rows_total, 256, 0, h->stream>>>(rhs, h->Npad, rows_total, (int)h->Npad, 0, Aplanes, rows_total * h->Npad, oz_scale);
+        });
+        toc(h, 3);
         tic(h, 0);
         dispatch_slices(S, [&](auto SS) {
             constexpr int SV = decltype(SS)::value;
-            oz::slice_rows_kernel<SV><<<(unsigned)rows_total, 256, 0, h->stream>>>(rhs, h->Npad, rows_total, (int)h->Npad, 0, Aplanes, rows_total * h->Npad, oz_scale);
-            oz::ozaki_trmm_kernel<SV><<<(unsigned)((long long)rowtiles * T64), oz::OTHREADS, oz::Cfg<SV>::SMEM_BYTES, h->stream>>>(
-                mapAq, h->mapBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part);
+            const long long ntiles = (long long)rowtiles * T64;
+            int nsm = 148;
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+            cudaMemsetAsync(h->info + 1, 0, sizeof(int), h->stream);      // dynamic tile counter
+            oz::ozaki_trmm_kernel<SV><<<(unsigned)(ntiles < nsm ? ntiles : nsm), oz::OTHREADS, oz::Cfg<SV>::SMEM_BYTES, h->stream>>>(
+                mapAq, h->mapBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1);
         });
         toc(h, 0);
         h->launches++;

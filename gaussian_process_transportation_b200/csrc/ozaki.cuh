@@ -100,44 +100,45 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
 
 // ------------------------------------------------------------------------------------------------------------
 // part[ti64][row] = sum_{i in 64-row tile ti64} ( sum_{k <= i} RHS[row][k] Linv[i][k] )^2   via S(S+1)/2 int8 GEMMs.
+// Persistent: grid = #SMs, CTA b runs tiles b, b + grid, ... of the L2-blocked, heaviest-first tile order; TMEM is
+// allocated once, the TMA producer streams straight into the next tile while the epilogue drains the accumulators
+// (the MMA thread only waits for that drain, ~1 us per ~20 us tile).
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void oz_tile_decode(long long idx, int T64, int rowtiles, int& rt, int& ti) {
+    constexpr int GR = 12, GI = 24;     // groups of 12 row tiles x 24 factor-row tiles (same span as the DMMA kernel's 12 x 12)
+    const long long per_tib = (long long)rowtiles * GI;
+    const int tib = (int)(idx / per_tib);
+    const long long rem = idx - (long long)tib * per_tib;
+    const int ti_cnt = min(GI, T64 - tib * GI);
+    const int rb = (int)(rem / ((long long)GR * ti_cnt));
+    const int rem2 = (int)(rem - (long long)rb * GR * ti_cnt);
+    rt = rb * GR + rem2 / ti_cnt;
+    ti = T64 - 1 - (tib * GI + rem2 % ti_cnt);
+}
+
 template <int S>
 __global__ void __launch_bounds__(OTHREADS, 1) ozaki_trmm_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                 const __grid_constant__ CUtensorMap mapB,
                                                                 const double* __restrict__ scaleA, const double* __restrict__ scaleB,
                                                                 int T64, int rowtiles, long long rows_total,
-                                                                double* __restrict__ part) {
+                                                                double* __restrict__ part, int* __restrict__ tile_counter) {
     using C = Cfg<S>;
     constexpr int NST = C::NST;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t full[NST], empty[NST], acc_full;
+    __shared__ __align__(8) uint64_t full[NST], empty[NST], acc_full, acc_empty, slot_full[2], slot_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ double sB_scale[ON];
+    __shared__ long long tile_slot[2];     // dynamic tile scheduler: the producer claims tiles, the other roles follow
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    // tile order: groups of 12 row tiles x 24 factor-row tiles (same L2 blocking as the DMMA kernel), heaviest first
-    int ti, rt;
-    {
-        constexpr int GR = 12, GI = 24;
-        const long long idx = blockIdx.x;
-        const long long per_tib = (long long)rowtiles * GI;
-        const int tib = (int)(idx / per_tib);
-        const long long rem = idx - (long long)tib * per_tib;
-        const int ti_cnt = min(GI, T64 - tib * GI);
-        const int rb = (int)(rem / ((long long)GR * ti_cnt));
-        const int rem2 = (int)(rem - (long long)rb * GR * ti_cnt);
-        rt = rb * GR + rem2 / ti_cnt;
-        ti = T64 - 1 - (tib * GI + rem2 % ti_cnt);
-    }
-    const int nchunk = ti + 1;      // k extent (ti+1)*64 bytes, 64 per chunk
+    const long long ntiles = (long long)rowtiles * T64;
 
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(&acc_full, 1);
+        mbar_init(&acc_empty, 4);          // one arrival per epilogue warp
+        for (int i = 0; i < 2; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 5); }   // MMA thread + 4 epilogue warps
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (tid < ON) sB_scale[tid] = scaleB[(long long)ti * ON + tid];
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
@@ -149,77 +150,126 @@ __global__ void __launch_bounds__(OTHREADS, 1) ozaki_trmm_kernel(const __grid_co
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int c = 0; c < nchunk; ++c) {
-                const int st = c % NST;
-                if (c >= NST) mbar_wait(&empty[st], ((c / NST) - 1) & 1);
-                uint8_t* sA = smem + st * C::STAGE_BYTES;
-                uint8_t* sB = sA + S * OM * OKB;
-                mbar_expect_tx(&full[st], C::STAGE_BYTES);
-                tma_load_3d_u8(sA, &mapA, c * OKB, rt * OM, 0, &full[st]);
-                tma_load_3d_u8(sB, &mapB, c * OKB, ti * ON, 0, &full[st]);
+            int gs = 0;                                          // chunks issued so far (ring position)
+            for (int lt = 0;; ++lt) {
+                // claim the next tile in the global L2-blocked order (all SMs stay inside one window of ~#SM tiles, which is
+                // what keeps the operand slabs L2-resident; a static stride let the CTAs drift apart and cost 25 %)
+                if (lt >= 2) mbar_wait(&slot_empty[lt & 1], ((lt >> 1) - 1) & 1);
+                long long t = (long long)atomicAdd(tile_counter, 1);
+                if (t >= ntiles) t = -1;
+                tile_slot[lt & 1] = t;
+                mbar_arrive(&slot_full[lt & 1]);
+                if (t < 0) break;
+                int rt, ti;
+                oz_tile_decode(t, T64, rowtiles, rt, ti);
+                for (int c = 0; c <= ti; ++c, ++gs) {
+                    const int st = gs % NST;
+                    if (gs >= NST) mbar_wait(&empty[st], ((gs / NST) - 1) & 1);
+                    uint8_t* sA = smem + st * C::STAGE_BYTES;
+                    uint8_t* sB = sA + S * OM * OKB;
+                    mbar_expect_tx(&full[st], C::STAGE_BYTES);
+                    tma_load_3d_u8(sA, &mapA, c * OKB, rt * OM, 0, &full[st]);
+                    tma_load_3d_u8(sB, &mapB, c * OKB, ti * ON, 0, &full[st]);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // instruction descriptor: D = S32, A = B = INT8, both K-major, N = 64, M = 128
-            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ON >> 3) << 17) | ((uint32_t)(OM >> 4) << 24);
-            for (int c = 0; c < nchunk; ++c) {
-                const int st = c % NST;
-                mbar_wait(&full[st], (c / NST) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint8_t* sA = smem + st * C::STAGE_BYTES;
-                const uint8_t* sB = sA + S * OM * OKB;
-#pragma unroll
-                for (int a = 0; a < S; ++a) {
-                    const uint64_t ad = smem_desc_sw64(sA + a * OM * OKB);
-#pragma unroll
-                    for (int b = 0; b < S - a; ++b) {
-                        const uint64_t bd = smem_desc_sw64(sB + b * ON * OKB);
-                        const uint32_t dcol = tmem_base + (uint32_t)((a + b) * ON);
-#pragma unroll
-                        for (int kk = 0; kk < OKB / 32; ++kk)
-                            umma_i8(dcol, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (a == 0 && c == 0 && kk == 0) ? 0u : 1u);
-                    }
+            // instruction descriptor: D = S32, A = B = INT8, both K-major, M = 128
+            const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OM >> 4) << 24);   // N is or-ed in per MMA
+            int gs = 0;
+            for (int lt = 0;; ++lt) {
+                mbar_wait(&slot_full[lt & 1], (lt >> 1) & 1);
+                const long long t = tile_slot[lt & 1];
+                mbar_arrive(&slot_empty[lt & 1]);
+                if (t < 0) break;
+                int rt, ti;
+                oz_tile_decode(t, T64, rowtiles, rt, ti);
+                if (lt > 0) {                                    // accumulators of the previous tile must be drained
+                    mbar_wait(&acc_empty, (lt - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 }
-                umma_commit(&empty[st]);        // the stage is free once these MMAs have read it
+                for (int c = 0; c <= ti; ++c, ++gs) {
+                    const int st = gs % NST;
+                    mbar_wait(&full[st], (gs / NST) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const uint8_t* sA = smem + st * C::STAGE_BYTES;
+                    const uint8_t* sB = sA + S * OM * OKB;
+                    // For a fixed A plane a the partner planes b = 0 .. S-1-a accumulate into the diagonals a+b = a .. S-1,
+                    // i.e. into CONTIGUOUS TMEM columns [64a, 64S); and those B planes are contiguous rows in shared memory.
+                    // So the S-a pair products are issued as ONE wide MMA (N = 64(S-a), split at 256): the A tile is read
+                    // from shared memory once per wide MMA instead of once per pair.  With per-pair N = 64 MMAs the operand
+                    // fetch (6 KB per 32-cycle MMA = 192 B/clk) exceeded the 128 B/clk shared-memory port and capped the
+                    // kernel at 2/3 of the tensor rate (ncu: sm__throughput 88 %, tensor pipe 42 %).
+#pragma unroll
+                    for (int a = 0; a < S; ++a) {
+                        const uint64_t ad = smem_desc_sw64(sA + a * OM * OKB);
+#pragma unroll
+                        for (int b0 = 0; b0 < S - a; b0 += 4) {
+                            const int nb = (S - a - b0) < 4 ? (S - a - b0) : 4;        // planes in this MMA (N = 64 nb <= 256)
+                            const uint64_t bd = smem_desc_sw64(sB + b0 * ON * OKB);
+                            const uint32_t dcol = tmem_base + (uint32_t)((a + b0) * ON);
+                            const uint32_t idn = idesc_base | ((uint32_t)((nb * ON) >> 3) << 17);
+#pragma unroll
+                            for (int kk = 0; kk < OKB / 32; ++kk)
+                                umma_i8(dcol, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idn, (a == 0 && c == 0 && kk == 0) ? 0u : 1u);
+                        }
+                    }
+                    umma_commit(&empty[st]);        // the stage is free once these MMAs have read it
+                }
+                umma_commit(&acc_full);
             }
-            umma_commit(&acc_full);
         }
     } else {
         // ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4 ----------------
         const int quarter = warp & 3;
         const int q = quarter * 32 + lane;                      // query row within the tile = TMEM lane
-        mbar_wait(&acc_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        double ssum = 0.0;
+        for (int lt = 0;; ++lt) {
+            mbar_wait(&slot_full[lt & 1], (lt >> 1) & 1);
+            const long long t = tile_slot[lt & 1];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slot_empty[lt & 1]);
+            if (t < 0) break;
+            int rt, ti;
+            oz_tile_decode(t, T64, rowtiles, rt, ti);
+            mbar_wait(&acc_full, lt & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            double ssum = 0.0;
 #pragma unroll 1
-        for (int cb = 0; cb < ON / 16; ++cb) {
-            double v[16];
+            for (int cb = 0; cb < ON / 16; ++cb) {
+                double v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0.0;
+                for (int j = 0; j < 16; ++j) v[j] = 0.0;
 #pragma unroll
-            for (int d = 0; d < S; ++d) {
-                uint32_t r[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(d * ON + cb * 16);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-                const double w = ldexp(1.0, -DIGIT_BITS * (d + 2));       // digits are 1-based: weight 2^-7(a+b), a+b = d+2
+                for (int d = 0; d < S; ++d) {
+                    uint32_t r[16];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(d * ON + cb * 16);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                    const double w = ldexp(1.0, -DIGIT_BITS * (d + 2));   // digits are 1-based: weight 2^-7(a+b), a+b = d+2
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = fma((double)(int)r[j], w, v[j]);
+                    for (int j = 0; j < 16; ++j) v[j] = fma((double)(int)r[j], w, v[j]);
+                }
+                if (cb == ON / 16 - 1) {
+                    // every accumulator column of this tile has been read: let the MMA thread start the next tile
+                    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const double vv = v[j] * __ldg(scaleB + (long long)ti * ON + cb * 16 + j);
+                    ssum = fma(vv, vv, ssum);
+                }
             }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const double vv = v[j] * sB_scale[cb * 16 + j];
-                ssum = fma(vv, vv, ssum);
-            }
+            const long long grow = (long long)rt * OM + q;
+            const double sa = scaleA[grow];
+            part[(long long)ti * rows_total + grow] = ssum * sa * sa;
         }
-        const long long grow = (long long)rt * OM + q;
-        const double sa = scaleA[grow];
-        part[(long long)ti * rows_total + grow] = ssum * sa * sa;
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();

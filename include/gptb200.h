@@ -123,7 +123,8 @@ int gptb_state_commit(gptb_handle* h);
 /* number of kernels this library has launched on the handle since creation (benchmark `gpu_launches`). */
 int64_t gptb_launch_count(gptb_handle* h);
 /* CUDA-event time (ms) of the dominant kernel class accumulated since the last reset: which = 0 triangular-multiply
- * (variance), 1 mean/Jacobian generator, 2 factorisation trailing update.  Returns launches through *n. */
+ * (variance; FP64 DMMA or INT8-sliced, whichever mode is active), 1 mean/Jacobian generator, 2 factorisation trailing
+ * update, 3 digit split of the right-hand sides (INT8-sliced mode).  Returns launches through *n. */
 int gptb_kernel_time(gptb_handle* h, int which, double* ms, int64_t* n);
 int gptb_timing_enable(gptb_handle* h, int on);
 int gptb_timing_reset(gptb_handle* h);
