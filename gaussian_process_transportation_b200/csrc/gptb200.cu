@@ -567,6 +567,8 @@ extern "C" int gptb_set_affine(gptb_handle* h, const double* R, double s, const 
 // ---------------------------------------------------------------------------------------------------------------
 // queries
 // ---------------------------------------------------------------------------------------------------------------
+static bool oz_fused_supported(int d, int p) { return d == p && (d == 2 || d == 3); }
+
 template <int D, int P>
 static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_dev, int B, int Bpad, unsigned flags, int nrhs,
                        unsigned genflags, const QueryOut& out, long long q_off, long long Mtot, double* rhs, double* part,
@@ -577,10 +579,35 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
     af.on = (flags & GPTB_AFFINE_IN) ? h->af.on : 0;
     dim3 grid(Bpad / QPB, nsplit);
     tic(h, 1);
-    if (genflags)
-        kstar_kernel<D, P, true><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, B, Bpad, h->kp, af, genflags, rhs, xr, macc, nsplit);
-    else
-        kstar_kernel<D, P, false><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, B, Bpad, h->kp, af, 0u, rhs, xr, macc, nsplit);
+    // digit planes straight from the generator when the INT8-sliced path is on and this (d,p) has a fused instantiation
+    const bool fused = (nrhs > 0 && h->var_mode == 1 && oz_fused_supported(D, P));
+    int8_t* Aplanes = reinterpret_cast<int8_t*>(oz_planes);
+    if (fused) {
+        DigitScales ds{};
+        auto set = [&](int idx, double bound) {
+            int ex = 0;
+            std::frexp(bound, &ex);
+            ds.down[idx] = std::ldexp(1.0, -(ex + 1));
+            ds.scale[idx] = std::ldexp(1.0, ex + 1);
+        };
+        set(0, h->kp.c);                                               // k* <= c
+        for (int a = 0; a < D; ++a) {
+            set(1 + a, h->kp.c * h->kp.inv_ell[a]);                    // |dk*/dx_a| = k |dx_a|/ell_a^2 <= c/ell_a (r e^{-r^2/2} < 1)
+            set(1 + D + a, h->kp.c * (1.0 + h->kp.inv_ell[a]));
+        }
+        if constexpr (D == P && (D == 2 || D == 3)) {
+            dispatch_slices(h->var_slices, [&](auto SS) {
+                kstar_kernel<D, P, 2, decltype(SS)::value><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, B, Bpad, h->kp, af, genflags,
+                                                                                       nullptr, xr, macc, nsplit, Aplanes, rows_total * h->Npad, oz_scale, ds);
+            });
+        }
+    } else if (genflags) {
+        kstar_kernel<D, P, 1, 5><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, B, Bpad, h->kp, af, genflags, rhs, xr, macc, nsplit,
+                                                             nullptr, 0, nullptr, DigitScales{});
+    } else {
+        kstar_kernel<D, P, 0, 5><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, B, Bpad, h->kp, af, 0u, rhs, xr, macc, nsplit, nullptr,
+                                                             0, nullptr, DigitScales{});
+    }
     toc(h, 1);
     LAUNCH_CHECK(h);
     int Tpart = T;
@@ -589,14 +616,16 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
         const int S = h->var_slices;
         const int rowtiles = (int)(rows_total / TS);
         const int T64 = (int)(h->Npad / oz::ON);
-        int8_t* Aplanes = reinterpret_cast<int8_t*>(oz_planes);
         CUtensorMap mapAq;
         if (!make_plane_map(&mapAq, Aplanes, rows_total, h->Npad, S, oz::OM)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
-        tic(h, 3);
-        dispatch_slices(S, [&](auto SS) {
-            oz::slice_rows_kernel<decltype(SS)::value><<<(unsigned)rows_total, 256, 0, h->stream>>>(rhs, h->Npad, rows_total, (int)h->Npad, 0, Aplanes, rows_total * h->Npad, oz_scale);
-        });
-        toc(h, 3);
+        if (!fused) {
+            tic(h, 3);
+            dispatch_slices(S, [&](auto SS) {
+                oz::slice_rows_kernel<decltype(SS)::value><<<(unsigned)rows_total, 256, 0, h->stream>>>(rhs, h->Npad, rows_total, (int)h->Npad, 0, Aplanes, rows_total * h->Npad, oz_scale);
+            });
+            toc(h, 3);
+            h->launches++;
+        }
         tic(h, 0);
         dispatch_slices(S, [&](auto SS) {
             constexpr int SV = decltype(SS)::value;
@@ -608,7 +637,6 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
                 mapAq, h->mapBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1);
         });
         toc(h, 0);
-        h->launches++;
         LAUNCH_CHECK(h);
         Tpart = T64;
     } else if (nrhs > 0) {
@@ -667,7 +695,8 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     // batch size: bounded by the workspace for the right-hand-side rows (nrhs * Bpad * Npad doubles)
     long long Bmax;
     if (nrhs > 0) {
-        Bmax = h->ws_limit / (long long)((sizeof(double) + (ozaki ? h->var_slices : 0)) * nrhs * h->Npad);
+        const long long per_elem = ozaki ? (oz_fused_supported(d, p) ? h->var_slices : (long long)sizeof(double) + h->var_slices) : (long long)sizeof(double);
+        Bmax = h->ws_limit / (per_elem * nrhs * h->Npad);
         Bmax = Bmax / TS * TS;
         if (Bmax < TS) Bmax = TS;
         if (Bmax > 65536) Bmax = 65536;
@@ -681,11 +710,12 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     int nsplit = 1;
     {
         long long ctas = Bfirst / QPB;
-        while (ctas * nsplit < 296 && nsplit * 2 <= h->Npad / 32 && nsplit < 64) nsplit *= 2;
+        while (ctas * nsplit < 296 && nsplit * 2 <= h->Npad / 128 && nsplit < 64) nsplit *= 2;
     }
     size_t need = 0;
     auto carve = [&](size_t doubles) { size_t off = need; need += (doubles * sizeof(double) + 255) / 256 * 256; return off; };
-    size_t o_rhs = carve((size_t)nrhs * Bfirst * h->Npad);
+    const bool fused_planes = ozaki && oz_fused_supported(d, p);
+    size_t o_rhs = carve(fused_planes ? 0 : (size_t)nrhs * Bfirst * h->Npad);
     size_t o_part = carve((size_t)(nrhs > 0 ? (ozaki ? 2 * T : T) : 0) * nrhs * Bfirst);
     size_t o_ozp = carve(ozaki ? ((size_t)h->var_slices * nrhs * Bfirst * h->Npad + 7) / 8 : 0);
     size_t o_ozs = carve(ozaki ? (size_t)nrhs * Bfirst : 0);
@@ -714,7 +744,7 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
         int B = (int)((M - q0 < Bfirst) ? (M - q0) : Bfirst);
         int Bpad = (B + TS - 1) / TS * TS;
         const CUtensorMap* mapR = nullptr;
-        if (nrhs > 0) {
+        if (nrhs > 0 && !fused_planes) {
             // the right-hand-side rows of this batch: (nrhs * Bpad) x Npad, row-major in the workspace
             CUtensorMap* m = (Bpad == Bfirst) ? &mapR_full : &mapR_tail;
             if (Bpad != Bpad_mapped) {
@@ -786,7 +816,7 @@ static int cov_generate(gptb_handle* h, const double* x_dev, int M, int Mpad, do
     Affine af = h->af;
     af.on = 0;
     dim3 grid(Mpad / QPB, 1);
-    kstar_kernel<D, P, true><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, M, Mpad, h->kp, af, 1u, rhs, xr, macc, 1);
+    kstar_kernel<D, P, 1, 5><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, M, Mpad, h->kp, af, 1u, rhs, xr, macc, 1, nullptr, 0, nullptr, DigitScales{});
     LAUNCH_CHECK(h);
     QueryOut out{mean_dev, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     finalize_kernel<D, P><<<(M + 127) / 128, 128, 0, h->stream>>>(macc, 1, nullptr, h->T, M, Mpad, Mpad, xr, nullptr, h->kp, h->af, GPTB_MEAN, out, 0, M);

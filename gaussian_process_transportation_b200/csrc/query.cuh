@@ -13,7 +13,6 @@ struct Affine {
     double Tbar[MAXD];
 };
 
-constexpr int QPW = 1;          // queries per warp
 constexpr int QPB = 8;          // queries per CTA (8 warps)
 constexpr int TRMM_GR = 12;     // L2 blocking of the variance triangular multiply: row tiles per group
 constexpr int TRMM_GI = 12;     //                                                   inverse-factor row tiles per group
@@ -64,105 +63,172 @@ __device__ __forceinline__ double exp_neg(double x, const double* tab) {
 // split when the batch alone cannot fill 148 SMs, partial sums are reduced in a fixed order by finalize.
 // Roofline: FP64 pipe (DFMA issue) -- ~21 DFMA slots for exp + 3D+2 for the distance + P(1+D) accumulate per pair.
 // ------------------------------------------------------------------------------------------------------------
-template <int D, int P, bool STORE>
+// MODE 0: no right-hand-side rows (mean/Jacobian only); 1: FP64 rows into `rhs`; 2: int8 digit planes into `planes`
+// (INT8-sliced variance path, ozaki.cuh) -- the digits are produced here, straight from the freshly generated values,
+// with one power-of-two scale per row TYPE (k* <= c, |dk*/dx_a| <= c/ell_a, ...), so the FP64 rows never touch HBM.
+struct DigitScales {
+    double down[1 + 2 * MAXD];     // 2^-e per row type: 0 = k*, 1+a = dk*/dx_a, 1+D+a = k* + dk*/dx_a
+    double scale[1 + 2 * MAXD];    // 2^e
+};
+
+template <int S>
+__device__ __forceinline__ void emit_digits(const double (&val)[4], double down, int8_t* __restrict__ planes, long long plane_stride,
+                                            long long off) {
+    // same cascade as oz::slice_rows_kernel (error-free: scaling by powers of two, rint and the subtraction are exact)
+    unsigned packed[S];
+#pragma unroll
+    for (int t = 0; t < S; ++t) packed[t] = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        double y = val[j] * down;
+#pragma unroll
+        for (int t = 0; t < S; ++t) {
+            y *= 128.0;
+            const double dgt = rint(y);
+            y -= dgt;
+            packed[t] |= ((unsigned)(__double2int_rn(dgt)) & 0xffu) << (8 * j);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < S; ++t) *reinterpret_cast<unsigned*>(planes + (long long)t * plane_stride + off) = packed[t];
+}
+
+template <int D, int P, int MODE, int S>
 __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ xq, const double* __restrict__ Xs,
                                                     const double* __restrict__ alpha, int N, int Npad, int B, int Bpad,
                                                     KParams kp, Affine af, unsigned flags, double* __restrict__ rhs,
-                                                    double* __restrict__ xr, double* __restrict__ macc, int nsplit) {
+                                                    double* __restrict__ xr, double* __restrict__ macc, int nsplit,
+                                                    int8_t* __restrict__ planes, long long plane_stride, double* __restrict__ scaleA,
+                                                    DigitScales ds) {
     constexpr int NACC = P + P * D;
     __shared__ double etab[16];
     if (threadIdx.x < 16) etab[threadIdx.x] = c_exp2_16[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q0 = blockIdx.x * QPB + warp * QPW;
-    double xs[QPW][D];
-    bool valid[QPW];
-#pragma unroll
-    for (int qq = 0; qq < QPW; ++qq) {
-        int q = q0 + qq;
-        valid[qq] = q < B;
+    const int q = blockIdx.x * QPB + warp;             // one query per warp; lanes run over training points (4 each)
+    const bool valid = q < B;
+    double xs[D];
+    {
         double xin[D], xe[D];
 #pragma unroll
-        for (int a = 0; a < D; ++a) xin[a] = valid[qq] ? xq[(long long)q * D + a] : 0.0;
+        for (int a = 0; a < D; ++a) xin[a] = valid ? xq[(long long)q * D + a] : 0.0;
         if (af.on) {
 #pragma unroll
             for (int a = 0; a < D; ++a) {
-                double s = 0.0;
+                double sacc = 0.0;
 #pragma unroll
-                for (int b = 0; b < D; ++b) s += af.R[a][b] * (xin[b] - af.Sbar[b]);
-                xe[a] = af.s * s + af.Tbar[a];
+                for (int b = 0; b < D; ++b) sacc += af.R[a][b] * (xin[b] - af.Sbar[b]);
+                xe[a] = af.s * sacc + af.Tbar[a];
             }
         } else {
 #pragma unroll
             for (int a = 0; a < D; ++a) xe[a] = xin[a];
         }
 #pragma unroll
-        for (int a = 0; a < D; ++a) xs[qq][a] = xe[a] / kp.ell[a];
-        if (blockIdx.y == 0 && lane == 0 && valid[qq])
+        for (int a = 0; a < D; ++a) xs[a] = xe[a] / kp.ell[a];
+        if (blockIdx.y == 0 && lane == 0 && valid)
 #pragma unroll
             for (int a = 0; a < D; ++a) xr[(long long)q * D + a] = xe[a];
     }
-    double acc[QPW][NACC];
+    double acc[NACC];
 #pragma unroll
-    for (int qq = 0; qq < QPW; ++qq)
-#pragma unroll
-        for (int v = 0; v < NACC; ++v) acc[qq][v] = 0.0;
+    for (int v = 0; v < NACC; ++v) acc[v] = 0.0;
 
-    const bool st_k = STORE && (flags & 1u), st_g = STORE && (flags & 2u), st_kg = STORE && (flags & 4u);
-    const int per = ((Npad / 32 + nsplit - 1) / nsplit) * 32;
+    const bool st_k = MODE != 0 && (flags & 1u), st_g = MODE != 0 && (flags & 2u), st_kg = MODE != 0 && (flags & 4u);
+    if (MODE == 2 && blockIdx.y == 0 && lane == 0) {
+        if (st_k) scaleA[q] = ds.scale[0];
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            if (st_g) scaleA[(long long)(1 + a) * Bpad + q] = ds.scale[1 + a];
+            if (st_kg) scaleA[(long long)(1 + D + a) * Bpad + q] = ds.scale[1 + D + a];
+        }
+    }
+    const int per = ((Npad / 128 + nsplit - 1) / nsplit) * 128;
     const int nbeg = blockIdx.y * per;
     const int nend = min(Npad, nbeg + per);
-    for (int n = nbeg + lane; n < nend; n += 32) {
-        double xn[D], al[P];
+    for (int n0 = nbeg + 4 * lane; n0 < nend; n0 += 128) {
+        double xn[D][4], al[P][4];
 #pragma unroll
-        for (int a = 0; a < D; ++a) xn[a] = Xs[(long long)a * Npad + n];
+        for (int a = 0; a < D; ++a) {
+            const double2 u0 = *reinterpret_cast<const double2*>(Xs + (long long)a * Npad + n0);
+            const double2 u1 = *reinterpret_cast<const double2*>(Xs + (long long)a * Npad + n0 + 2);
+            xn[a][0] = u0.x; xn[a][1] = u0.y; xn[a][2] = u1.x; xn[a][3] = u1.y;
+        }
 #pragma unroll
-        for (int o = 0; o < P; ++o) al[o] = alpha[(long long)o * Npad + n];
-        const bool inb = n < N;
+        for (int o = 0; o < P; ++o) {
+            const double2 u0 = *reinterpret_cast<const double2*>(alpha + (long long)o * Npad + n0);
+            const double2 u1 = *reinterpret_cast<const double2*>(alpha + (long long)o * Npad + n0 + 2);
+            al[o][0] = u0.x; al[o][1] = u0.y; al[o][2] = u1.x; al[o][3] = u1.y;
+        }
+        double kv[4], gv[D][4];
 #pragma unroll
-        for (int qq = 0; qq < QPW; ++qq) {
-            double df[D], s = 0.0;
+        for (int j = 0; j < 4; ++j) {
+            double df[D], sacc = 0.0;
 #pragma unroll
             for (int a = 0; a < D; ++a) {
-                df[a] = xs[qq][a] - xn[a];
-                s += df[a] * df[a];
+                df[a] = xs[a] - xn[a][j];
+                sacc += df[a] * df[a];
             }
-            double k = (inb && valid[qq]) ? kp.c * kernel_profile(s, kp.kind, [&](double z) { return exp_neg(z, etab); }) : 0.0;
-            const long long row = (long long)(q0 + qq) * Npad + n;
-            if (STORE && st_k) rhs[row] = k;
+            const bool inb = (n0 + j) < N;
+            const double k = (inb && valid) ? kp.c * kernel_profile(sacc, kp.kind, [&](double z) { return exp_neg(z, etab); }) : 0.0;
+            kv[j] = k;
 #pragma unroll
-            for (int o = 0; o < P; ++o) acc[qq][o] = fma(k, al[o], acc[qq][o]);
+            for (int o = 0; o < P; ++o) acc[o] = fma(k, al[o][j], acc[o]);
 #pragma unroll
             for (int a = 0; a < D; ++a) {
-                double u = -k * df[a];                 // k * (X_a - x_a)/ell_a
-                if (STORE && (st_g | st_kg)) {
-                    double gval = u * kp.inv_ell[a];
-                    if (st_g) rhs[(long long)(1 + a) * Bpad * Npad + row] = gval;
-                    if (st_kg) rhs[(long long)(1 + D + a) * Bpad * Npad + row] = k + gval;
-                }
+                const double u = -k * df[a];                 // k * (X_a - x_a)/ell_a
+                gv[a][j] = u * kp.inv_ell[a];                // dk*/dx_a
 #pragma unroll
-                for (int o = 0; o < P; ++o) acc[qq][P + o * D + a] = fma(u, al[o], acc[qq][P + o * D + a]);
+                for (int o = 0; o < P; ++o) acc[P + o * D + a] = fma(u, al[o][j], acc[P + o * D + a]);
+            }
+        }
+        if (MODE == 1) {
+            const long long row = (long long)q * Npad + n0;
+            if (st_k) {
+                *reinterpret_cast<double2*>(rhs + row) = make_double2(kv[0], kv[1]);
+                *reinterpret_cast<double2*>(rhs + row + 2) = make_double2(kv[2], kv[3]);
+            }
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+                if (st_g) {
+                    double* dst = rhs + (long long)(1 + a) * Bpad * Npad + row;
+                    *reinterpret_cast<double2*>(dst) = make_double2(gv[a][0], gv[a][1]);
+                    *reinterpret_cast<double2*>(dst + 2) = make_double2(gv[a][2], gv[a][3]);
+                }
+                if (st_kg) {
+                    double* dst = rhs + (long long)(1 + D + a) * Bpad * Npad + row;
+                    *reinterpret_cast<double2*>(dst) = make_double2(kv[0] + gv[a][0], kv[1] + gv[a][1]);
+                    *reinterpret_cast<double2*>(dst + 2) = make_double2(kv[2] + gv[a][2], kv[3] + gv[a][3]);
+                }
+            }
+        } else if (MODE == 2) {
+            const long long off = (long long)q * Npad + n0;
+            if (st_k) emit_digits<S>(kv, ds.down[0], planes, plane_stride, off);
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+                if (st_g) emit_digits<S>(gv[a], ds.down[1 + a], planes, plane_stride, (long long)(1 + a) * Bpad * Npad + off);
+                if (st_kg) {
+                    const double kg[4] = {kv[0] + gv[a][0], kv[1] + gv[a][1], kv[2] + gv[a][2], kv[3] + gv[a][3]};
+                    emit_digits<S>(kg, ds.down[1 + D + a], planes, plane_stride, (long long)(1 + D + a) * Bpad * Npad + off);
+                }
             }
         }
     }
 #pragma unroll
-    for (int qq = 0; qq < QPW; ++qq) {
+    for (int v = 0; v < NACC; ++v) {
+        double x = acc[v];
 #pragma unroll
-        for (int v = 0; v < NACC; ++v) {
-            double x = acc[qq][v];
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        acc[v] = x;
+    }
+    if (lane == 0) {
+        double* dst = macc + ((long long)blockIdx.y * Bpad + q) * NACC;
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-            acc[qq][v] = x;
-        }
-        if (lane == 0) {
-            double* dst = macc + ((long long)blockIdx.y * Bpad + q0 + qq) * NACC;
+        for (int o = 0; o < P; ++o) dst[o] = acc[o];
 #pragma unroll
-            for (int o = 0; o < P; ++o) dst[o] = acc[qq][o];
+        for (int o = 0; o < P; ++o)
 #pragma unroll
-            for (int o = 0; o < P; ++o)
-#pragma unroll
-                for (int a = 0; a < D; ++a) dst[P + o * D + a] = acc[qq][P + o * D + a] * kp.inv_ell[a];
-        }
+            for (int a = 0; a < D; ++a) dst[P + o * D + a] = acc[P + o * D + a] * kp.inv_ell[a];
     }
 }
 
