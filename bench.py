@@ -377,8 +377,16 @@ def main():
             ops_per_launch = 2.0 * pairs * q_per_launch * Npad * (Npad + 64.0) / 2.0
             achieved = ops_per_launch / (avg_launch_ms * 1e-3) * 1e-12
             int8_peak, int8_src = measure_int8_peak(torch, dev)
+            traffic = None
+            try:   # DRAM bytes per launch from the committed ncu capture, only when it is the same launch shape
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ozaki_traffic.json")))
+                if tr["N"] == N and abs(tr["queries_per_launch"] - q_per_launch) < 1 and S_ == 6:
+                    traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            except Exception:
+                pass
             roofline = {"bound": "tensor", "kernel": f"ozaki_trmm_kernel<{S_}> (tcgen05.mma kind::i8, TMEM accumulators, {pairs} digit-plane products)",
-                        "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": achieved / int8_peak, "traffic": None,
+                        "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": achieved / int8_peak, "traffic": traffic,
+                        "traffic_unit": "bytes/launch (ncu dram read+write)",
                         "peak_source": int8_src, "algorithmic_ops_per_launch": ops_per_launch, "launch_ms": avg_launch_ms,
                         "fp64_equivalent_tflops": q_per_launch * Npad * (Npad + 64.0) / (avg_launch_ms * 1e-3) * 1e-12,
                         "fp64_dgemm_peak_tflops": dgemm_peak, "share_of_step": trmm_ms / ms_total,

@@ -488,6 +488,9 @@ static int build_bplanes(gptb_handle* h) {
     if (rc) return rc;
     const long long Npad = h->Npad;
     const int S = h->var_slices;
+    // exactness of the int32 accumulators: up to S digit-plane products of K terms, each |digit product| <= 2^12
+    if ((long long)S * Npad * 4096 > 2147483647LL)
+        GPTB_FAIL(h, -1, "INT8-sliced variance path: N=%lld with %d digit planes would overflow the int32 accumulators", (long long)h->N, S);
     if (h->Bplanes) { cudaFree(h->Bplanes); h->Bplanes = nullptr; }
     CU(h, cudaMalloc(&h->Bplanes, (size_t)S * Npad * Npad));
     if (!h->scaleB) CU(h, cudaMalloc(&h->scaleB, sizeof(double) * Npad));
