@@ -30,6 +30,7 @@ SYMBOLS = {
     "gptb_query": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_uint32, _dp] + [_dp] * 9),
     "gptb_query_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p] + [C.c_void_p] * 9),
     "gptb_query_cov": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp, _dp]),
+    "gptb_transport_orientation": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, _dp, _dp]),
     "gptb_export_L": (C.c_int, [C.c_void_p, _dp]),
     "gptb_export_alpha": (C.c_int, [C.c_void_p, _dp]),
     "gptb_export_Kinv": (C.c_int, [C.c_void_p, _dp]),
@@ -203,6 +204,17 @@ class Engine:
         if M:
             self._check(self.lib.gptb_query_cov(self.h, ptr(x), M, ptr(mean), ptr(cov)), "gptb_query_cov")
         return mean, cov
+
+    def transport_orientation(self, pos, ori):
+        """q_hat = quat(Jphi(pos)) (x) ori on the device; returns (ori_out (M,4), jphi (M,3,3))."""
+        pos, ori = as_f64(pos), as_f64(ori)
+        M = pos.shape[0]
+        if pos.shape != (M, 3) or ori.shape != (M, 4):
+            raise ValueError(f"orientation transport needs pos (M,3) and ori (M,4), got {pos.shape} and {ori.shape}")
+        out, jphi = np.empty((M, 4)), np.empty((M, 3, 3))
+        if M:
+            self._check(self.lib.gptb_transport_orientation(self.h, ptr(pos), ptr(ori), M, ptr(out), ptr(jphi)), "gptb_transport_orientation")
+        return out, jphi
 
     def query_dev(self, x_ptr, M, flags, vel_ptr=0, mean=0, std=0, jac=0, jacvar=0, xhat=0, vhat=0, vvar=0, jphi=0, dvar=0):
         rc = self.lib.gptb_query_dev(self.h, x_ptr, M, int(flags), vel_ptr or None, mean or None, std or None, jac or None, jacvar or None,

@@ -891,6 +891,48 @@ extern "C" int gptb_query_cov(gptb_handle* h, const double* x, int64_t M, double
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// orientation transport
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int gptb_transport_orientation(gptb_handle* h, const double* pos, const double* ori, int64_t M, double* ori_out, double* jphi) {
+    if (!h || M < 0) return -1;
+    if (M == 0) return 0;
+    if (!pos || !ori || !ori_out) return -1;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->have_alpha) GPTB_FAIL(h, -1, "gptb_transport_orientation: model is not fitted");
+    if (h->d != 3 || h->p != 3) GPTB_FAIL(h, -1, "orientation transport needs a 3-D map (d = p = 3), got d=%d p=%d", h->d, h->p);
+    double *pd = nullptr, *od = nullptr, *jd = nullptr, *jp = nullptr, *qd = nullptr;
+    auto cleanup = [&]() {
+        for (double* q : {pd, od, jd, jp, qd})
+            if (q) cudaFree(q);
+    };
+    auto fail = [&](cudaError_t e, int line) {
+        cleanup();
+        char b[256];
+        snprintf(b, sizeof(b), "CUDA error %s at %s:%d", cudaGetErrorString(e), __FILE__, line);
+        h->err = b;
+        return -2;
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&pd, sizeof(double) * M * 3)) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMalloc(&od, sizeof(double) * M * 4)) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMalloc(&jd, sizeof(double) * M * 9)) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMalloc(&jp, sizeof(double) * M * 9)) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMalloc(&qd, sizeof(double) * M * 4)) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMemcpyAsync(pd, pos, sizeof(double) * M * 3, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMemcpyAsync(od, ori, sizeof(double) * M * 4, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return fail(e, __LINE__);
+    int rc = gptb_query_dev(h, pd, M, GPTB_JAC | GPTB_JPHI, nullptr, nullptr, nullptr, jd, nullptr, nullptr, nullptr, nullptr, jp, nullptr);
+    if (rc) { cleanup(); return rc; }
+    quat_transport_kernel<<<(unsigned)((M + 127) / 128), 128, 0, h->stream>>>(jp, od, M, qd);
+    h->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMemcpyAsync(ori_out, qd, sizeof(double) * M * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) return fail(e, __LINE__);
+    if (jphi && (e = cudaMemcpyAsync(jphi, jp, sizeof(double) * M * 9, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return fail(e, __LINE__);
+    cleanup();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // exports
 // ---------------------------------------------------------------------------------------------------------------
 static int export_square(gptb_handle* h, const double* src, double* dst, bool lower_only) {

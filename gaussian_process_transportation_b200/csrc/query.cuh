@@ -478,4 +478,101 @@ __global__ void __launch_bounds__(128) finalize_kernel(const double* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Orientation epilogue (policy_transportation.py:61-77): q_hat = quat(Jphi) (x) q, with quat() the Bar-Itzhack
+// quaternion of a possibly non-orthogonal 3x3 matrix (numpy-quaternion's from_rotation_matrix(nonorthogonal=True)):
+// dominant eigenvector of the symmetric 4x4 matrix K3, found here with cyclic Jacobi rotations (one thread per point,
+// everything in registers).  Quaternions are (w, x, y, z); the eigenvector sign is normalised to w >= 0.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) quat_transport_kernel(const double* __restrict__ jphi, const double* __restrict__ ori, long long M,
+                                                             double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    double R[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) R[r][c] = jphi[i * 9 + r * 3 + c];
+    double A[4][4];
+    A[0][0] = (R[0][0] - R[1][1] - R[2][2]) / 3.0;
+    A[0][1] = (R[1][0] + R[0][1]) / 3.0;
+    A[0][2] = (R[2][0] + R[0][2]) / 3.0;
+    A[0][3] = (R[1][2] - R[2][1]) / 3.0;
+    A[1][1] = (R[1][1] - R[0][0] - R[2][2]) / 3.0;
+    A[1][2] = (R[2][1] + R[1][2]) / 3.0;
+    A[1][3] = (R[2][0] - R[0][2]) / 3.0;
+    A[2][2] = (R[2][2] - R[0][0] - R[1][1]) / 3.0;
+    A[2][3] = (R[0][1] - R[1][0]) / 3.0;
+    A[3][3] = (R[0][0] + R[1][1] + R[2][2]) / 3.0;
+#pragma unroll
+    for (int r = 1; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < r; ++c) A[r][c] = A[c][r];
+    double V[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) V[r][c] = (r == c) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 24; ++sweep) {
+        double off = 0.0, diag = 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            diag += A[r][r] * A[r][r];
+#pragma unroll
+            for (int c = r + 1; c < 4; ++c) off += A[r][c] * A[r][c];
+        }
+        if (off <= 1e-34 * (diag + off)) break;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                const double apq = A[p][q];
+                if (apq != 0.0) {
+                    const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {           // A <- A J
+                        const double akp = A[k][p], akq = A[k][q];
+                        A[k][p] = c * akp - sn * akq;
+                        A[k][q] = sn * akp + c * akq;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {           // A <- J^T A
+                        const double apk = A[p][k], aqk = A[q][k];
+                        A[p][k] = c * apk - sn * aqk;
+                        A[q][k] = sn * apk + c * aqk;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {           // V <- V J
+                        const double vkp = V[k][p], vkq = V[k][q];
+                        V[k][p] = c * vkp - sn * vkq;
+                        V[k][q] = sn * vkp + c * vkq;
+                    }
+                }
+            }
+    }
+    int best = 0;
+#pragma unroll
+    for (int r = 1; r < 4; ++r)
+        if (A[r][r] > A[best][best]) best = r;
+    double e[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        double v = V[r][0];
+        if (best == 1) v = V[r][1];
+        if (best == 2) v = V[r][2];
+        if (best == 3) v = V[r][3];
+        e[r] = v;
+    }
+    double nrm = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3]);
+    double sgn = (e[3] < 0.0) ? -1.0 / nrm : 1.0 / nrm;
+    const double aw = e[3] * sgn, ax = -e[0] * sgn, ay = -e[1] * sgn, az = -e[2] * sgn;
+    const double bw = ori[i * 4 + 0], bx = ori[i * 4 + 1], by = ori[i * 4 + 2], bz = ori[i * 4 + 3];
+    out[i * 4 + 0] = aw * bw - ax * bx - ay * by - az * bz;
+    out[i * 4 + 1] = aw * bx + ax * bw + ay * bz - az * by;
+    out[i * 4 + 2] = aw * by - ax * bz + ay * bw + az * bx;
+    out[i * 4 + 3] = aw * bz + ax * by - ay * bx + az * bw;
+}
+
 }  // namespace gptb

@@ -81,6 +81,12 @@ class PolicyTransportation():
         return J_gamma + J_phi @ J_gamma
 
     def transport_orientation(self, pos, ori):
+        if self._fused and np.shape(pos)[1] == 3 and self.delta_map.n_outputs == 3:
+            # Jacobian, Jphi = R + Jpsi R, the 4x4 eigen-problem and the Hamilton product all run on the GPU
+            self.delta_map._ensure_fitted_factor()
+            ori_out, J_phi = self.delta_map._engine.transport_orientation(pos, ori)
+            print("Is the map locally diffeomorphic?", np.all(np.linalg.det(J_phi) > 0))
+            return ori_out
         J_phi = self._jphi_unrotated(pos)
         print("Is the map locally diffeomorphic?", np.all(np.linalg.det(J_phi) > 0))
         if J_phi[0].shape[0] == 3:

@@ -103,6 +103,11 @@ int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, uint32_t flag
  * The covariance is output-independent (the host replicates it over p as sklearn does). */
 int gptb_query_cov(gptb_handle* h, const double* x, int64_t M, double* mean, double* cov);
 
+/* ---- orientation transport (policy_transportation.py:61-77): Jphi = R + Jpsi(pos) R evaluated at the UN-rotated positions
+ * (the reference's behaviour), q_hat = quat(Jphi) (x) q with the Bar-Itzhack quaternion of the non-orthogonal 3x3 Jphi.
+ * pos (M,3), ori (M,4) as (w,x,y,z) in; ori_out (M,4); jphi (M,3,3) optional (may be NULL).  Needs d == p == 3. */
+int gptb_transport_orientation(gptb_handle* h, const double* pos, const double* ori, int64_t M, double* ori_out, double* jphi);
+
 /* ---- read-back of fitted state (GaussianProcess attributes `gp.L_`, `gp.alpha_`, `K_inv`; gaussian_process.py:42-43).
  * L is (N,N) lower (upper part zero), alpha is (N,p), Kinv is (N,N) symmetric. */
 int gptb_export_L(gptb_handle* h, double* L);
