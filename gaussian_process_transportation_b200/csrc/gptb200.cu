@@ -517,7 +517,7 @@ static int build_kinv(gptb_handle* h) {
 extern "C" int gptb_prepare_variance(gptb_handle* h) {
     if (!h) return -1;
     CU(h, cudaSetDevice(h->device));
-    int rc = build_minv(h);
+    int rc = (h->var_mode == 1) ? build_bplanes(h) : build_minv(h);
     if (rc) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
@@ -762,15 +762,12 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     return 0;
 }
 
-extern "C" int gptb_query(gptb_handle* h, const double* x, int64_t M, uint32_t flags, const double* vel, double* mean, double* std,
-                          double* jac, double* jacvar, double* xhat, double* vhat, double* vvar, double* jphi, double* dvar) {
-    if (!h || M < 0) return -1;
-    if (M == 0) return 0;
-    if (!x) return -1;
-    CU(h, cudaSetDevice(h->device));
+// Host-pointer query: staged through device buffers in slices of at most HOST_CHUNK points so that arbitrarily long
+// query streams (BASELINE configs 4/5: 2^26 .. 2^29 points) never need more than ~1 GB of staging.
+static int query_host_chunk(gptb_handle* h, const double* x, int64_t M, uint32_t flags, const double* vel, double* mean, double* std,
+                            double* jac, double* jacvar, double* xhat, double* vhat, double* vvar, double* jphi, double* dvar,
+                            int64_t dvar_ld) {
     const int d = h->d, p = h->p;
-    if (d < 1) GPTB_FAIL(h, -1, "gptb_query: model is not fitted");
-    // staging layout (doubles per query)
     struct Seg { const double* hin; double* hout; size_t per; size_t off; };
     Seg segs[11] = {{x, nullptr, (size_t)d, 0},
                     {(flags & GPTB_VELOCITY) ? vel : nullptr, nullptr, (size_t)d, 0},
@@ -783,12 +780,11 @@ extern "C" int gptb_query(gptb_handle* h, const double* x, int64_t M, uint32_t f
                     {nullptr, ((flags & GPTB_VELOCITY) && (flags & GPTB_JACVAR)) ? vvar : nullptr, (size_t)p, 0},
                     {nullptr, (flags & GPTB_JPHI) ? jphi : nullptr, (size_t)d * d, 0},
                     {nullptr, (flags & GPTB_DVAR) ? dvar : nullptr, (size_t)d, 0}};
-    if ((flags & GPTB_VELOCITY) && !vel) GPTB_FAIL(h, -1, "GPTB_VELOCITY without vel");
     size_t tot = 0;
-    for (auto& s : segs) {
-        if (s.hin || s.hout) {
-            s.off = tot;
-            tot += (s.per * (size_t)M * sizeof(double) + 255) / 256 * 256;
+    for (auto& sg : segs) {
+        if (sg.hin || sg.hout) {
+            sg.off = tot;
+            tot += (sg.per * (size_t)M * sizeof(double) + 255) / 256 * 256;
         }
     }
     if (tot > h->stage_bytes) {
@@ -805,9 +801,32 @@ extern "C" int gptb_query(gptb_handle* h, const double* x, int64_t M, uint32_t f
         if (segs[i].hin) CU(h, cudaMemcpyAsync(dp(i), segs[i].hin, segs[i].per * M * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     int rc = gptb_query_dev(h, dp(0), M, flags, dp(1), dp(2), dp(3), dp(4), dp(5), dp(6), dp(7), dp(8), dp(9), dp(10));
     if (rc) return rc;
-    for (int i = 2; i < 11; ++i)
+    for (int i = 2; i < 10; ++i)
         if (segs[i].hout) CU(h, cudaMemcpyAsync(segs[i].hout, dp(i), segs[i].per * M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (segs[10].hout)   // dvar is (d, Mtotal): this slice fills columns [0, M) of each row
+        CU(h, cudaMemcpy2DAsync(dvar, sizeof(double) * dvar_ld, dp(10), sizeof(double) * M, sizeof(double) * M, d, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int gptb_query(gptb_handle* h, const double* x, int64_t M, uint32_t flags, const double* vel, double* mean, double* std,
+                          double* jac, double* jacvar, double* xhat, double* vhat, double* vvar, double* jphi, double* dvar) {
+    if (!h || M < 0) return -1;
+    if (M == 0) return 0;
+    if (!x) return -1;
+    CU(h, cudaSetDevice(h->device));
+    const int d = h->d, p = h->p;
+    if (d < 1) GPTB_FAIL(h, -1, "gptb_query: model is not fitted");
+    if ((flags & GPTB_VELOCITY) && !vel) GPTB_FAIL(h, -1, "GPTB_VELOCITY without vel");
+    const int64_t HOST_CHUNK = 1 << 22;
+    for (int64_t q0 = 0; q0 < M; q0 += HOST_CHUNK) {
+        const int64_t m = (M - q0 < HOST_CHUNK) ? (M - q0) : HOST_CHUNK;
+        auto at = [&](double* ptr, size_t per) -> double* { return ptr ? ptr + (size_t)q0 * per : nullptr; };
+        int rc = query_host_chunk(h, x + q0 * d, m, flags, vel ? vel + q0 * d : nullptr, at(mean, p), at(std, p), at(jac, (size_t)p * d),
+                                  at(jacvar, (size_t)p * d), at(xhat, d), at(vhat, d), at(vvar, p), at(jphi, (size_t)d * d),
+                                  dvar ? dvar + q0 : nullptr, M);
+        if (rc) return rc;
+    }
     return 0;
 }
 

@@ -240,19 +240,22 @@ __global__ void __launch_bounds__(OTHREADS, 1) ozaki_trmm_kernel(const __grid_co
                 double v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = 0.0;
+                uint32_t r[S][16];
 #pragma unroll
-                for (int d = 0; d < S; ++d) {
-                    uint32_t r[16];
+                for (int d = 0; d < S; ++d) {          // all S diagonals of this column block in flight, one wait
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(d * ON + cb * 16);
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "=r"(r[d][0]), "=r"(r[d][1]), "=r"(r[d][2]), "=r"(r[d][3]), "=r"(r[d][4]), "=r"(r[d][5]), "=r"(r[d][6]), "=r"(r[d][7]),
+                          "=r"(r[d][8]), "=r"(r[d][9]), "=r"(r[d][10]), "=r"(r[d][11]), "=r"(r[d][12]), "=r"(r[d][13]), "=r"(r[d][14]), "=r"(r[d][15])
                         : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+                for (int d = 0; d < S; ++d) {
                     const double w = ldexp(1.0, -DIGIT_BITS * (d + 2));   // digits are 1-based: weight 2^-7(a+b), a+b = d+2
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fma((double)(int)r[j], w, v[j]);
+                    for (int j = 0; j < 16; ++j) v[j] = fma((double)(int)r[d][j], w, v[j]);
                 }
                 if (cb == ON / 16 - 1) {
                     // every accumulator column of this tile has been read: let the MMA thread start the next tile
