@@ -42,6 +42,7 @@ SYMBOLS = {
     "gptb_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "gptb_timing_reset": (C.c_int, [C.c_void_p]),
     "gptb_stream": (C.c_void_p, [C.c_void_p]),
+    "gptb_set_trailing_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "gptb_set_workspace_limit": (C.c_int, [C.c_void_p, C.c_int64]),
     "gptb_test_gemm_nt": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gptb_test_potrf_tile": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.POINTER(C.c_int)]),
@@ -254,6 +255,9 @@ class Engine:
 
     def stream(self):
         return self.lib.gptb_stream(self.h)
+
+    def set_trailing_variant(self, variant):
+        self._check(self.lib.gptb_set_trailing_variant(self.h, int(variant)), "gptb_set_trailing_variant")
 
     def set_workspace_limit(self, nbytes):
         self._check(self.lib.gptb_set_workspace_limit(self.h, int(nbytes)), "gptb_set_workspace_limit")

@@ -404,6 +404,150 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_trailing_kernel(const _
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Trailing update, half-tile variant: the same rank-128k SYRK with 128 x 64 output tiles, 4 consumer warps + 1 TMA
+// producer warp per CTA, a 2-stage 48 KB ring -- so TWO CTAs fit on an SM and one CTA's read-modify-write epilogue
+// runs underneath the other CTA's DMMA stream (with one 128 x 128 CTA per SM the pipe idled ~19 % of the time during
+// the epilogues; profiles/r01_trailing_v1_ncu_key_metrics.txt).  Jobs come from a global atomic queue; a CTA that
+// lands on the reserved SM exits at once, which keeps that SM free for the look-ahead diagonal-tile kernel.
+//   mode 0: lower triangle of tiles base <= j <= i < T, two column halves each;  mode 1: tile column j = base.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int H_BN = 64;
+constexpr int H_CONS = 128;                       // 4 consumer warps: 2 (m) x 2 (n), warp tile 64 x 32
+constexpr int H_THREADS = H_CONS + 32;
+constexpr int H_NSTAGE = 2;
+constexpr int H_STAGE_DOUBLES = (TS + H_BN) * BK;
+constexpr int H_SMEM_BYTES = H_NSTAGE * H_STAGE_DOUBLES * 8;   // 96 KB
+
+__device__ __forceinline__ unsigned smid() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+
+__global__ void __launch_bounds__(H_THREADS, 2) potrf_trailing64_kernel(const __grid_constant__ CUtensorMap mapL,
+                                                                       const __grid_constant__ CUtensorMap mapL64,
+                                                                       double* __restrict__ Lbuf, long long ld, int k0, int k1, int base,
+                                                                       int mode, int njobs, int* __restrict__ job_counter,
+                                                                       int reserved_sm) {
+    extern __shared__ __align__(128) double smem[];
+    __shared__ __align__(8) uint64_t full[H_NSTAGE], empty[H_NSTAGE], slot_full[2], slot_empty[2];
+    __shared__ int job_slot[2];
+    if ((int)smid() == reserved_sm) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < H_NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], H_CONS / 32); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], H_CONS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    auto decode = [&](int job, int& ti, int& tj, int& half) {
+        half = job & 1;
+        const int tjob = job >> 1;
+        if (mode == 0) {
+            int a, b;
+            tri_decode(tjob, a, b);
+            ti = base + a;
+            tj = base + b;
+        } else {
+            ti = base + tjob;
+            tj = base;
+        }
+    };
+    const int nslab = (k1 - k0) * SLABS_PER_TILE, s0 = k0 * SLABS_PER_TILE;
+    if (warp == H_CONS / 32) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            int gs = 0;
+            for (int lt = 0;; ++lt) {
+                if (lt >= 2) mbar_wait(&slot_empty[lt & 1], ((lt >> 1) - 1) & 1);
+                int job = atomicAdd(job_counter, 1);
+                if (job >= njobs) job = -1;
+                job_slot[lt & 1] = job;
+                mbar_arrive(&slot_full[lt & 1]);
+                if (job < 0) break;
+                int ti, tj, half;
+                decode(job, ti, tj, half);
+                const int brow = tj * TS + half * H_BN;
+                for (int it = 0; it < nslab + 2; ++it, ++gs) {
+                    const int st = gs % H_NSTAGE;
+                    if (gs >= H_NSTAGE) mbar_wait(&empty[st], ((gs / H_NSTAGE) - 1) & 1);
+                    double* sA = smem + st * H_STAGE_DOUBLES;
+                    double* sB = sA + SLAB_DOUBLES;
+                    if (it < nslab) {
+                        const int kel = (s0 + it) * BK;
+                        mbar_expect_tx(&full[st], H_STAGE_DOUBLES * 8);
+                        tma_load_3d(sA, &mapL, 0, ti * TS, kel >> 2, &full[st]);
+                        tma_load_3d(sB, &mapL64, 0, brow, kel >> 2, &full[st]);
+                    } else {
+                        // old values of the output half tile: 32 columns per ring entry, staged like an A slab
+                        mbar_expect_tx(&full[st], SLAB_DOUBLES * 8);
+                        tma_load_3d(sA, &mapL, 0, ti * TS, (brow + 32 * (it - nslab)) >> 2, &full[st]);
+                    }
+                }
+            }
+        }
+        return;
+    }
+    // ---------------- consumers ----------------
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    int gs = 0;
+    for (int lt = 0;; ++lt) {
+        mbar_wait(&slot_full[lt & 1], (lt >> 1) & 1);
+        const int job = job_slot[lt & 1];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&slot_empty[lt & 1]);
+        if (job < 0) break;
+        int ti, tj, half;
+        decode(job, ti, tj, half);
+        double acc[8][4][2];
+        acc_clear(acc);
+        for (int it = 0; it < nslab; ++it, ++gs) {
+            const int st = gs % H_NSTAGE;
+            mbar_wait(&full[st], (gs / H_NSTAGE) & 1);
+            const double* sA = smem + st * H_STAGE_DOUBLES;
+            const double* sB = sA + SLAB_DOUBLES;
+            const double* pa = sA + ((wm * 64 + g) << 2) + t;
+            const double* pbf = sB + ((wn * 32 + g) << 2) + t;
+#pragma unroll
+            for (int kg = 0; kg < BK / 4; ++kg) {
+                double a[8], b[4];
+#pragma unroll
+                for (int mi = 0; mi < 8; ++mi) a[mi] = pa[(kg * TS + mi * 8) << 2];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) b[ni] = pbf[(kg * H_BN + ni * 8) << 2];
+#pragma unroll
+                for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+        double* out = Lbuf + (long long)ti * TS * ld + (long long)tj * TS + half * H_BN;
+        for (int e = 0; e < 2; ++e, ++gs) {
+            const int st = gs % H_NSTAGE;
+            mbar_wait(&full[st], (gs / H_NSTAGE) & 1);
+            if (wn == e) {
+                const double* box = smem + st * H_STAGE_DOUBLES;      // [c/4][row][c%4], 32 columns of this warp
+#pragma unroll
+                for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) {
+                        const int r = wm * 64 + mi * 8 + g;
+                        const int kg = ni * 2 + (t >> 1), off = (2 * t) & 3;
+                        const double2 old = *reinterpret_cast<const double2*>(box + (((kg * TS) + r) << 2) + off);
+                        *reinterpret_cast<double2*>(out + (long long)r * ld + wn * 32 + ni * 8 + 2 * t) =
+                            make_double2(old.x - acc[mi][ni][0], old.y - acc[mi][ni][1]);
+                    }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Back substitution alpha = L^-T z (the forward half z = L^-1 y is fused into the factorisation above), block by block
 // from the last tile:  step k:  alpha_k = Dinv_k^T z_k
 //                               z_j -= L[k,j]^T alpha_k  for j < k   (one CTA per tile j; reads the 128x128 tile of the

@@ -33,12 +33,12 @@ EncodeTiledFn get_encoder() {
 
 // 3-D TMA view (4, rows, K/4) of a row-major FP64 matrix (rows x K, leading dimension ld): box (4, 128, BK/4) lands in
 // shared memory as [k/4][row][k%4], the conflict-free fragment layout of gemm_engine.cuh.
-bool make_operand_map(CUtensorMap* m, const double* base, long long rows, long long K, long long ld) {
+bool make_operand_map(CUtensorMap* m, const double* base, long long rows, long long K, long long ld, int box_rows = TS) {
     EncodeTiledFn enc = get_encoder();
     if (!enc) return false;
     cuuint64_t dims[3] = {4, (cuuint64_t)rows, (cuuint64_t)(K / 4)};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 8, 32};
-    cuuint32_t box[3] = {4, (cuuint32_t)TS, (cuuint32_t)(BK / 4)};
+    cuuint32_t box[3] = {4, (cuuint32_t)box_rows, (cuuint32_t)(BK / 4)};
     cuuint32_t es[3] = {1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -72,8 +72,10 @@ struct gptb_handle {
     double* header = nullptr;
     int* info = nullptr;
     CUtensorMap mapL, mapD, mapM, mapW;      // TMA views of Lbuf, Dinv, Minv, Wbuf
+    CUtensorMap mapL64;                      // Lbuf with a 64-row box (half-tile trailing update)
     // INT8-sliced variance path (ozaki.cuh): digit planes of the inverse factor + per-row scales
     int var_mode = 0, var_slices = 6;
+    int trailing_variant = 1;                // 0: 128x128 tiles, one CTA/SM; 1: 128x64 half tiles, two CTAs/SM
     int8_t* Bplanes = nullptr;
     double* scaleB = nullptr;
     CUtensorMap mapBq;
@@ -149,6 +151,7 @@ static int set_kernel_attrs(gptb_handle* h) {
     CU(h, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(potrf_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(potrf_trailing64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(trtri_level_p1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(trtri_level_p2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(kinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -216,6 +219,11 @@ extern "C" void gptb_destroy(gptb_handle* h) {
 extern "C" const char* gptb_last_error(gptb_handle* h) { return h ? h->err.c_str() : "null handle"; }
 extern "C" int64_t gptb_launch_count(gptb_handle* h) { return h ? h->launches : 0; }
 extern "C" void* gptb_stream(gptb_handle* h) { return h ? (void*)h->stream : nullptr; }
+extern "C" int gptb_set_trailing_variant(gptb_handle* h, int variant) {
+    if (!h || variant < 0 || variant > 1) return -1;
+    h->trailing_variant = variant;
+    return 0;
+}
 extern "C" int gptb_set_workspace_limit(gptb_handle* h, int64_t bytes) {
     if (!h || bytes < (1 << 20)) return -1;
     h->ws_limit = bytes;
@@ -263,6 +271,7 @@ static int alloc_model(gptb_handle* h, long long N, int d, int p, bool train) {
             CU(h, cudaMalloc(&h->Lbuf, sizeof(double) * Npad * Npad));
             CU(h, cudaMalloc(&h->Dinv, sizeof(double) * Npad * TS));
             MAKE_MAP(h, &h->mapL, h->Lbuf, Npad, Npad, Npad);
+            if (!make_operand_map(&h->mapL64, h->Lbuf, Npad, Npad, Npad, H_BN)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed (64-row box)");
             MAKE_MAP(h, &h->mapD, h->Dinv, Npad, TS, TS);
         }
     }
@@ -383,10 +392,21 @@ static int factorize_device(gptb_handle* h) {
         if (r > 1) {
             const int r2 = r - 1;
             const int njobs = r2 * (r2 + 1) / 2;
-            const int grid = njobs < nsm - 1 ? njobs : nsm - 1;
-            tic(h, 2);
-            potrf_trailing_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->Lbuf, ld, kt, kt + 1, kt + 2, 0, njobs);
-            toc(h, 2);
+            if (h->trailing_variant == 0) {
+                const int grid = njobs < nsm - 1 ? njobs : nsm - 1;
+                tic(h, 2);
+                potrf_trailing_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->Lbuf, ld, kt, kt + 1, kt + 2, 0, njobs);
+                toc(h, 2);
+            } else {
+                // half tiles, two CTAs per SM, dynamic queue; SM nsm-1 stays free for the look-ahead diagonal tile
+                const int njobs2 = 2 * njobs;
+                const int grid = njobs2 < 2 * nsm ? njobs2 : 2 * nsm;
+                CU(h, cudaMemsetAsync(h->info + 2, 0, sizeof(int), h->stream));
+                tic(h, 2);
+                potrf_trailing64_kernel<<<grid, H_THREADS, H_SMEM_BYTES, h->stream>>>(h->mapL, h->mapL64, h->Lbuf, ld, kt, kt + 1, kt + 2, 0, njobs2, h->info + 2,
+                                                                                    njobs2 > 2 * (nsm - 1) ? nsm - 1 : -1);
+                toc(h, 2);
+            }
             LAUNCH_CHECK(h);
         }
     }

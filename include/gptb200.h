@@ -135,6 +135,9 @@ int gptb_timing_enable(gptb_handle* h, int on);
 int gptb_timing_reset(gptb_handle* h);
 /* stream the handle launches on (cudaStream_t as void*), so callers can record events on it. */
 void* gptb_stream(gptb_handle* h);
+/* schedule of the Cholesky trailing update: 0 = 128x128 tiles, one persistent CTA per SM; 1 (default) = 128x64 half tiles,
+ * two CTAs per SM with a dynamic job queue (tuning / A-B measurement knob; results are bit-identical). */
+int gptb_set_trailing_variant(gptb_handle* h, int variant);
 /* workspace cap for query batches in bytes (default 8 GiB). */
 int gptb_set_workspace_limit(gptb_handle* h, int64_t bytes);
 
