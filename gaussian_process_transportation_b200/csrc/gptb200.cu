@@ -447,7 +447,7 @@ extern "C" int gptb_factorize(gptb_handle* h, double c, const double* ell, doubl
     CU(h, cudaSetDevice(h->device));
     int rc = set_params(h, c, ell, s2, jitter);
     if (rc) return rc;
-    h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = false;
+    h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = h->have_bplanes = false;
     if ((rc = factorize_device(h))) return rc;
     if ((rc = solve_alpha(h))) return rc;
     h->have_factor = h->have_alpha = true;
@@ -503,7 +503,8 @@ static void dispatch_slices(int S, F f) {
 
 // digit planes of the inverse factor for the INT8-sliced variance path
 static int build_bplanes(gptb_handle* h) {
-    if (h->have_bplanes) return 0;
+    if (h->have_bplanes && h->have_minv) return 0;      // a refit invalidates the inverse factor and with it the planes
+    h->have_bplanes = false;
     int rc = build_minv(h);
     if (rc) return rc;
     const long long Npad = h->Npad;

@@ -412,3 +412,23 @@ def test_int8_sliced_full_size_n4096():
     assert np.max(np.abs(o["std"] - ref["std"])) / np.sqrt(0.1 + 1e-4) < 2e-8
     with pytest.raises(L.GptbError):
         eng.set_variance_mode(1, 4)
+
+
+def test_refit_invalidates_cached_inverse_factor_and_digit_planes():
+    """A second fit on the same handle must not reuse the inverse factor / int8 digit planes of the first one."""
+    from gaussian_process_transportation_b200 import _lib as L
+    from oracle.gp_oracle import ChoGP, synthetic_pairs
+    S1, T1 = synthetic_pairs(300, 3, seed=1)
+    S2, T2 = synthetic_pairs(300, 3, seed=2)
+    xq = np.random.default_rng(0).random((200, 3))
+    for mode in (0, 1):
+        eng = L.Engine(0)
+        eng.set_variance_mode(mode, 6)
+        eng.set_train(S1, T1 - S1); eng.factorize(0.1, [0.1] * 3, 1e-4, 1e-10)
+        eng.query(xq, L.MEAN | L.STD)
+        eng.set_train(S2, T2 - S2); eng.factorize(0.2, [0.15] * 3, 1e-3, 1e-10)
+        o = eng.query(xq, L.MEAN | L.STD | L.JACVAR | L.JAC)
+        ora = ChoGP(0.2, [0.15] * 3, 1e-3).fit(S2, T2 - S2)
+        m, sd = ora.predict(xq, return_std=True)
+        assert rel(o["mean"], m) < TOL_MEAN
+        assert np.max(np.abs(o["std"] - sd)) / np.sqrt(0.2 + 1e-3) < TOL_STD
