@@ -84,3 +84,21 @@ def test_quaternion_helpers_match_oracle():
     assert np.max(np.abs(a * s - b)) < 1e-12
     q = rng.standard_normal((30, 4))
     assert np.allclose(multiply(a, q), quat_mul(a, q))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) prints one JSON line with the
+    contract keys; smallest workload so the CPU suite stays fast."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ["impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"]:
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
