@@ -220,9 +220,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--queries", type=int, default=0, help="override queries per step per GPU")
-    ap.add_argument("--variance", default="int8x6", choices=["fp64", "int8x5", "int8x6", "int8x7"],
+    ap.add_argument("--variance", default="int8w5", choices=["fp64", "int8x5", "int8x6", "int8x7", "int8w4", "int8w5", "int8w6"],
                     help="evaluation of the predictive-variance products: FP64 DMMA tile engine, or the INT8-sliced tcgen05 path "
-                         "(exact int32 digit-plane GEMMs, FP64 recombination; 6 planes keep std within ~2e-9 of the FP64 path)")
+                         "(exact int32 digit-plane GEMMs, FP64 recombination): int8xS = S 7-bit digit planes (6 keep std within ~2e-9 "
+                         "of the FP64 path), int8wS = S 8-bit digit planes (5 planes = 15 plane products keep it within ~1e-8)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -249,7 +250,7 @@ def main():
 
     eng = L.Engine(local_rank)
     if args.variance != "fp64":
-        eng.set_variance_mode(1, int(args.variance[5:]))
+        eng.set_variance_mode(args.variance)
     S, T, xq = make_inputs(N, M, rank)
     fit_ms = prep_ms = bcast_ms = None
     if rank == 0:
@@ -338,7 +339,7 @@ def main():
         o_ms, o_n = eng.kernel_time(0)
         eng.timing(False); eng.timing_reset()
         other = {"ms": ms_o, "steps": Ko, "trmm_ms": o_ms, "trmm_n": o_n}
-        eng.set_variance_mode(1, int(args.variance[5:]))
+        eng.set_variance_mode(args.variance)
 
     # ---- end to end through the host-pointer C ABI with pinned buffers ------------------------------------------
     xh = torch.from_numpy(xq).pin_memory()
@@ -380,11 +381,12 @@ def main():
             traffic = None
             try:   # DRAM bytes per launch from the committed ncu capture, only when it is the same launch shape
                 tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ozaki_traffic.json")))
-                if tr["N"] == N and abs(tr["queries_per_launch"] - q_per_launch) < 1 and S_ == 6:
+                if tr["N"] == N and abs(tr["queries_per_launch"] - q_per_launch) < 1 and tr.get("variance", "int8x6") == args.variance:
                     traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             except Exception:
                 pass
-            roofline = {"bound": "tensor", "kernel": f"ozaki_trmm_kernel<{S_}> (tcgen05.mma kind::i8, TMEM accumulators, {pairs} digit-plane products)",
+            bits = 8 if args.variance[4] == "w" else 7
+            roofline = {"bound": "tensor", "kernel": f"ozaki_trmm_kernel<{S_}> (tcgen05.mma kind::i8, TMEM accumulators, {pairs} products of {bits}-bit digit planes)",
                         "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": achieved / int8_peak, "traffic": traffic,
                         "traffic_unit": "bytes/launch (ncu dram read+write)",
                         "peak_source": int8_src, "algorithmic_ops_per_launch": ops_per_launch, "launch_ms": avg_launch_ms,
@@ -435,7 +437,7 @@ def main():
                    "sample": f"oracle port (sklearn GaussianProcessRegressor + restated reference wrapper) on {nq} of the workload's "
                              f"queries, predict(return_std)+derivative(), chunks of 2048; host has {cb['host_cpus']} cpus",
                    "fit_ms": cb["fit_ms"], "parity_vs_gpu": parity}
-        dtype = "f64" if not int8 else f"f64 (mean/Jacobian/fit in FP64; variance products as {args.variance[5:]}x7-bit int8 digit planes, exact int32 accumulation, FP64 recombination)"
+        dtype = "f64" if not int8 else f"f64 (mean/Jacobian/fit in FP64; variance products as {args.variance[5:]}x{8 if args.variance[4] == 'w' else 7}-bit int8 digit planes, exact int32 accumulation, FP64 recombination)"
         line = {"metric": METRIC, "value": value, "unit": "query-points/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
                 "data": "synthetic",

@@ -82,6 +82,16 @@ class GptbError(RuntimeError):
     pass
 
 
+def parse_variance_mode(name):
+    """'fp64' -> (0, 6); 'int8xS' -> (1, S) (7-bit digit planes); 'int8wS' -> (2, S) (8-bit digit planes)."""
+    vm = str(name).lower()
+    if vm == "fp64":
+        return 0, 6
+    if len(vm) == 6 and vm[:4] == "int8" and vm[4] in "xw" and vm[5].isdigit():
+        return (1 if vm[4] == "x" else 2), int(vm[5])
+    raise ValueError(f"unknown variance_mode {name!r} (use 'fp64', 'int8x5'..'int8x7' or 'int8w4'..'int8w6')")
+
+
 class Engine:
     """One handle = one device + stream + model state (not thread-safe, cf. include/gptb200.h)."""
 
@@ -156,7 +166,10 @@ class Engine:
         return rc, out.value, g
 
     def set_variance_mode(self, mode, slices=6):
-        """0 = FP64 DMMA (default); 1 = INT8-sliced tcgen05 path with `slices` digit planes (5..7)."""
+        """0 = FP64 DMMA (default); 1 = INT8-sliced tcgen05 path with `slices` 7-bit digit planes (5..7);
+        2 = the same path with `slices` 8-bit digit planes (4..6).  A string ("fp64", "int8x6", "int8w5") is parsed."""
+        if isinstance(mode, str):
+            mode, slices = parse_variance_mode(mode)
         self._check(self.lib.gptb_set_variance_mode(self.h, int(mode), int(slices)), "gptb_set_variance_mode")
 
     def prepare_variance(self):

@@ -74,7 +74,7 @@ struct gptb_handle {
     CUtensorMap mapL, mapD, mapM, mapW;      // TMA views of Lbuf, Dinv, Minv, Wbuf
     CUtensorMap mapL64;                      // Lbuf with a 64-row box (half-tile trailing update)
     // INT8-sliced variance path (ozaki.cuh): digit planes of the inverse factor + per-row scales
-    int var_mode = 0, var_slices = 6;
+    int var_mode = 0, var_slices = 6, var_bits = 7;   // var_mode 1 = INT8-sliced; var_bits = digit width (7 balanced | 8 full range)
     int trailing_variant = 1;                // 0: 128x128 tiles, one CTA/SM; 1: 128x64 half tiles, two CTAs/SM
     int8_t* Bplanes = nullptr;
     double* scaleB = nullptr;
@@ -156,6 +156,7 @@ static int set_kernel_attrs(gptb_handle* h) {
     CU(h, cudaFuncSetAttribute(trtri_level_p2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(kinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(trmm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<4>::SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<5>::SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<6>::SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<7>::SMEM_BYTES));
@@ -282,11 +283,13 @@ static int alloc_model(gptb_handle* h, long long N, int d, int p, bool train) {
 
 extern "C" int gptb_set_variance_mode(gptb_handle* h, int mode, int slices) {
     if (!h) return -1;
-    if (mode < 0 || mode > 1) GPTB_FAIL(h, -1, "unknown variance mode %d", mode);
-    if (mode == 1 && (slices < 5 || slices > 7)) GPTB_FAIL(h, -1, "the INT8-sliced variance path supports 5, 6 or 7 digit planes (got %d)", slices);
-    if (mode == 1 && slices != h->var_slices) h->have_bplanes = false;
-    h->var_mode = mode;
-    if (mode == 1) h->var_slices = slices;
+    if (mode < 0 || mode > 2) GPTB_FAIL(h, -1, "unknown variance mode %d", mode);
+    if (mode == 1 && (slices < 5 || slices > 7)) GPTB_FAIL(h, -1, "the INT8-sliced variance path supports 5, 6 or 7 seven-bit digit planes (got %d)", slices);
+    if (mode == 2 && (slices < 4 || slices > 6)) GPTB_FAIL(h, -1, "the INT8-sliced variance path supports 4, 5 or 6 eight-bit digit planes (got %d)", slices);
+    const int bits = (mode == 2) ? 8 : 7;
+    if (mode >= 1 && (slices != h->var_slices || bits != h->var_bits)) h->have_bplanes = false;
+    h->var_mode = mode >= 1 ? 1 : 0;
+    if (mode >= 1) { h->var_slices = slices; h->var_bits = bits; }
     return 0;
 }
 
@@ -496,9 +499,24 @@ static int build_minv(gptb_handle* h) {
 
 template <typename F>
 static void dispatch_slices(int S, F f) {
-    if (S == 5) f(std::integral_constant<int, 5>{});
+    if (S == 4) f(std::integral_constant<int, 4>{});
+    else if (S == 5) f(std::integral_constant<int, 5>{});
     else if (S == 6) f(std::integral_constant<int, 6>{});
     else f(std::integral_constant<int, 7>{});
+}
+// (planes, digit width) pairs with an instantiated slicer / fused generator: 5..7 x 7-bit, 4..6 x 8-bit
+template <typename F>
+static void dispatch_digits(int S, int bits, F f) {
+    using std::integral_constant;
+    if (bits == 8) {
+        if (S == 4) f(integral_constant<int, 4>{}, integral_constant<int, 8>{});
+        else if (S == 5) f(integral_constant<int, 5>{}, integral_constant<int, 8>{});
+        else f(integral_constant<int, 6>{}, integral_constant<int, 8>{});
+    } else {
+        if (S == 5) f(integral_constant<int, 5>{}, integral_constant<int, 7>{});
+        else if (S == 6) f(integral_constant<int, 6>{}, integral_constant<int, 7>{});
+        else f(integral_constant<int, 7>{}, integral_constant<int, 7>{});
+    }
 }
 
 // digit planes of the inverse factor for the INT8-sliced variance path
@@ -509,14 +527,14 @@ static int build_bplanes(gptb_handle* h) {
     if (rc) return rc;
     const long long Npad = h->Npad;
     const int S = h->var_slices;
-    // exactness of the int32 accumulators: up to S digit-plane products of K terms, each |digit product| <= 2^12
-    if ((long long)S * Npad * 4096 > 2147483647LL)
-        GPTB_FAIL(h, -1, "INT8-sliced variance path: N=%lld with %d digit planes would overflow the int32 accumulators", (long long)h->N, S);
+    // exactness of the int32 accumulators: up to S digit-plane products of K terms, each |digit product| <= 2^12 (2^14 for 8-bit digits)
+    if ((long long)S * Npad * (h->var_bits == 8 ? 16384 : 4096) > 2147483647LL)
+        GPTB_FAIL(h, -1, "INT8-sliced variance path: N=%lld with %d %d-bit digit planes could overflow the int32 accumulators", (long long)h->N, S, h->var_bits);
     if (h->Bplanes) { cudaFree(h->Bplanes); h->Bplanes = nullptr; }
     CU(h, cudaMalloc(&h->Bplanes, (size_t)S * Npad * Npad));
     if (!h->scaleB) CU(h, cudaMalloc(&h->scaleB, sizeof(double) * Npad));
-    dispatch_slices(S, [&](auto SS) {
-        oz::slice_rows_kernel<decltype(SS)::value><<<(unsigned)Npad, 256, 0, h->stream>>>(h->Minv, Npad, Npad, (int)Npad, 1, h->Bplanes, Npad * Npad, h->scaleB);
+    dispatch_digits(S, h->var_bits, [&](auto SS, auto BB) {
+        oz::slice_rows_kernel<decltype(SS)::value, decltype(BB)::value><<<(unsigned)Npad, 256, 0, h->stream>>>(h->Minv, Npad, Npad, (int)Npad, 1, h->Bplanes, Npad * Npad, h->scaleB);
     });
     LAUNCH_CHECK(h);
     if (!make_plane_map(&h->mapBq, h->Bplanes, Npad, Npad, S, oz::ON)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
@@ -609,10 +627,9 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
     if (fused) {
         DigitScales ds{};
         auto set = [&](int idx, double bound) {
-            int ex = 0;
-            std::frexp(bound, &ex);
-            ds.down[idx] = std::ldexp(1.0, -(ex + 1));
-            ds.scale[idx] = std::ldexp(1.0, ex + 1);
+            const int ex = digit_scale_exp(bound, h->var_bits);
+            ds.down[idx] = std::ldexp(1.0, (h->var_bits == 8 ? 8 * h->var_slices : 0) - ex);   // 8-bit planes: digits8_pack4 wants 2^-e * 256^S
+            ds.scale[idx] = std::ldexp(1.0, ex);
         };
         set(0, h->kp.c);                                               // k* <= c
         for (int a = 0; a < D; ++a) {
@@ -620,8 +637,8 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
             set(1 + D + a, h->kp.c * (1.0 + h->kp.inv_ell[a]));
         }
         if constexpr (D == P && (D == 2 || D == 3)) {
-            dispatch_slices(h->var_slices, [&](auto SS) {
-                kstar_kernel<D, P, 2, decltype(SS)::value><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, B, Bpad, h->kp, af, genflags,
+            dispatch_digits(h->var_slices, h->var_bits, [&](auto SS, auto BB) {
+                kstar_kernel<D, P, 2, decltype(SS)::value, decltype(BB)::value><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, B, Bpad, h->kp, af, genflags,
                                                                                        nullptr, xr, macc, nsplit, Aplanes, rows_total * h->Npad, oz_scale, ds);
             });
         }
@@ -644,8 +661,8 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
         if (!make_plane_map(&mapAq, Aplanes, rows_total, h->Npad, S, oz::OM)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
         if (!fused) {
             tic(h, 3);
-            dispatch_slices(S, [&](auto SS) {
-                oz::slice_rows_kernel<decltype(SS)::value><<<(unsigned)rows_total, 256, 0, h->stream>>>(rhs, h->Npad, rows_total, (int)h->Npad, 0, Aplanes, rows_total * h->Npad, oz_scale);
+            dispatch_digits(S, h->var_bits, [&](auto SS, auto BB) {
+                oz::slice_rows_kernel<decltype(SS)::value, decltype(BB)::value><<<(unsigned)rows_total, 256, 0, h->stream>>>(rhs, h->Npad, rows_total, (int)h->Npad, 0, Aplanes, rows_total * h->Npad, oz_scale);
             });
             toc(h, 3);
             h->launches++;
@@ -658,7 +675,7 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
             cudaMemsetAsync(h->info + 1, 0, sizeof(int), h->stream);      // dynamic tile counter
             oz::ozaki_trmm_kernel<SV><<<(unsigned)(ntiles < nsm ? ntiles : nsm), oz::OTHREADS, oz::Cfg<SV>::SMEM_BYTES, h->stream>>>(
-                mapAq, h->mapBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1);
+                mapAq, h->mapBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits);
         });
         toc(h, 0);
         LAUNCH_CHECK(h);

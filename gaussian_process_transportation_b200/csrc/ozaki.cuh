@@ -17,6 +17,7 @@
 // accumulates in TMEM columns [64 d, 64 d + 64).
 #pragma once
 #include "gemm_engine.cuh"
+#include "digits.cuh"
 
 namespace gptb {
 namespace oz {
@@ -25,7 +26,8 @@ constexpr int OM = 128;      // queries per tile (UMMA M)
 constexpr int ON = 64;       // inverse-factor rows per tile (UMMA N)
 constexpr int OKB = 64;      // k bytes (= k elements) per pipeline chunk, one 64-byte swizzle row
 constexpr int OTHREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
-constexpr int DIGIT_BITS = 7;
+// digit width: 7 (balanced digits, "int8xS") or 8 (full int8 range, "int8wS"; digits.cuh) -- a template parameter of the
+// slicers and a run-time argument of the product kernel (it only changes the recombination weights)
 
 template <int S> struct Cfg {
     static constexpr int STAGE_BYTES = S * (OM * OKB + ON * OKB);
@@ -65,7 +67,7 @@ __device__ __forceinline__ void tma_load_3d_u8(void* dst, const CUtensorMap* m, 
 // k <= row are split (the strict upper part -- the mirror -- becomes zero digits).
 // scale[row] = 2^e with |x| * 2^-e < 1/2 for the whole row.
 // ------------------------------------------------------------------------------------------------------------
-template <int S>
+template <int S, int BITS>
 __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ src, long long ld, long long rows, int ncols,
                                                          int lower, int8_t* __restrict__ planes, long long plane_stride,
                                                          double* __restrict__ scale) {
@@ -82,18 +84,29 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
         __syncthreads();
     }
     mx = red[0];
-    int ex = 0;
-    if (mx > 0.0) { frexp(mx, &ex); ex += 1; }          // mx = m * 2^(ex-1), m in [0.5,1)  ->  |x| * 2^-ex < 1/2
+    const int ex = digit_scale_exp(mx, BITS);           // |x| * 2^-ex fits the first digit for the whole row
     const double down = ldexp(1.0, -ex);
     if (threadIdx.x == 0) scale[row] = ldexp(1.0, ex);
-    for (int k = threadIdx.x; k < ncols; k += 256) {
-        double y = (k < kmax) ? rp[k] * down : 0.0;
+    if constexpr (BITS == 8) {
+        // four columns per thread, one 32-bit store per plane (ncols is a multiple of 128)
+        const double mul = ldexp(1.0, 8 * S - ex);
+        for (int k = 4 * threadIdx.x; k < ncols; k += 1024) {
+            double v[4];
 #pragma unroll
-        for (int t = 0; t < S; ++t) {
-            y *= 128.0;
-            const double dgt = rint(y);
-            y -= dgt;
-            planes[(long long)t * plane_stride + row * (long long)ncols + k] = (int8_t)(int)dgt;
+            for (int j = 0; j < 4; ++j) v[j] = (k + j < kmax) ? rp[k + j] : 0.0;
+            unsigned packed[S];
+            digits8_pack4<S>(v, mul, packed);
+#pragma unroll
+            for (int t = 0; t < S; ++t) *reinterpret_cast<unsigned*>(planes + (long long)t * plane_stride + row * (long long)ncols + k) = packed[t];
+        }
+    } else {
+        for (int k = threadIdx.x; k < ncols; k += 256) {
+            double y = (k < kmax) ? rp[k] * down : 0.0;
+#pragma unroll
+            for (int t = 0; t < S; ++t) {
+                const double dgt = digit_step<BITS>(y);
+                planes[(long long)t * plane_stride + row * (long long)ncols + k] = (int8_t)(int)dgt;
+            }
         }
     }
 }
@@ -121,7 +134,7 @@ __global__ void __launch_bounds__(OTHREADS, 1) ozaki_trmm_kernel(const __grid_co
                                                                 const __grid_constant__ CUtensorMap mapB,
                                                                 const double* __restrict__ scaleA, const double* __restrict__ scaleB,
                                                                 int T64, int rowtiles, long long rows_total,
-                                                                double* __restrict__ part, int* __restrict__ tile_counter) {
+                                                                double* __restrict__ part, int* __restrict__ tile_counter, int digit_bits) {
     using C = Cfg<S>;
     constexpr int NST = C::NST;
     extern __shared__ uint8_t smem_raw[];
@@ -224,6 +237,9 @@ __global__ void __launch_bounds__(OTHREADS, 1) ozaki_trmm_kernel(const __grid_co
         // ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4 ----------------
         const int quarter = warp & 3;
         const int q = quarter * 32 + lane;                      // query row within the tile = TMEM lane
+        double wgt[S];                                          // digits are 1-based: diagonal d = a+b-2 carries 2^-bits(d+2)
+#pragma unroll
+        for (int d = 0; d < S; ++d) wgt[d] = ldexp(1.0, -digit_bits * (d + 2));
         for (int lt = 0;; ++lt) {
             mbar_wait(&slot_full[lt & 1], (lt >> 1) & 1);
             const long long t = tile_slot[lt & 1];
@@ -253,9 +269,8 @@ __global__ void __launch_bounds__(OTHREADS, 1) ozaki_trmm_kernel(const __grid_co
                 asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
                 for (int d = 0; d < S; ++d) {
-                    const double w = ldexp(1.0, -DIGIT_BITS * (d + 2));   // digits are 1-based: weight 2^-7(a+b), a+b = d+2
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fma((double)(int)r[d][j], w, v[j]);
+                    for (int j = 0; j < 16; ++j) v[j] = fma((double)(int)r[d][j], wgt[d], v[j]);
                 }
                 if (cb == ON / 16 - 1) {
                     // every accumulator column of this tile has been read: let the MMA thread start the next tile

@@ -2,6 +2,7 @@
 // multiply (|L^-1 k*|^2 and |L^-1 dk*/dx_a|^2 on the DMMA tile engine) and the transport epilogue.
 #pragma once
 #include "factor.cuh"
+#include "digits.cuh"
 
 namespace gptb {
 
@@ -71,29 +72,31 @@ struct DigitScales {
     double scale[1 + 2 * MAXD];    // 2^e
 };
 
-template <int S>
+template <int S, int BITS>
 __device__ __forceinline__ void emit_digits(const double (&val)[4], double down, int8_t* __restrict__ planes, long long plane_stride,
                                             long long off) {
-    // same cascade as oz::slice_rows_kernel (error-free: scaling by powers of two, rint and the subtraction are exact)
     unsigned packed[S];
+    if constexpr (BITS == 8) {
+        digits8_pack4<S>(val, down, packed);          // here `down` already carries the 256^S factor (DigitScales)
+    } else {
+        // same cascade as oz::slice_rows_kernel (error-free: scaling by powers of two, rint and the subtraction are exact)
 #pragma unroll
-    for (int t = 0; t < S; ++t) packed[t] = 0u;
+        for (int t = 0; t < S; ++t) packed[t] = 0u;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        double y = val[j] * down;
+        for (int j = 0; j < 4; ++j) {
+            double y = val[j] * down;
 #pragma unroll
-        for (int t = 0; t < S; ++t) {
-            y *= 128.0;
-            const double dgt = rint(y);
-            y -= dgt;
-            packed[t] |= ((unsigned)(__double2int_rn(dgt)) & 0xffu) << (8 * j);
+            for (int t = 0; t < S; ++t) {
+                const double dgt = digit_step<BITS>(y);
+                packed[t] |= ((unsigned)(__double2int_rn(dgt)) & 0xffu) << (8 * j);
+            }
         }
     }
 #pragma unroll
     for (int t = 0; t < S; ++t) *reinterpret_cast<unsigned*>(planes + (long long)t * plane_stride + off) = packed[t];
 }
 
-template <int D, int P, int MODE, int S>
+template <int D, int P, int MODE, int S, int BITS = 7>
 __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ xq, const double* __restrict__ Xs,
                                                     const double* __restrict__ alpha, int N, int Npad, int B, int Bpad,
                                                     KParams kp, Affine af, unsigned flags, double* __restrict__ rhs,
@@ -203,13 +206,13 @@ __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ x
             }
         } else if (MODE == 2) {
             const long long off = (long long)q * Npad + n0;
-            if (st_k) emit_digits<S>(kv, ds.down[0], planes, plane_stride, off);
+            if (st_k) emit_digits<S, BITS>(kv, ds.down[0], planes, plane_stride, off);
 #pragma unroll
             for (int a = 0; a < D; ++a) {
-                if (st_g) emit_digits<S>(gv[a], ds.down[1 + a], planes, plane_stride, (long long)(1 + a) * Bpad * Npad + off);
+                if (st_g) emit_digits<S, BITS>(gv[a], ds.down[1 + a], planes, plane_stride, (long long)(1 + a) * Bpad * Npad + off);
                 if (st_kg) {
                     const double kg[4] = {kv[0] + gv[a][0], kv[1] + gv[a][1], kv[2] + gv[a][2], kv[3] + gv[a][3]};
-                    emit_digits<S>(kg, ds.down[1 + D + a], planes, plane_stride, (long long)(1 + D + a) * Bpad * Npad + off);
+                    emit_digits<S, BITS>(kg, ds.down[1 + D + a], planes, plane_stride, (long long)(1 + D + a) * Bpad * Npad + off);
                 }
             }
         }

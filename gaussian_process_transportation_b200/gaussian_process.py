@@ -81,7 +81,8 @@ class GaussianProcess:
         self.kernel = kernel
         self.alpha = alpha
         self._device = device
-        # how |L^-1 k*|^2 is evaluated: "fp64" (DMMA, default) or "int8x5|6|7" (INT8-sliced tcgen05 path, include/gptb200.h);
+        # how |L^-1 k*|^2 is evaluated: "fp64" (DMMA, default), "int8x5|6|7" (INT8-sliced tcgen05 path, 7-bit digit planes) or
+        # "int8w4|5|6" (same path, 8-bit digit planes: fewer plane products for the same accuracy; include/gptb200.h);
         # the environment variable GPTB_VARIANCE_MODE sets the default for objects that do not say
         import os as _os
         self._variance_mode = variance_mode or _os.environ.get("GPTB_VARIANCE_MODE", "fp64")
@@ -99,10 +100,8 @@ class GaussianProcess:
                 dev = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("GPTB_DEVICE") is None else int(os.environ["GPTB_DEVICE"])
             self._engine_obj = _lib.Engine(dev)
             vm = str(self._variance_mode).lower()
-            if vm.startswith("int8x"):
-                self._engine_obj.set_variance_mode(1, int(vm[5:]))
-            elif vm != "fp64":
-                raise ValueError(f"unknown variance_mode {self._variance_mode!r} (use 'fp64' or 'int8x5'..'int8x7')")
+            if vm != "fp64":
+                self._engine_obj.set_variance_mode(*_lib.parse_variance_mode(vm))
         return self._engine_obj
 
     # -- fit -------------------------------------------------------------------------------------------------------

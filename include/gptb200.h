@@ -74,7 +74,9 @@ int gptb_lml(gptb_handle* h, double c, const double* ell, double s2, double jitt
 /* ---- how the variance products |L^-1 k*|^2 are evaluated: mode 0 (default) = FP64 DMMA tile engine; mode 1 = INT8-sliced
  * ("Ozaki") evaluation on tcgen05 tensor cores with `slices` in {5,6,7} 7-bit digit planes per operand (exact int32
  * accumulation of the digit products, FP64 recombination).  6 planes reproduce the FP64 std to ~1e-9 of sqrt(c+s2)
- * (tolerance 1e-7), 7 to ~1e-11; the posterior mean and Jacobian are unaffected. */
+ * (tolerance 1e-7), 7 to ~1e-11; the posterior mean and Jacobian are unaffected.  mode 2 = the same evaluation with
+ * `slices` in {4,5,6} 8-bit digit planes (the full int8 range): 5 planes (15 plane products instead of 21) give ~5e-9,
+ * 6 give ~2e-11; limited to N <= 26112 by the exactness bound of the int32 accumulators (S * N * 2^14 < 2^31). */
 int gptb_set_variance_mode(gptb_handle* h, int mode, int slices);
 
 /* ---- explicit inverse factor for the variance queries (built lazily by gptb_query when needed). */

@@ -362,10 +362,11 @@ def test_matern_optimised_fit_matches_sklearn(pkg):
 # ---------------------------------------------------------------------------------------------------------------
 # INT8-sliced (tcgen05) variance path: same tolerances as the FP64 path
 # ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["int8x6", "int8w5"])
 @pytest.mark.parametrize("name", ["syn_ard300.npz", "syn_ard1000.npz", "syn_iso500.npz"])
-def test_int8_sliced_variance_vs_reference_golden(pkg, golden_dir, name):
+def test_int8_sliced_variance_vs_reference_golden(pkg, golden_dir, name, mode):
     g = load(golden_dir, name)
-    gp = pkg.GaussianProcess(kernel=kernel_of(g), optimizer=None, variance_mode="int8x6")
+    gp = pkg.GaussianProcess(kernel=kernel_of(g), optimizer=None, variance_mode=mode)
     gp.fit(g["X"], g["Y"])
     sc = np.sqrt(float(g["c"]) + float(g["s2"]))
     mean, std = gp.predict(g["xq"], return_std=True)
@@ -380,7 +381,7 @@ def test_int8_sliced_transport_flow_and_slices(pkg, golden_dir):
     g = load(golden_dir, "c2_clouds3d_fixed.npz")
     sc = np.sqrt(float(g["c"]) + float(g["s2"]))
     errs = {}
-    for mode in ("int8x6", "int8x7"):
+    for mode in ("int8x6", "int8x7", "int8w5", "int8w6"):
         t = pkg.GaussianProcessTransportation(kernel_transport=kernel_of(g))
         t.method = pkg.PolicyTransportation(pkg.GaussianProcess(kernel=kernel_of(g), optimizer=None, variance_mode=mode))
         t.source_distribution, t.target_distribution = g["S"], g["T"]
@@ -392,6 +393,7 @@ def test_int8_sliced_transport_flow_and_slices(pkg, golden_dir):
         assert errs[mode] < TOL_STD
         assert rel(t.var_vel_transported, g["var_vel"]) < 1e-6
     assert errs["int8x7"] <= errs["int8x6"] * 1.5 + 1e-12
+    assert errs["int8w6"] <= errs["int8w5"] * 1.5 + 1e-12
 
 
 def test_int8_sliced_full_size_n4096():
@@ -412,6 +414,13 @@ def test_int8_sliced_full_size_n4096():
     assert np.max(np.abs(o["std"] - ref["std"])) / np.sqrt(0.1 + 1e-4) < 2e-8
     with pytest.raises(L.GptbError):
         eng.set_variance_mode(1, 4)
+    # 8-bit digit planes: 5 planes (15 plane products) stay within the same bound; digits use the full int8 range
+    eng.set_variance_mode("int8w5")
+    o = eng.query(xq, L.MEAN | L.STD | L.JAC)
+    assert np.array_equal(o["mean"], ref["mean"]) and np.array_equal(o["jac"], ref["jac"])
+    assert np.max(np.abs(o["std"] - ref["std"])) / np.sqrt(0.1 + 1e-4) < 2e-8
+    with pytest.raises(L.GptbError):
+        eng.set_variance_mode(2, 7)
 
 
 def test_refit_invalidates_cached_inverse_factor_and_digit_planes():
@@ -421,9 +430,9 @@ def test_refit_invalidates_cached_inverse_factor_and_digit_planes():
     S1, T1 = synthetic_pairs(300, 3, seed=1)
     S2, T2 = synthetic_pairs(300, 3, seed=2)
     xq = np.random.default_rng(0).random((200, 3))
-    for mode in (0, 1):
+    for mode, planes in ((0, 6), (1, 6), (2, 5)):
         eng = L.Engine(0)
-        eng.set_variance_mode(mode, 6)
+        eng.set_variance_mode(mode, planes)
         eng.set_train(S1, T1 - S1); eng.factorize(0.1, [0.1] * 3, 1e-4, 1e-10)
         eng.query(xq, L.MEAN | L.STD)
         eng.set_train(S2, T2 - S2); eng.factorize(0.2, [0.15] * 3, 1e-3, 1e-10)
