@@ -44,6 +44,7 @@ SYMBOLS = {
     "gptb_stream": (C.c_void_p, [C.c_void_p]),
     "gptb_set_trailing_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "gptb_set_workspace_limit": (C.c_int, [C.c_void_p, C.c_int64]),
+    "gptb_set_query_pipeline": (C.c_int, [C.c_void_p, C.c_int]),
     "gptb_test_gemm_nt": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gptb_test_potrf_tile": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.POINTER(C.c_int)]),
 }
@@ -271,6 +272,11 @@ class Engine:
 
     def set_trailing_variant(self, variant):
         self._check(self.lib.gptb_set_trailing_variant(self.h, int(variant)), "gptb_set_trailing_variant")
+
+    def set_query_pipeline(self, on):
+        """INT8-sliced path: overlap the generator of the next batch with the products of the current one (default off:
+        no gain under the power cap, see include/gptb200.h)."""
+        self._check(self.lib.gptb_set_query_pipeline(self.h, int(bool(on))), "gptb_set_query_pipeline")
 
     def set_workspace_limit(self, nbytes):
         self._check(self.lib.gptb_set_workspace_limit(self.h, int(nbytes)), "gptb_set_workspace_limit")

@@ -63,6 +63,10 @@ struct gptb_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t aux = nullptr;               // high-priority stream for the look-ahead diagonal tile
+    cudaStream_t gen = nullptr;               // lowest-priority stream: the generator of batch i+1 runs under the int8 products of batch i
+    cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_start = nullptr;
+    int pipeline = 0;                         // 1 overlaps the generator of batch i+1 with the products of batch i (opt-in: measured no gain, the
+                                              // int8 products run at the 1 kW power cap, so the two kernels share one energy budget)
     std::vector<cudaEvent_t> ev_diag, ev_col; // per-step dependencies between the two streams
     std::string err;
     long long N = 0, Npad = 0;
@@ -86,7 +90,7 @@ struct gptb_handle {
     // query workspace
     double* ws = nullptr;
     size_t ws_bytes = 0;
-    long long ws_limit = 8LL << 30;
+    long long ws_limit = 16LL << 30;
     // staging for the host-pointer query
     double* stage = nullptr;
     size_t stage_bytes = 0;
@@ -121,17 +125,17 @@ struct gptb_handle {
         if (_e != cudaSuccess) GPTB_FAIL(h, -3, "kernel launch failed: %s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
-static void tic(gptb_handle* h, int cls) {
+static void tic(gptb_handle* h, int cls, cudaStream_t st = nullptr) {
     if (!h->timing) return;
     EvPair e;
     cudaEventCreate(&e.a);
     cudaEventCreate(&e.b);
-    cudaEventRecord(e.a, h->stream);
+    cudaEventRecord(e.a, st ? st : h->stream);
     h->ev[cls].push_back(e);
 }
-static void toc(gptb_handle* h, int cls) {
+static void toc(gptb_handle* h, int cls, cudaStream_t st = nullptr) {
     if (!h->timing) return;
-    cudaEventRecord(h->ev[cls].back().b, h->stream);
+    cudaEventRecord(h->ev[cls].back().b, st ? st : h->stream);
 }
 
 static void free_model(gptb_handle* h) {
@@ -181,8 +185,15 @@ extern "C" int gptb_create(int device, gptb_handle** out) {
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return -2; }
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete h; return -2; }
+    // numerically lower = higher priority: aux (look-ahead tile) > main > gen (the generator only fills what the products leave free)
+    const int prio_main = (prio_lo - 1 >= prio_hi) ? prio_lo - 1 : prio_lo;
+    if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_main) != cudaSuccess) { delete h; return -2; }
     if (cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete h; return -2; }
+    if (cudaStreamCreateWithPriority(&h->gen, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete h; return -2; }
+    for (int i = 0; i < 2; ++i)
+        if (cudaEventCreateWithFlags(&h->ev_gen[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return -2; }
+    if (cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming) != cudaSuccess) { delete h; return -2; }
     if (cudaMalloc(&h->info, 4 * sizeof(int)) != cudaSuccess || cudaMalloc(&h->scal, 64 * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->header, 32 * sizeof(double)) != cudaSuccess) {
         delete h;
@@ -212,6 +223,10 @@ extern "C" void gptb_destroy(gptb_handle* h) {
         for (auto& e : v) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : h->ev_diag) cudaEventDestroy(e);
     for (auto e : h->ev_col) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_gen[i]); cudaEventDestroy(h->ev_done[i]); }
+    cudaEventDestroy(h->ev_start);
+    cudaStreamSynchronize(h->gen);
+    cudaStreamDestroy(h->gen);
     cudaStreamDestroy(h->aux);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -223,6 +238,11 @@ extern "C" void* gptb_stream(gptb_handle* h) { return h ? (void*)h->stream : nul
 extern "C" int gptb_set_trailing_variant(gptb_handle* h, int variant) {
     if (!h || variant < 0 || variant > 1) return -1;
     h->trailing_variant = variant;
+    return 0;
+}
+extern "C" int gptb_set_query_pipeline(gptb_handle* h, int on) {
+    if (!h) return -1;
+    h->pipeline = on != 0;
     return 0;
 }
 extern "C" int gptb_set_workspace_limit(gptb_handle* h, int64_t bytes) {
@@ -614,13 +634,17 @@ static bool oz_fused_supported(int d, int p) { return d == p && (d == 2 || d == 
 template <int D, int P>
 static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_dev, int B, int Bpad, unsigned flags, int nrhs,
                        unsigned genflags, const QueryOut& out, long long q_off, long long Mtot, double* rhs, double* part,
-                       double* macc, double* xr, int nsplit, const CUtensorMap* mapR, void* oz_planes, double* oz_scale) {
+                       double* macc, double* xr, int nsplit, const CUtensorMap* mapR, void* oz_planes, double* oz_scale, int pipe_slot) {
     const int T = h->T;
+    // pipe_slot >= 0: this batch's generator runs on the low-priority stream into buffer set `pipe_slot`; the products and
+    // the epilogue follow on the main stream once it has finished, so the NEXT batch's generator (FP64 pipe) overlaps them
+    // (tensor pipe).  The caller orders buffer reuse through ev_done[].
+    cudaStream_t gs = (pipe_slot >= 0) ? h->gen : h->stream;
     const long long rows_total = (long long)nrhs * Bpad;
     Affine af = h->af;
     af.on = (flags & GPTB_AFFINE_IN) ? h->af.on : 0;
     dim3 grid(Bpad / QPB, nsplit);
-    tic(h, 1);
+    tic(h, 1, gs);
     // digit planes straight from the generator when the INT8-sliced path is on and this (d,p) has a fused instantiation
     const bool fused = (nrhs > 0 && h->var_mode == 1 && oz_fused_supported(D, P));
     int8_t* Aplanes = reinterpret_cast<int8_t*>(oz_planes);
@@ -638,7 +662,7 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
         }
         if constexpr (D == P && (D == 2 || D == 3)) {
             dispatch_digits(h->var_slices, h->var_bits, [&](auto SS, auto BB) {
-                kstar_kernel<D, P, 2, decltype(SS)::value, decltype(BB)::value><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, B, Bpad, h->kp, af, genflags,
+                kstar_kernel<D, P, 2, decltype(SS)::value, decltype(BB)::value><<<grid, 256, 0, gs>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, B, Bpad, h->kp, af, genflags,
                                                                                        nullptr, xr, macc, nsplit, Aplanes, rows_total * h->Npad, oz_scale, ds);
             });
         }
@@ -649,8 +673,12 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
         kstar_kernel<D, P, 0, 5><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, B, Bpad, h->kp, af, 0u, rhs, xr, macc, nsplit, nullptr,
                                                              0, nullptr, DigitScales{});
     }
-    toc(h, 1);
+    toc(h, 1, gs);
     LAUNCH_CHECK(h);
+    if (pipe_slot >= 0) {
+        CU(h, cudaEventRecord(h->ev_gen[pipe_slot], gs));
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_gen[pipe_slot], 0));
+    }
     int Tpart = T;
     if (nrhs > 0 && h->var_mode == 1) {
         // INT8-sliced path: split the right-hand-side rows into digit planes, then S(S+1)/2 exact int8 GEMMs per tile
@@ -693,7 +721,7 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
 }
 
 typedef int (*chunk_fn)(gptb_handle*, const double*, const double*, int, int, unsigned, int, unsigned, const QueryOut&, long long,
-                        long long, double*, double*, double*, double*, int, const CUtensorMap*, void*, double*);
+                        long long, double*, double*, double*, double*, int, const CUtensorMap*, void*, double*, int);
 
 static chunk_fn pick_chunk_fn(int d, int p) {
     static const chunk_fn table[4][4] = {
@@ -733,16 +761,27 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
         int rc = ozaki ? build_bplanes(h) : build_minv(h);
         if (rc) return rc;
     }
-    // batch size: bounded by the workspace for the right-hand-side rows (nrhs * Bpad * Npad doubles)
-    long long Bmax;
-    if (nrhs > 0) {
-        const long long per_elem = ozaki ? (oz_fused_supported(d, p) ? h->var_slices : (long long)sizeof(double) + h->var_slices) : (long long)sizeof(double);
-        Bmax = h->ws_limit / (per_elem * nrhs * h->Npad);
-        Bmax = Bmax / TS * TS;
-        if (Bmax < TS) Bmax = TS;
-        if (Bmax > 65536) Bmax = 65536;
-    } else {
-        Bmax = 1 << 20;
+    // batch size: bounded by the workspace for the right-hand-side rows (nrhs * Bpad * Npad doubles / digit bytes)
+    const bool fused_planes = ozaki && oz_fused_supported(d, p);
+    const long long per_elem = ozaki ? (fused_planes ? h->var_slices : (long long)sizeof(double) + h->var_slices) : (long long)sizeof(double);
+    auto batch_cap = [&](int nbuf) {
+        long long bm = h->ws_limit / (nbuf * per_elem * nrhs * h->Npad);
+        bm = bm / TS * TS;
+        if (bm < TS) bm = TS;
+        if (bm > 65536) bm = 65536;
+        return bm;
+    };
+    long long Bmax = (nrhs > 0) ? batch_cap(1) : (1LL << 20);
+    // INT8-sliced path with the fused generator: double-buffered batches so the generator of batch i+1 (FP64 pipe, gen stream)
+    // runs under the digit-plane products of batch i (tensor pipe, main stream).  The stream is cut into >= 8 batches of
+    // >= 8192 queries (enough 128 x 64 tiles to fill the persistent product kernel many times over).
+    int nbuf = 1;
+    if (fused_planes && h->pipeline && M >= 2 * 8192) {
+        long long bp = (M / 8 + TS - 1) / TS * TS;
+        if (bp < 8192) bp = 8192;
+        const long long cap2 = batch_cap(2);
+        if (bp > cap2) bp = cap2;
+        if (bp < M) { nbuf = 2; Bmax = bp; }
     }
     long long Bfirst = (M < Bmax) ? (M + TS - 1) / TS * TS : Bmax;
     const int T = h->T;
@@ -755,15 +794,18 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     }
     size_t need = 0;
     auto carve = [&](size_t doubles) { size_t off = need; need += (doubles * sizeof(double) + 255) / 256 * 256; return off; };
-    const bool fused_planes = ozaki && oz_fused_supported(d, p);
     size_t o_rhs = carve(fused_planes ? 0 : (size_t)nrhs * Bfirst * h->Npad);
-    size_t o_part = carve((size_t)(nrhs > 0 ? (ozaki ? 2 * T : T) : 0) * nrhs * Bfirst);
-    size_t o_ozp = carve(ozaki ? ((size_t)h->var_slices * nrhs * Bfirst * h->Npad + 7) / 8 : 0);
-    size_t o_ozs = carve(ozaki ? (size_t)nrhs * Bfirst : 0);
-    size_t o_macc = carve((size_t)nsplit * Bfirst * NACC);
-    size_t o_xr = carve((size_t)Bfirst * d);
+    size_t o_part[2], o_ozp[2], o_ozs[2], o_macc[2], o_xr[2];
+    for (int b = 0; b < nbuf; ++b) {
+        o_part[b] = carve((size_t)(nrhs > 0 ? (ozaki ? 2 * T : T) : 0) * nrhs * Bfirst);
+        o_ozp[b] = carve(ozaki ? ((size_t)h->var_slices * nrhs * Bfirst * h->Npad + 7) / 8 : 0);
+        o_ozs[b] = carve(ozaki ? (size_t)nrhs * Bfirst : 0);
+        o_macc[b] = carve((size_t)nsplit * Bfirst * NACC);
+        o_xr[b] = carve((size_t)Bfirst * d);
+    }
     if (need > h->ws_bytes) {
         CU(h, cudaStreamSynchronize(h->stream));
+        CU(h, cudaStreamSynchronize(h->gen));
         if (h->ws) cudaFree(h->ws);
         h->ws = nullptr;
         h->ws_bytes = 0;
@@ -772,16 +814,16 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     }
     char* base = reinterpret_cast<char*>(h->ws);
     double* rhs = reinterpret_cast<double*>(base + o_rhs);
-    double* part = reinterpret_cast<double*>(base + o_part);
-    double* macc = reinterpret_cast<double*>(base + o_macc);
-    double* xr = reinterpret_cast<double*>(base + o_xr);
-    void* oz_planes = base + o_ozp;
-    double* oz_scale = reinterpret_cast<double*>(base + o_ozs);
     QueryOut out{mean_dev, std_dev, jac_dev, jacvar_dev, xhat_dev, vhat_dev, vvar_dev, jphi_dev, dvar_dev};
     chunk_fn fn = pick_chunk_fn(d, p);
     CUtensorMap mapR_full, mapR_tail;
     int Bpad_mapped = -1;
-    for (long long q0 = 0; q0 < M; q0 += Bfirst) {
+    if (nbuf == 2) {   // the generator stream starts behind everything already queued on the main stream (inputs, digit planes of L^-1)
+        CU(h, cudaEventRecord(h->ev_start, h->stream));
+        CU(h, cudaStreamWaitEvent(h->gen, h->ev_start, 0));
+    }
+    long long ib = 0;
+    for (long long q0 = 0; q0 < M; q0 += Bfirst, ++ib) {
         int B = (int)((M - q0 < Bfirst) ? (M - q0) : Bfirst);
         int Bpad = (B + TS - 1) / TS * TS;
         const CUtensorMap* mapR = nullptr;
@@ -794,8 +836,14 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
             }
             mapR = m;
         }
-        int rc = fn(h, x_dev + q0 * d, vel_dev ? vel_dev + q0 * d : nullptr, B, Bpad, flags, nrhs, genflags, out, q0, M, rhs, part, macc, xr, nsplit, mapR, oz_planes, oz_scale);
+        const int b = (nbuf == 2) ? (int)(ib & 1) : 0;
+        if (nbuf == 2 && ib >= 2) CU(h, cudaStreamWaitEvent(h->gen, h->ev_done[b], 0));     // buffer set b is free again
+        int rc = fn(h, x_dev + q0 * d, vel_dev ? vel_dev + q0 * d : nullptr, B, Bpad, flags, nrhs, genflags, out, q0, M, rhs,
+                    reinterpret_cast<double*>(base + o_part[b]), reinterpret_cast<double*>(base + o_macc[b]),
+                    reinterpret_cast<double*>(base + o_xr[b]), nsplit, mapR, base + o_ozp[b], reinterpret_cast<double*>(base + o_ozs[b]),
+                    nbuf == 2 ? b : -1);
         if (rc) return rc;
+        if (nbuf == 2) CU(h, cudaEventRecord(h->ev_done[b], h->stream));
     }
     return 0;
 }

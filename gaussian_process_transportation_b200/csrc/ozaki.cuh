@@ -25,7 +25,14 @@ namespace oz {
 constexpr int OM = 128;      // queries per tile (UMMA M)
 constexpr int ON = 64;       // inverse-factor rows per tile (UMMA N)
 constexpr int OKB = 64;      // k bytes (= k elements) per pipeline chunk, one 64-byte swizzle row
-constexpr int OTHREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
+constexpr int OTHREADS = 256;   // warp group 0: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner (2, 3 idle); warp group 1: epilogue
+// Register budget (setmaxnreg): __launch_bounds__(256, 2) launches the CTA with 128 registers per thread; warp group 0
+// gives back down to 80 and the epilogue warp group grows to 176 (128*80 + 128*176 = 256*128; ptxas compiles each
+// branch against its own budget, no spills).  What matters is the LAUNCH footprint: 2 warps x 128 x 32 = 8 K of the 16 K
+// registers of each SM sub-partition, which leaves room for one 256-thread generator CTA (2 warps x 120 x 32 per
+// sub-partition) next to the persistent product CTA -- the generator of the next batch runs on the FP64 pipe while this
+// kernel keeps the tensor pipe busy (gptb_set_query_pipeline).  With 6 warps x 168 registers the generator never fitted.
+constexpr int OREG_LIGHT = 80, OREG_EPI = 176;
 // digit width: 7 (balanced digits, "int8xS") or 8 (full int8 range, "int8wS"; digits.cuh) -- a template parameter of the
 // slicers and a run-time argument of the product kernel (it only changes the recombination weights)
 
@@ -130,7 +137,7 @@ __device__ __forceinline__ void oz_tile_decode(long long idx, int T64, int rowti
 }
 
 template <int S>
-__global__ void __launch_bounds__(OTHREADS, 1) ozaki_trmm_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                 const __grid_constant__ CUtensorMap mapB,
                                                                 const double* __restrict__ scaleA, const double* __restrict__ scaleB,
                                                                 int T64, int rowtiles, long long rows_total,
@@ -160,6 +167,9 @@ __global__ void __launch_bounds__(OTHREADS, 1) ozaki_trmm_kernel(const __grid_co
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(OREG_LIGHT));
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(OREG_EPI));
 
     if (warp == 0) {
         if (lane == 0) {
@@ -217,12 +227,16 @@ __global__ void __launch_bounds__(OTHREADS, 1) ozaki_trmm_kernel(const __grid_co
 #pragma unroll
                     for (int a = 0; a < S; ++a) {
                         const uint64_t ad = smem_desc_sw64(sA + a * OM * OKB);
+                        // N = 64 (S-a) columns; above 256 the product is issued as two EQUAL halves (e.g. 320 = 160 + 160, not
+                        // 256 + 64: a 64-wide MMA re-reads the 4 KB A tile for 32 cycles of work and is operand-port bound)
+                        const int ncols = ON * (S - a);
+                        const int nhalf = (ncols > 256) ? 2 : 1;
+                        const int nw = ncols / nhalf;                                   // multiple of 32
 #pragma unroll
-                        for (int b0 = 0; b0 < S - a; b0 += 4) {
-                            const int nb = (S - a - b0) < 4 ? (S - a - b0) : 4;        // planes in this MMA (N = 64 nb <= 256)
-                            const uint64_t bd = smem_desc_sw64(sB + b0 * ON * OKB);
-                            const uint32_t dcol = tmem_base + (uint32_t)((a + b0) * ON);
-                            const uint32_t idn = idesc_base | ((uint32_t)((nb * ON) >> 3) << 17);
+                        for (int hf = 0; hf < nhalf; ++hf) {
+                            const uint64_t bd = smem_desc_sw64(sB + hf * nw * OKB);    // nw rows further down the stacked B planes
+                            const uint32_t dcol = tmem_base + (uint32_t)(a * ON + hf * nw);
+                            const uint32_t idn = idesc_base | ((uint32_t)(nw >> 3) << 17);
 #pragma unroll
                             for (int kk = 0; kk < OKB / 32; ++kk)
                                 umma_i8(dcol, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idn, (a == 0 && c == 0 && kk == 0) ? 0u : 1u);
@@ -233,8 +247,8 @@ __global__ void __launch_bounds__(OTHREADS, 1) ozaki_trmm_kernel(const __grid_co
                 umma_commit(&acc_full);
             }
         }
-    } else {
-        // ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4 ----------------
+    } else if (warp >= 4) {
+        // ---------------- epilogue warps 4..7: TMEM lane quarter = warp % 4 ----------------
         const int quarter = warp & 3;
         const int q = quarter * 32 + lane;                      // query row within the tile = TMEM lane
         double wgt[S];                                          // digits are 1-based: diagonal d = a+b-2 carries 2^-bits(d+2)

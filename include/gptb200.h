@@ -140,8 +140,13 @@ void* gptb_stream(gptb_handle* h);
 /* schedule of the Cholesky trailing update: 0 = 128x128 tiles, one persistent CTA per SM; 1 (default) = 128x64 half tiles,
  * two CTAs per SM with a dynamic job queue (tuning / A-B measurement knob; results are bit-identical). */
 int gptb_set_trailing_variant(gptb_handle* h, int variant);
-/* workspace cap for query batches in bytes (default 8 GiB). */
+/* workspace cap for query batches in bytes (default 16 GiB). */
 int gptb_set_workspace_limit(gptb_handle* h, int64_t bytes);
+/* INT8-sliced path only: overlap the k* generator of batch i+1 (FP64 pipe, low-priority stream) with the digit-plane
+ * products of batch i (tensor pipe) through double-buffered batches.  Off by default: on this pool's B200 the product
+ * kernel runs at the 1 kW power cap (SM clock ~1.72 GHz), the two kernels then share one energy budget and the overlapped
+ * step is no faster than the serialised one (profiles/r01_pipeline_ab.log).  Results are bit-identical either way. */
+int gptb_set_query_pipeline(gptb_handle* h, int on);
 
 /* ---- unit-test hooks: exercise the DMMA tile engine and the small factor kernels in isolation.
  * C (128*mt,128*nt) = A (128*mt,K) * B(128*nt,K)^T, all row-major host arrays, K multiple of 128. */
