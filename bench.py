@@ -380,7 +380,8 @@ def main():
             int8_peak, int8_src = measure_int8_peak(torch, dev)
             traffic = None
             try:   # DRAM bytes per launch from the committed ncu capture, only when it is the same launch shape
-                tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ozaki_traffic.json")))
+                tf = os.path.join(ROOT, "profiles", f"r01_ozaki_traffic_{args.variance}.json")
+                tr = json.load(open(tf if os.path.exists(tf) else os.path.join(ROOT, "profiles", "r01_ozaki_traffic.json")))
                 if tr["N"] == N and abs(tr["queries_per_launch"] - q_per_launch) < 1 and tr.get("variance", "int8x6") == args.variance:
                     traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             except Exception:
