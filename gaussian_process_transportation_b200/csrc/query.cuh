@@ -164,22 +164,35 @@ __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ x
             al[o][0] = u0.x; al[o][1] = u0.y; al[o][2] = u1.x; al[o][3] = u1.y;
         }
         double kv[4], gv[D][4];
+        double dfj[D][4], sj[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            double df[D], sacc = 0.0;
+            sj[j] = 0.0;
 #pragma unroll
             for (int a = 0; a < D; ++a) {
-                df[a] = xs[a] - xn[a][j];
-                sacc += df[a] * df[a];
+                dfj[a][j] = xs[a] - xn[a][j];
+                sj[j] += dfj[a][j] * dfj[a][j];
             }
+        }
+        // the kernel family is a run-time parameter: branch ONCE per four points (not per point) so that the four exp chains of
+        // the RBF path sit in one basic block and interleave on the FP64 pipe
+        if (kp.kind == KIND_RBF) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) kv[j] = exp_neg(-0.5 * sj[j], etab);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) kv[j] = kernel_profile(sj[j], kp.kind, [&](double z) { return exp_neg(z, etab); });
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
             const bool inb = (n0 + j) < N;
-            const double k = (inb && valid) ? kp.c * kernel_profile(sacc, kp.kind, [&](double z) { return exp_neg(z, etab); }) : 0.0;
+            const double k = (inb && valid) ? kp.c * kv[j] : 0.0;
             kv[j] = k;
 #pragma unroll
             for (int o = 0; o < P; ++o) acc[o] = fma(k, al[o][j], acc[o]);
 #pragma unroll
             for (int a = 0; a < D; ++a) {
-                const double u = -k * df[a];                 // k * (X_a - x_a)/ell_a
+                const double u = -k * dfj[a][j];             // k * (X_a - x_a)/ell_a
                 gv[a][j] = u * kp.inv_ell[a];                // dk*/dx_a
 #pragma unroll
                 for (int o = 0; o < P; ++o) acc[P + o * D + a] = fma(u, al[o][j], acc[P + o * D + a]);

@@ -1,5 +1,4 @@
 set -x
-python tools/pipe_ab.py 4096 1048576 2>&1 | tail -4
-python tools/pipe_ab.py 16384 131072 2>&1 | tail -4
-python tools/pipe_ab.py 4096 1048576 int8x6 2>&1 | tail -2
-python -m pytest tests -m gpu -x -q -k "int8 or refit" 2>&1 | tail -3
+python tools/ozaki_time.py 4096 262144 2>&1 | tail -3
+python tools/power_probe.py 4096 1048576 2>&1 | grep -E "serialised|A0"
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
