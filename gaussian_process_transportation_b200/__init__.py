@@ -6,6 +6,9 @@ from .affine_transform import AffineTransform
 from .gaussian_process import GaussianProcess
 from .policy_transportation import PolicyTransportation
 from .gaussian_process_transportation import GaussianProcessTransportation
+from .gaussian_process_transportation_diffeomorphic import GaussianProcessTransportationDiffeo
+from .gaussian_process_al import GaussianProcess as GaussianProcessAL
 
-__all__ = ['AffineTransform', 'GaussianProcessTransportation', 'GaussianProcess', 'PolicyTransportation']
+__all__ = ['AffineTransform', 'GaussianProcessTransportation', 'GaussianProcess', 'PolicyTransportation',
+           'GaussianProcessTransportationDiffeo', 'GaussianProcessAL']
 __version__ = "0.1.0"

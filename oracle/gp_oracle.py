@@ -323,6 +323,90 @@ class OracleGPT:
             self.training_ori = self.method.transport_orientation(self.training_traj_old, self.training_ori)
 
 
+class OracleDiffeo:
+    """Restates ``policy_transportation/transportation/gaussian_process_transportation_diffeomorphic.py:15-141`` (the
+    delta-map GP owned directly, Jacobian at the ROTATED positions, inverse-map consistency error)."""
+
+    def __init__(self, kernel_transport):
+        self.kernel_transport = kernel_transport
+
+    def fit_transportation(self, optimize=True, do_scale=False, do_rotation=True):
+        self.affine_transform = OracleAffine(do_scale=do_scale, do_rotation=do_rotation)
+        self.affine_transform.fit(self.source_distribution, self.target_distribution)
+        S2 = self.affine_transform.predict(self.source_distribution)
+        self.delta_distribution = self.target_distribution - S2
+        kw = dict(n_restarts_optimizer=5) if optimize else dict(optimizer=None)
+        self.gp_delta_map = SkGaussianProcess(kernel=self.kernel_transport, **kw)
+        self.gp_delta_map.fit(S2, self.delta_distribution)
+        self.kernel_transport = self.gp_delta_map.kernel
+
+    def apply_transportation(self):
+        self.training_traj_old = self.training_traj
+        self.traj_rotated = self.affine_transform.predict(self.training_traj)
+        self.delta_map_mean, self.std = self.gp_delta_map.predict(self.traj_rotated, return_std=True)
+        self.training_traj = self.traj_rotated + self.delta_map_mean
+        if hasattr(self, "training_delta") or hasattr(self, "training_ori"):
+            J, Jv = self.gp_delta_map.derivative(self.traj_rotated, return_var=True)
+            rot_gp = np.eye(J[0].shape[0]) + J
+            Jg = self.affine_transform.derivative(self.traj_rotated)
+        if hasattr(self, "training_delta"):
+            v = Jg @ self.training_delta[:, :, None]
+            self.var_vel_transported = (Jv @ v ** 2)[:, :, 0]
+            self.training_delta = (rot_gp @ v)[:, :, 0]
+        if hasattr(self, "training_ori"):
+            q_aff = quat_from_matrix_nonorthogonal(self.affine_transform.rotation_matrix)
+            self.training_ori = quat_mul(quat_from_matrix_nonorthogonal(rot_gp), quat_mul(q_aff, self.training_ori))
+
+    def check_invertibility(self):
+        self.training_traj_old = self.training_traj
+        self.traj_rotated = self.affine_transform.predict(self.training_traj)
+        self.delta_map_mean, self.std = self.gp_delta_map.predict(self.traj_rotated, return_std=True)
+        self.training_traj = self.traj_rotated + self.delta_map_mean
+        self.gp_delta_inv = SkGaussianProcess(kernel=self.kernel_transport, optimizer=None)
+        self.gp_delta_inv.fit(self.target_distribution, -self.delta_distribution)
+        self.delta_map_inv_mean = self.gp_delta_inv.predict(self.training_traj)[0]        # first ROW (file:121)
+        self.traj_rotated_inv = self.training_traj + self.delta_map_inv_mean
+        return np.sum(np.linalg.norm(self.delta_map_mean + self.delta_map_inv_mean, axis=1))
+
+
+class OracleGPAL:
+    """Restates ``policy_transportation/models/gaussian_process_al.py:15-107`` (greedy max-std subset + exact GP)."""
+
+    def __init__(self, kernel, alpha=1e-10, n_restarts_optimizer=5, n_samples_max=20000):
+        self.kernel0, self.alpha, self.nro, self.n_samples_max = kernel, alpha, n_restarts_optimizer, n_samples_max
+
+    def fit(self, X, Y):
+        X, Y = np.asarray(X, float), np.asarray(Y, float)
+        n = X.shape[0]
+        if n > self.n_samples_max:
+            n_initial = int(0.1 * self.n_samples_max)
+            idx = np.random.choice(range(n), size=n_initial, replace=False)
+            Xs, Ys = X[idx], Y[idx]
+            Xt, Yt = np.delete(X, idx, axis=0), np.delete(Y, idx, axis=0)
+            from sklearn.gaussian_process import GaussianProcessRegressor
+            act = GaussianProcessRegressor(kernel=self.kernel0, alpha=self.alpha)
+            act.fit(Xs, Ys)
+            for _ in range(self.n_samples_max - n_initial):
+                _, std = act.predict(Xt, return_std=True)
+                q = np.argmax(std.reshape(-1, Yt.shape[1])[:, 0])
+                Xs, Ys = np.vstack([Xs, Xt[q]]), np.vstack([Ys, Yt[q]])
+                Xt, Yt = np.delete(Xt, q, axis=0), np.delete(Yt, q, axis=0)
+                act.fit(Xs, Ys)
+            X, Y = Xs, Ys
+        self.X, self.Y = X, Y
+        self.model = SkGaussianProcess(kernel=self.kernel0, alpha=self.alpha, n_restarts_optimizer=self.nro)
+        self.model.fit(X, Y)
+        self.kernel = self.model.kernel
+        return self
+
+    def predict(self, x):
+        return self.model.predict(x, return_std=True)
+
+    def derivative(self, x):
+        J = self.model.derivative(x)
+        return np.transpose(J, (0, 2, 1)), np.transpose(self.model.derivative_of_variance(x))[:, :, None]
+
+
 # --------------------------------------------------------------------------------------------------------------
 # Synthetic workloads (SURVEY.md §8(d)); shared by tests and bench so GPU and CPU arms see identical inputs
 # --------------------------------------------------------------------------------------------------------------

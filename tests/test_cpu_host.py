@@ -102,3 +102,13 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["value"] > 0 and line["vs_baseline"] is None
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_variance_mode_names():
+    from gaussian_process_transportation_b200 import _lib
+    assert _lib.parse_variance_mode("fp64") == (0, 6)
+    assert _lib.parse_variance_mode("int8x6") == (1, 6)
+    assert _lib.parse_variance_mode("INT8W5") == (2, 5)
+    for bad in ("int8", "int8y5", "fp32", "int8x"):
+        with pytest.raises(ValueError):
+            _lib.parse_variance_mode(bad)

@@ -1,0 +1,119 @@
+"""GPU parity tests for the SURVEY.md section-8 "next" row f4 -- callers one level above the delta-map GP -- against golden
+vectors produced by the UNMODIFIED reference (oracle/make_golden_f4.py):
+  * GaussianProcessTransportationDiffeo (transportation/gaussian_process_transportation_diffeomorphic.py): apply flow, joint
+    samples, inverse-map consistency error, one objective evaluation of the length-scale-bound study;
+  * the active-learning GP (models/gaussian_process_al.py): greedy subset, predict, derivative.
+Tolerances as in test_gpu_parity.py (mean / Jacobian 1e-9, std 1e-7 of sqrt(c + s2))."""
+import contextlib
+import io
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+TOL_MEAN, TOL_STD = 1e-9, 1e-7
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def kern(c, ell, s2, **kw):
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+    return C(float(c)) * RBF(np.asarray(ell, float), **kw) + WhiteKernel(float(s2))
+
+
+class FixedTrial:
+    def __init__(self, value):
+        self.value = value
+
+    def suggest_float(self, name, lo, hi, log=False):
+        return self.value
+
+
+@pytest.mark.parametrize("name,mode", [("f4_diffeo2d.npz", "fp64"), ("f4_diffeo3d.npz", "fp64"), ("f4_diffeo3d.npz", "int8w5")])
+def test_diffeo_apply_flow_vs_reference(golden_dir, name, mode, monkeypatch):
+    import gaussian_process_transportation_b200 as pkg
+    monkeypatch.setenv("GPTB_VARIANCE_MODE", mode)
+    g = np.load(os.path.join(golden_dir, name))
+    t = pkg.GaussianProcessTransportationDiffeo(kernel_transport=kern(g["c"], g["ell"], g["s2"]))
+    t.source_distribution, t.target_distribution = g["S"], g["T"]
+    t.training_traj, t.training_delta = g["traj_in"].copy(), g["delta_in"].copy()
+    with contextlib.redirect_stdout(io.StringIO()):
+        t.fit_transportation(optimize=False)
+        t.apply_transportation()
+    sc = np.sqrt(float(g["c"]) + float(g["s2"]))
+    assert rel(t.training_traj, g["traj_out"]) < TOL_MEAN
+    assert rel(t.training_delta, g["delta_out"]) < TOL_MEAN
+    assert np.max(np.abs(t.std - g["std"])) / sc < TOL_STD
+    assert rel(t.var_vel_transported, g["var_vel"]) < 1e-6
+    if "samples" in g.files:
+        assert rel(t.traj_rotated, g["traj_rotated"]) < 1e-13 and rel(t.delta_map_mean, g["delta_map_mean"]) < TOL_MEAN
+        with contextlib.redirect_stdout(io.StringIO()):
+            smp = t.sample_transportation()
+        assert smp.shape == g["samples"].shape
+        # the draw factorises the (M, M) covariance by SVD: agreement is limited by the conditioning of that factorisation
+        assert rel(smp, g["samples"]) < 1e-5
+
+
+def test_diffeo_invertibility_and_study_objective_vs_reference(golden_dir):
+    import gaussian_process_transportation_b200 as pkg
+    g = np.load(os.path.join(golden_dir, "f4_diffeo2d.npz"))
+    t = pkg.GaussianProcessTransportationDiffeo(kernel_transport=kern(g["c"], g["ell"], g["s2"]))
+    t.source_distribution, t.target_distribution = g["S"], g["T"]
+    t.training_traj = g["traj_in"].copy()
+    with contextlib.redirect_stdout(io.StringIO()):
+        t.fit_transportation(optimize=False)
+        err = t.check_invertibility()
+    assert abs(err - float(g["invertibility_error"])) / float(g["invertibility_error"]) < 1e-9
+    assert rel(t.traj_rotated_inv, g["traj_rotated_inv"]) < TOL_MEAN
+    # one objective evaluation: LML optimisation with 5 restarts (global RNG seeded as the golden run), then the inverse-map error
+    t2 = pkg.GaussianProcessTransportationDiffeo(kernel_transport=kern(g["c"], g["ell"], g["s2"]))
+    t2.source_distribution, t2.target_distribution = g["S"], g["T"]
+    t2.training_traj = g["traj_in"].copy()
+    np.random.seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        e2 = t2.diffeomorphism_error(FixedTrial(5.0))
+    assert abs(t2.gp_delta_map.gp.log_marginal_likelihood_value_ - float(g["diffeo_lml"])) < 1e-6 * abs(float(g["diffeo_lml"]))
+    assert abs(e2 - float(g["diffeo_error_ml5"])) / float(g["diffeo_error_ml5"]) < 1e-4
+    with pytest.raises(ImportError):
+        t2.optimize_diffeomorphism(n_trials=1)          # optuna is the reference's dependency; absent here, fails loudly
+
+
+def test_active_learning_gp_vs_reference(golden_dir):
+    import gaussian_process_transportation_b200 as pkg
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+    g = np.load(os.path.join(golden_dir, "f4_al_fixed.npz"))
+    k = C(float(g["c"]), constant_value_bounds="fixed") * RBF(g["ell"], length_scale_bounds="fixed") + \
+        WhiteKernel(float(g["s2"]), noise_level_bounds="fixed")
+    al = pkg.GaussianProcessAL(kernel=k, n_restarts_optimizer=0, n_samples_max=int(g["n_samples_max"]))
+    np.random.seed(int(g["seed"]))
+    with contextlib.redirect_stdout(io.StringIO()):
+        al.fit(g["X"], g["Y"])
+    assert al.X.shape == g["X_sel"].shape and np.array_equal(al.X, g["X_sel"]) and np.array_equal(al.Y, g["Y_sel"])   # same greedy order
+    mean, std = al.predict(g["xq"])
+    dy, ds = al.derivative(g["xq"])
+    sc = np.sqrt(float(g["c"]) + float(g["s2"]))
+    assert rel(mean, g["mean"]) < TOL_MEAN and np.max(np.abs(std - g["std"])) / sc < TOL_STD
+    assert dy.shape == g["dy_dx"].shape and ds.shape == g["dsigma_dx"].shape
+    assert rel(dy, g["dy_dx"]) < TOL_MEAN and rel(ds, g["dsigma_dx"]) < 1e-6
+    assert abs(al.max_var - float(g["max_var"])) < 1e-15
+
+
+def test_active_learning_gp_with_refits_vs_reference(golden_dir):
+    """Hyper-parameters re-optimised after every added point (the class default): same greedy subset, same final optimum."""
+    import gaussian_process_transportation_b200 as pkg
+    g = np.load(os.path.join(golden_dir, "f4_al_optimised.npz"))
+    al = pkg.GaussianProcessAL(kernel=kern(g["k0_c"], g["k0_ell"], g["k0_s2"]), n_restarts_optimizer=0, n_samples_max=int(g["n_samples_max"]))
+    np.random.seed(int(g["seed"]))
+    with contextlib.redirect_stdout(io.StringIO()):
+        al.fit(g["X"], g["Y"])
+    assert np.array_equal(al.X, g["X_sel"])
+    assert abs(al.gp.log_marginal_likelihood_value_ - float(g["lml"])) < 1e-6 * max(1.0, abs(float(g["lml"])))
+    mean, std = al.predict(g["xq"])
+    assert rel(mean, g["mean"]) < 1e-5
+    assert np.max(np.abs(std - g["std"])) / np.sqrt(float(g["c"]) + float(g["s2"])) < 1e-5

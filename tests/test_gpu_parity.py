@@ -423,6 +423,26 @@ def test_int8_sliced_full_size_n4096():
         eng.set_variance_mode(2, 7)
 
 
+def test_generator_product_overlap_is_bit_identical():
+    """gptb_set_query_pipeline: double-buffered batches with the generator on its own stream give the same bits as the serial order."""
+    from gaussian_process_transportation_b200 import _lib as L
+    from oracle.gp_oracle import synthetic_pairs
+    S, T = synthetic_pairs(1000, 3, seed=3)
+    eng = L.Engine(0)
+    eng.set_train(S, T - S)
+    assert eng.factorize(0.1, [0.1] * 3, 1e-4, 1e-10)[0] == 0
+    eng.set_variance_mode("int8w5")
+    xq = -0.1 + 1.2 * np.random.default_rng(9).random((40000 + 77, 3))      # 5 batches of 8192 + a ragged tail
+    vel = np.random.default_rng(10).normal(size=xq.shape)
+    fl = L.MEAN | L.STD | L.JAC | L.JACVAR | L.VELOCITY
+    a = eng.query(xq, fl, vel)
+    eng.set_query_pipeline(True)
+    b = eng.query(xq, fl, vel)
+    c = eng.query(xq, fl, vel)
+    for k in a:
+        assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k]), k
+
+
 def test_refit_invalidates_cached_inverse_factor_and_digit_planes():
     """A second fit on the same handle must not reuse the inverse factor / int8 digit planes of the first one."""
     from gaussian_process_transportation_b200 import _lib as L

@@ -102,3 +102,50 @@ def test_quaternion_restatement_self_consistency():
     assert np.max(np.abs(qq * s - q)) < 1e-12
     one = np.array([1.0, 0, 0, 0])
     assert np.allclose(quat_mul(one, q), q)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SURVEY section-8 "next" row f4: the oracle restatements of the Diffeo flow and the active-learning GP against
+# goldens from the unmodified reference (oracle/make_golden_f4.py)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["f4_diffeo2d.npz", "f4_diffeo3d.npz"])
+def test_oracle_diffeo_flow_matches_reference_golden(golden_dir, name):
+    import contextlib, io
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+    from oracle.gp_oracle import OracleDiffeo
+    g = np.load(os.path.join(golden_dir, name))
+    k = C(float(g["c"])) * RBF(g["ell"]) + WhiteKernel(float(g["s2"]))
+    t = OracleDiffeo(k)
+    t.source_distribution, t.target_distribution = g["S"], g["T"]
+    t.training_traj, t.training_delta = g["traj_in"].copy(), g["delta_in"].copy()
+    with contextlib.redirect_stdout(io.StringIO()):
+        t.fit_transportation(optimize=False)
+        t.apply_transportation()
+    assert np.allclose(t.training_traj, g["traj_out"], rtol=1e-11, atol=1e-13)
+    assert np.allclose(t.training_delta, g["delta_out"], rtol=1e-10, atol=1e-13)
+    assert np.allclose(t.std, g["std"], rtol=0, atol=1e-10)
+    assert np.allclose(t.var_vel_transported, g["var_vel"], rtol=1e-8, atol=1e-16)
+    if "invertibility_error" in g.files:
+        t2 = OracleDiffeo(k)
+        t2.source_distribution, t2.target_distribution = g["S"], g["T"]
+        t2.training_traj = g["traj_in"].copy()
+        with contextlib.redirect_stdout(io.StringIO()):
+            t2.fit_transportation(optimize=False)
+            assert abs(t2.check_invertibility() - float(g["invertibility_error"])) < 1e-9 * float(g["invertibility_error"])
+
+
+def test_oracle_active_learning_gp_matches_reference_golden(golden_dir):
+    import contextlib, io
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+    from oracle.gp_oracle import OracleGPAL
+    g = np.load(os.path.join(golden_dir, "f4_al_fixed.npz"))
+    k = C(float(g["c"]), constant_value_bounds="fixed") * RBF(g["ell"], length_scale_bounds="fixed") + \
+        WhiteKernel(float(g["s2"]), noise_level_bounds="fixed")
+    np.random.seed(int(g["seed"]))
+    with contextlib.redirect_stdout(io.StringIO()):
+        al = OracleGPAL(k, n_restarts_optimizer=0, n_samples_max=int(g["n_samples_max"])).fit(g["X"], g["Y"])
+    assert np.array_equal(al.X, g["X_sel"])
+    mean, std = al.predict(g["xq"])
+    dy, ds = al.derivative(g["xq"])
+    assert np.allclose(mean, g["mean"], rtol=1e-11, atol=1e-13) and np.allclose(std, g["std"], rtol=0, atol=1e-10)
+    assert np.allclose(dy, g["dy_dx"], rtol=1e-10, atol=1e-12) and np.allclose(ds, g["dsigma_dx"], rtol=1e-7, atol=1e-12)
