@@ -31,6 +31,7 @@ SYMBOLS = {
     "gptb_query_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p] + [C.c_void_p] * 9),
     "gptb_query_cov": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp, _dp]),
     "gptb_transport_orientation": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, _dp, _dp]),
+    "gptb_transport_stiffness": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, _dp, _dp]),
     "gptb_export_L": (C.c_int, [C.c_void_p, _dp]),
     "gptb_export_alpha": (C.c_int, [C.c_void_p, _dp]),
     "gptb_export_Kinv": (C.c_int, [C.c_void_p, _dp]),
@@ -229,6 +230,17 @@ class Engine:
         out, jphi = np.empty((M, 4)), np.empty((M, 3, 3))
         if M:
             self._check(self.lib.gptb_transport_orientation(self.h, ptr(pos), ptr(ori), M, ptr(out), ptr(jphi)), "gptb_transport_orientation")
+        return out, jphi
+
+    def transport_stiffness(self, pos, stiff):
+        """K_hat = Jphi(pos) K Jphi(pos)^T on the device; returns (stiff_out (M,d,d), jphi (M,d,d))."""
+        pos, stiff = as_f64(pos), as_f64(stiff)
+        M, d = pos.shape
+        if stiff.shape != (M, d, d):
+            raise ValueError(f"stiffness transport needs pos (M,d) and stiffness (M,d,d), got {pos.shape} and {stiff.shape}")
+        out, jphi = np.empty((M, d, d)), np.empty((M, d, d))
+        if M:
+            self._check(self.lib.gptb_transport_stiffness(self.h, ptr(pos), ptr(stiff), M, ptr(out), ptr(jphi)), "gptb_transport_stiffness")
         return out, jphi
 
     def query_dev(self, x_ptr, M, flags, vel_ptr=0, mean=0, std=0, jac=0, jacvar=0, xhat=0, vhat=0, vvar=0, jphi=0, dvar=0):

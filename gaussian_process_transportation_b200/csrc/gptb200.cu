@@ -1037,6 +1037,51 @@ extern "C" int gptb_transport_orientation(gptb_handle* h, const double* pos, con
     return 0;
 }
 
+extern "C" int gptb_transport_stiffness(gptb_handle* h, const double* pos, const double* stiff, int64_t M, double* stiff_out, double* jphi) {
+    if (!h || M < 0) return -1;
+    if (M == 0) return 0;
+    if (!pos || !stiff || !stiff_out) return -1;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->have_alpha) GPTB_FAIL(h, -1, "gptb_transport_stiffness: model is not fitted");
+    const int d = h->d;
+    if (d != h->p || d < 2) GPTB_FAIL(h, -1, "stiffness transport needs a square map (d = p >= 2), got d=%d p=%d", h->d, h->p);
+    const size_t dd = (size_t)d * d;
+    double *pd = nullptr, *kd = nullptr, *jd = nullptr, *jp = nullptr, *od = nullptr;
+    auto cleanup = [&]() {
+        for (double* q : {pd, kd, jd, jp, od})
+            if (q) cudaFree(q);
+    };
+    auto fail = [&](cudaError_t e, int line) {
+        cleanup();
+        char b[256];
+        snprintf(b, sizeof(b), "CUDA error %s at %s:%d", cudaGetErrorString(e), __FILE__, line);
+        h->err = b;
+        return -2;
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&pd, sizeof(double) * M * d)) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMalloc(&kd, sizeof(double) * M * dd)) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMalloc(&jd, sizeof(double) * M * dd)) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMalloc(&jp, sizeof(double) * M * dd)) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMalloc(&od, sizeof(double) * M * dd)) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMemcpyAsync(pd, pos, sizeof(double) * M * d, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMemcpyAsync(kd, stiff, sizeof(double) * M * dd, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return fail(e, __LINE__);
+    // Jphi(x) = (I + Jpsi(gamma(x))) R: the Jacobian of the whole map at x, as for the velocity (policy_transportation.py:37-46)
+    int rc = gptb_query_dev(h, pd, M, GPTB_JAC | GPTB_JPHI | GPTB_AFFINE_IN, nullptr, nullptr, nullptr, jd, nullptr, nullptr, nullptr, nullptr, jp, nullptr);
+    if (rc) { cleanup(); return rc; }
+    const unsigned grid = (unsigned)((M + 127) / 128);
+    if (d == 2) stiffness_transport_kernel<2><<<grid, 128, 0, h->stream>>>(jp, kd, M, od);
+    else if (d == 3) stiffness_transport_kernel<3><<<grid, 128, 0, h->stream>>>(jp, kd, M, od);
+    else stiffness_transport_kernel<4><<<grid, 128, 0, h->stream>>>(jp, kd, M, od);
+    h->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaMemcpyAsync(stiff_out, od, sizeof(double) * M * dd, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) return fail(e, __LINE__);
+    if (jphi && (e = cudaMemcpyAsync(jphi, jp, sizeof(double) * M * dd, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) return fail(e, __LINE__);
+    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return fail(e, __LINE__);
+    cleanup();
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // exports
 // ---------------------------------------------------------------------------------------------------------------

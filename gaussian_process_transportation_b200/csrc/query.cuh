@@ -591,4 +591,43 @@ __global__ void __launch_bounds__(128) quat_transport_kernel(const double* __res
     out[i * 4 + 3] = aw * bz + ax * by - ay * bx + az * bw;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Stiffness epilogue: K_hat = Jphi K Jphi^T per point (a stiffness / damping matrix is a (0,2)-type quantity of the demo
+// frame; it follows the local linearisation of the map like the velocity does).  The reference code has no stiffness
+// transport (its README announces it); for an orthogonal Jphi every candidate form reduces
+// to this congruence.  One thread per point, everything in registers.
+// ------------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) stiffness_transport_kernel(const double* __restrict__ jphi, const double* __restrict__ Kin, long long M,
+                                                                  double* __restrict__ Kout) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    double J[D][D], K[D][D], T[D][D];
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            J[r][c] = jphi[i * D * D + r * D + c];
+            K[r][c] = Kin[i * D * D + r * D + c];
+        }
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) s = fma(J[r][k], K[k][c], s);
+            T[r][c] = s;
+        }
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) s = fma(T[r][k], J[c][k], s);
+            Kout[i * D * D + r * D + c] = s;
+        }
+}
+
 }  // namespace gptb

@@ -26,6 +26,9 @@ class GaussianProcessTransportation():
             self.training_traj, self.std = self.method.transport(self.training_traj_old)
         if hasattr(self, 'training_ori'):
             self.training_ori = self.method.transport_orientation(self.training_traj_old, self.training_ori)
+        if hasattr(self, 'training_stiff'):
+            # not in the reference façade (its README announces stiffness transport, the code has none): K_hat = Jphi K Jphi^T
+            self.training_stiff = self.method.transport_stiffness(self.training_traj_old, self.training_stiff)
 
     def sample_transportation(self):
         return self.method.sample_transportation(self.training_traj_old)

@@ -95,6 +95,21 @@ class PolicyTransportation():
         print("The Jacobain of the map as shape ", J_phi[0].shape, " but it should be (3x3)")
         print("Robot orientation is not transported")
 
+    # -- stiffness -------------------------------------------------------------------------------------------------
+    def transport_stiffness(self, pos, stiffness):
+        """K_hat = Jphi K Jphi^T with Jphi = R + Jpsi(gamma(pos)) R, the linearisation the velocity transport uses.
+        Not part of the reference code (README.md:6 announces it) -- provided because the transport
+        of "position, velocity, orientation and stiffness" is the stated scope.  stiffness: (M, d, d)."""
+        stiffness = np.asarray(stiffness, dtype=np.float64)
+        if self._fused:
+            self.delta_map._ensure_fitted_factor()
+            out, _ = self.delta_map._engine.transport_stiffness(pos, stiffness)
+            return out
+        pos_rotated = self.affine_transform.predict(pos)
+        J_gamma = self.affine_transform.derivative(pos)
+        J_phi = J_gamma + self.delta_map.derivative(pos_rotated) @ J_gamma
+        return J_phi @ stiffness @ np.transpose(J_phi, (0, 2, 1))
+
     # -- everything the façade needs, one generator pass --------------------------------------------------------------
     def transport_all(self, pos, vel=None):
         """Position (+std) and, when `vel` is given, velocity (+variance) in a single fused query (B200 path only)."""

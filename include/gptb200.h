@@ -110,6 +110,13 @@ int gptb_query_cov(gptb_handle* h, const double* x, int64_t M, double* mean, dou
  * pos (M,3), ori (M,4) as (w,x,y,z) in; ori_out (M,4); jphi (M,3,3) optional (may be NULL).  Needs d == p == 3. */
 int gptb_transport_orientation(gptb_handle* h, const double* pos, const double* ori, int64_t M, double* ori_out, double* jphi);
 
+/* ---- stiffness transport: K_hat = Jphi K Jphi^T per point, Jphi(x) = (I + Jpsi(gamma(x))) R the Jacobian of the whole map
+ * at x (the linearisation the velocity transport uses, policy_transportation.py:37-46).  NOT in the reference code: its
+ * README (README.md:6) and the paper announce stiffness transport, the repository has no implementation; for an orthogonal
+ * Jphi every candidate form reduces to this congruence.  pos (M,d), stiff (M,d,d) in;
+ * stiff_out (M,d,d); jphi (M,d,d) optional (may be NULL).  Needs d == p. */
+int gptb_transport_stiffness(gptb_handle* h, const double* pos, const double* stiff, int64_t M, double* stiff_out, double* jphi);
+
 /* ---- read-back of fitted state (GaussianProcess attributes `gp.L_`, `gp.alpha_`, `K_inv`; gaussian_process.py:42-43).
  * L is (N,N) lower (upper part zero), alpha is (N,p), Kinv is (N,N) symmetric. */
 int gptb_export_L(gptb_handle* h, double* L);

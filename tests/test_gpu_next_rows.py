@@ -117,3 +117,44 @@ def test_active_learning_gp_with_refits_vs_reference(golden_dir):
     mean, std = al.predict(g["xq"])
     assert rel(mean, g["mean"]) < 1e-5
     assert np.max(np.abs(std - g["std"])) / np.sqrt(float(g["c"]) + float(g["s2"])) < 1e-5
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_stiffness_transport_congruence(d):
+    """f3: K_hat = Jphi K Jphi^T with Jphi = R + Jpsi(gamma(x)) R (no reference implementation exists: checked against the oracle's
+    Jacobians and through properties -- symmetry / positive-definiteness preserved, pure rotation for a rigid map)."""
+    import gaussian_process_transportation_b200 as pkg
+    from oracle.gp_oracle import OraclePolicyTransportation, SkGaussianProcess, synthetic_pairs, helix_queries
+    S, T = synthetic_pairs(200, d, seed=6)
+    k = kern(0.1, [0.2] * d, 1e-4)
+    mine = pkg.PolicyTransportation(pkg.GaussianProcess(kernel=k, optimizer=None))
+    ora = OraclePolicyTransportation(SkGaussianProcess(kernel=k, optimizer=None))
+    with contextlib.redirect_stdout(io.StringIO()):
+        mine.fit(S, T)
+        ora.fit(S, T)
+    pos, _ = helix_queries(50, d)
+    rng = np.random.default_rng(2)
+    A = rng.normal(size=(50, d, d))
+    K = A @ np.transpose(A, (0, 2, 1)) + 50.0 * np.eye(d)
+    out = mine.transport_stiffness(pos, K)
+    pr = ora.affine_transform.predict(pos)
+    Jg = ora.affine_transform.derivative(pos)
+    Jphi = Jg + ora.delta_map.derivative(pr) @ Jg
+    want = Jphi @ K @ np.transpose(Jphi, (0, 2, 1))
+    assert rel(out, want) < TOL_MEAN
+    assert np.allclose(out, np.transpose(out, (0, 2, 1)), rtol=1e-12, atol=1e-12) and np.all(np.linalg.eigvalsh(out) > 0)
+    # rigid map (target = rotated source, zero delta): Jphi = R and the stiffness is simply rotated
+    th = 0.3
+    R = np.eye(d); R[0, 0], R[0, 1], R[1, 0], R[1, 1] = np.cos(th), -np.sin(th), np.sin(th), np.cos(th)
+    rigid = pkg.PolicyTransportation(pkg.GaussianProcess(kernel=k, optimizer=None))
+    with contextlib.redirect_stdout(io.StringIO()):
+        rigid.fit(S, S @ R.T + 0.1)
+    out2 = rigid.transport_stiffness(pos, K)
+    assert rel(out2, R @ K @ R.T) < 1e-8
+    # façade attribute
+    g = pkg.GaussianProcessTransportation(kernel_transport=k)
+    g.method = mine
+    g.training_traj, g.training_stiff = pos.copy(), K.copy()
+    with contextlib.redirect_stdout(io.StringIO()):
+        g.apply_transportation()
+    assert np.array_equal(g.training_stiff, out)
