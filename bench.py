@@ -59,35 +59,52 @@ def affine_and_delta(S, T):
 
 
 class ClockSampler(threading.Thread):
+    """One streaming `nvidia-smi -lms 100` process; every sample is time-stamped so that the summary can be restricted to
+    the timed regions (the int8 products run at the power cap with the SM clock near 1.7 GHz, the FP64 phases at 1.965 GHz:
+    a median over the whole run would hide that)."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                self.samples.append([s.strip() for s in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            while not self.stop_flag:
+                line = self.proc.stdout.readline()
+                if not line:
+                    break
+                self.samples.append((time.perf_counter(), [v.strip() for v in line.split(",")]))
+        except Exception:
+            pass
 
-    def summary(self):
-        sm, mx, reasons = [], 0, set()
+    def stop(self):
+        self.stop_flag = True
+        try:
+            if self.proc:
+                self.proc.kill()
+        except Exception:
+            pass
+        self.join(timeout=2)
+
+    def summary(self, windows=None):
+        sm, pw, mx, reasons = [], [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for t, s in self.samples:
+            if windows and not any(a <= t <= b for a, b in windows):
+                continue
             try:
-                sm.append(float(s[0])); mx = max(mx, float(s[1]))
-                for n, v in zip(names, s[2:6]):
+                sm.append(float(s[0])); mx = max(mx, float(s[1])); pw.append(float(s[2]))
+                for n, v in zip(names, s[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "power_w": float(np.median(pw)) if pw else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def measure_dgemm_peak(torch, dev, n=6144):
@@ -120,7 +137,16 @@ def measure_int8_peak(torch, dev, n=8192):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); torch._int_mm(a, b); e1.record(); torch.cuda.synchronize(dev)
             best = min(best, e0.elapsed_time(e1))
-        return 2.0 * n ** 3 / best * 1e-9, f"cuBLASLt int8 GEMM {n}^3 (torch._int_mm) measured live in this run"
+        # the same GEMM back to back for ~1.5 s: the rate the library sustains under the 1 kW power cap (what a kernel timed
+        # inside a long step should be compared with; MEASURED_PEAKS.json carries the bf16 analogue of both figures)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(10, int(1.5e3 / best))
+        e0.record()
+        for _ in range(reps):
+            torch._int_mm(a, b)
+        e1.record(); torch.cuda.synchronize(dev)
+        measure_int8_peak.sustained = 2.0 * n ** 3 * reps / e0.elapsed_time(e1) * 1e-9
+        return 2.0 * n ** 3 / best * 1e-9, f"cuBLASLt int8 GEMM {n}^3 (torch._int_mm) measured live in this run, best single launch (burst)"
     except Exception as exc:  # pragma: no cover
         try:
             pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -214,7 +240,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -322,7 +348,10 @@ def main():
         sampler.start()
     launches0 = eng.launch_count()
     eng.timing(True); eng.timing_reset()
+    windows = []
+    t_w = time.perf_counter()
     ms_total = timed(step_dev, K)
+    windows.append((t_w, time.perf_counter()))
     trmm_ms, trmm_n = eng.kernel_time(0)
     gen_ms, gen_n = eng.kernel_time(1)
     eng.timing(False); eng.timing_reset()
@@ -355,12 +384,13 @@ def main():
         assert rc == 0, eng.error()
 
     step_e2e()
-    Ke = max(1, min(K, 3))
+    Ke = max(1, min(K, 5))
+    t_w = time.perf_counter()
     e2e_ms = timed(step_e2e, Ke)
+    windows.append((t_w, time.perf_counter()))
     e2e_value = world * M * Ke / (e2e_ms * 1e-3)
     if sampler:
-        sampler.stop_flag = True
-        sampler.join(timeout=2)
+        sampler.stop()
     h2d = M * d * 8
     d2h = M * (p + p + p * d) * 8
 
@@ -390,7 +420,10 @@ def main():
             roofline = {"bound": "tensor", "kernel": f"ozaki_trmm_kernel<{S_}> (tcgen05.mma kind::i8, TMEM accumulators, {pairs} products of {bits}-bit digit planes)",
                         "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": achieved / int8_peak, "traffic": traffic,
                         "traffic_unit": "bytes/launch (ncu dram read+write)",
-                        "peak_source": int8_src, "algorithmic_ops_per_launch": ops_per_launch, "launch_ms": avg_launch_ms,
+                        "peak_source": int8_src, "peak_sustained": getattr(measure_int8_peak, "sustained", None),
+                        "frac_of_sustained": (achieved / measure_int8_peak.sustained) if getattr(measure_int8_peak, "sustained", None) else None,
+                        "peak_sustained_source": "the same cuBLASLt int8 GEMM back to back for ~1.5 s under the power cap (this kernel is timed inside a long step)",
+                        "algorithmic_ops_per_launch": ops_per_launch, "launch_ms": avg_launch_ms,
                         "fp64_equivalent_tflops": q_per_launch * Npad * (Npad + 64.0) / (avg_launch_ms * 1e-3) * 1e-12,
                         "fp64_dgemm_peak_tflops": dgemm_peak, "share_of_step": trmm_ms / ms_total,
                         "generator_share_of_step": gen_ms / ms_total}
@@ -449,7 +482,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "query-points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / Ke, "steps": Ke},
                 "gpu_launches": int(launches), "roofline": roofline, "fp64_dmma_variance": other_out, "cpu_baseline": cpu,
-                "clocks": sampler.summary() if sampler else None}
+                "clocks": dict(sampler.summary(windows), scope="samples inside the two timed regions (device-resident and e2e), 100 ms period",
+                               whole_run=sampler.summary()) if sampler else None}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
