@@ -9,6 +9,9 @@ predictive std and analytic Jacobian).  Workloads (BASELIN
   c3 (default)  N = 4096 pairs, M = 2^20 queries per step per GPU          -- "synthetic 3D GPT N=4096, M=1M, 1 B200"
   c4            N = 16384 pairs, M = 2^17 queries per step per GPU         -- a batch of config 4's 64M-query stream
   c2            N = 834 (shipped cloud size), M = 2^20                      -- small-N regime
+  c5            N = 32768 pairs, M = 2^16 queries per step per GPU         -- a batch of config 5's 512M-point grid (the
+                8-bit digit planes stop at N = 26112: this workload runs the 7-bit planes, int8x6; no CPU baseline -- the
+                CPU fit alone takes minutes at this size)
 Multi-GPU: fit on rank 0, one NCCL broadcast of the model state, queries block-partitioned (weak scaling: M per GPU
 fixed), no data-path collective.
 `value`  : inputs/outputs resident in HBM (gptb_query_dev).
@@ -35,6 +38,7 @@ WORKLOADS = {
     "c3": dict(N=4096, M=1 << 20, name="c3: synthetic 3D GPT N=4096 pairs, M=2^20 queries/step/GPU, mean+std+Jacobian"),
     "c4": dict(N=16384, M=1 << 17, name="c4: synthetic 3D GPT N=16384 pairs, M=2^17-query batch/step/GPU of the 64M stream, mean+std+Jacobian"),
     "c2": dict(N=834, M=1 << 20, name="c2-size: N=834 pairs, M=2^20 queries/step/GPU, mean+std+Jacobian"),
+    "c5": dict(N=32768, M=1 << 16, name="c5: synthetic 3D GPT N=32768 pairs (FP64 fit), M=2^16-query batch/step/GPU of the 512M dense grid, mean+std+Jacobian"),
 }
 KERNEL = dict(c=0.1, ell=[0.1, 0.1, 0.1], s2=1e-4, jitter=1e-10)
 METRIC = "GP transport query-points/sec (mean+std+Jacobian) @N train"
@@ -270,6 +274,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     N, M = wl["N"], (args.queries or wl["M"])
+    if N > 16384:
+        args.no_cpu_baseline = True
     d = p = 3
     W = max(args.warmup, 3)
     K = args.steps

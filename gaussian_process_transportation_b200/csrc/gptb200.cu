@@ -547,16 +547,29 @@ static int build_bplanes(gptb_handle* h) {
     if (rc) return rc;
     const long long Npad = h->Npad;
     const int S = h->var_slices;
-    // exactness of the int32 accumulators: up to S digit-plane products of K terms, each |digit product| <= 2^12 (2^14 for 8-bit digits)
-    if ((long long)S * Npad * (h->var_bits == 8 ? 16384 : 4096) > 2147483647LL)
-        GPTB_FAIL(h, -1, "INT8-sliced variance path: N=%lld with %d %d-bit digit planes could overflow the int32 accumulators", (long long)h->N, S, h->var_bits);
+    // exactness of the int32 accumulators: a diagonal sums up to S digit-plane products of K terms, each |digit product| <= 2^12
+    // (2^14 for 8-bit digits).  When that worst-case bound fails for 8-bit digits the slicer's data-dependent bound decides:
+    // |sum_k a_k b_k| <= 128 * sum_k |b_k| over the actual digits of each inverse-factor row (most of them are far below 128).
+    const bool static_ok = (long long)S * Npad * (h->var_bits == 8 ? 16384 : 4096) <= 2147483647LL;
+    if (!static_ok && h->var_bits != 8)
+        GPTB_FAIL(h, -1, "INT8-sliced variance path: N=%lld with %d 7-bit digit planes could overflow the int32 accumulators", (long long)h->N, S);
     if (h->Bplanes) { cudaFree(h->Bplanes); h->Bplanes = nullptr; }
     CU(h, cudaMalloc(&h->Bplanes, (size_t)S * Npad * Npad));
     if (!h->scaleB) CU(h, cudaMalloc(&h->scaleB, sizeof(double) * Npad));
+    unsigned long long* l1max = reinterpret_cast<unsigned long long*>(h->scal + 32);
+    CU(h, cudaMemsetAsync(l1max, 0, sizeof(unsigned long long), h->stream));
     dispatch_digits(S, h->var_bits, [&](auto SS, auto BB) {
-        oz::slice_rows_kernel<decltype(SS)::value, decltype(BB)::value><<<(unsigned)Npad, 256, 0, h->stream>>>(h->Minv, Npad, Npad, (int)Npad, 1, h->Bplanes, Npad * Npad, h->scaleB);
+        oz::slice_rows_kernel<decltype(SS)::value, decltype(BB)::value><<<(unsigned)Npad, 256, 0, h->stream>>>(h->Minv, Npad, Npad, (int)Npad, 1, h->Bplanes, Npad * Npad, h->scaleB, l1max);
     });
     LAUNCH_CHECK(h);
+    if (!static_ok) {
+        unsigned long long l1 = 0;
+        CU(h, cudaMemcpyAsync(&l1, l1max, sizeof(l1), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        if (l1 * 128ULL > 2147483647ULL)
+            GPTB_FAIL(h, -1, "INT8-sliced variance path: N=%lld with %d 8-bit digit planes could overflow the int32 accumulators "
+                             "(largest row sum of |digits| = %llu); use the 7-bit planes (mode 1)", (long long)h->N, S, l1);
+    }
     if (!make_plane_map(&h->mapBq, h->Bplanes, Npad, Npad, S, oz::ON)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
     h->have_bplanes = true;
     return 0;

@@ -77,7 +77,7 @@ __device__ __forceinline__ void tma_load_3d_u8(void* dst, const CUtensorMap* m, 
 template <int S, int BITS>
 __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ src, long long ld, long long rows, int ncols,
                                                          int lower, int8_t* __restrict__ planes, long long plane_stride,
-                                                         double* __restrict__ scale) {
+                                                         double* __restrict__ scale, unsigned long long* __restrict__ l1max = nullptr) {
     const long long row = blockIdx.x;
     const int kmax = lower ? (int)min((long long)ncols, row + 1) : ncols;
     const double* rp = src + row * ld;
@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
     if constexpr (BITS == 8) {
         // four columns per thread, one 32-bit store per plane (ncols is a multiple of 128)
         const double mul = ldexp(1.0, 8 * S - ex);
+        unsigned long long l1 = 0;
         for (int k = 4 * threadIdx.x; k < ncols; k += 1024) {
             double v[4];
 #pragma unroll
@@ -104,7 +105,23 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
             unsigned packed[S];
             digits8_pack4<S>(v, mul, packed);
 #pragma unroll
-            for (int t = 0; t < S; ++t) *reinterpret_cast<unsigned*>(planes + (long long)t * plane_stride + row * (long long)ncols + k) = packed[t];
+            for (int t = 0; t < S; ++t) {
+                *reinterpret_cast<unsigned*>(planes + (long long)t * plane_stride + row * (long long)ncols + k) = packed[t];
+                l1 += __vsadu4(__vabsss4(packed[t]), 0u);          // sum of |digit| over the four bytes (|-128| saturates to 127: +1 each below)
+                l1 += __popc(__vcmpeq4(packed[t], 0x80808080u) & 0x01010101u);
+            }
+        }
+        if (l1max != nullptr) {
+            // data-dependent exactness bound of the int32 accumulators: |sum_k a_k b_k| <= 128 * sum_k |b_k|, summed over this row's planes
+            __syncthreads();
+            unsigned long long* redl = reinterpret_cast<unsigned long long*>(red);
+            redl[threadIdx.x] = l1;
+            __syncthreads();
+            for (int w = 128; w > 0; w >>= 1) {
+                if (threadIdx.x < w) redl[threadIdx.x] += redl[threadIdx.x + w];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) atomicMax(l1max, redl[0]);
         }
     } else {
         for (int k = threadIdx.x; k < ncols; k += 256) {

@@ -76,7 +76,8 @@ int gptb_lml(gptb_handle* h, double c, const double* ell, double s2, double jitt
  * accumulation of the digit products, FP64 recombination).  6 planes reproduce the FP64 std to ~1e-9 of sqrt(c+s2)
  * (tolerance 1e-7), 7 to ~1e-11; the posterior mean and Jacobian are unaffected.  mode 2 = the same evaluation with
  * `slices` in {4,5,6} 8-bit digit planes (the full int8 range): 5 planes (15 plane products instead of 21) give ~5e-9,
- * 6 give ~2e-11; limited to N <= 26112 by the exactness bound of the int32 accumulators (S * N * 2^14 < 2^31). */
+ * 6 give ~2e-11; limited to N <= 26112 by the worst-case exactness bound of the int32 accumulators (S * N * 2^14 < 2^31); beyond it the slicer's data-dependent
+ * bound (128 * largest row sum of |digit| of the inverse factor < 2^31) decides, and the call fails if that does not hold either. */
 int gptb_set_variance_mode(gptb_handle* h, int mode, int slices);
 
 /* ---- explicit inverse factor for the variance queries (built lazily by gptb_query when needed). */
