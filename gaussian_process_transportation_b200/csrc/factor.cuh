@@ -16,7 +16,7 @@ constexpr int MAXP = 4;
 
 // Radial profile of the stationary part: RBF (sklearn:kernels.py:1558-1587) or Matern nu = 1.5 / 2.5
 // (sklearn:kernels.py Matern.__call__), all as functions of s = sum_a ((x_a - y_a)/ell_a)^2.
-enum { KIND_RBF = 0, KIND_MATERN15 = 1, KIND_MATERN25 = 2 };
+enum { KIND_RBF = 0, KIND_MATERN15 = 1, KIND_MATERN25 = 2, KIND_MATERN05 = 3 };
 
 struct KParams {
     double c, s2, jitter;
@@ -30,6 +30,7 @@ template <typename EXPF>
 __device__ __forceinline__ double kernel_profile(double s, int kind, EXPF expf_neg) {
     if (kind == KIND_RBF) return expf_neg(-0.5 * s);
     const double r = sqrt(s);
+    if (kind == KIND_MATERN05) return expf_neg(-r);            // exponential kernel (sklearn Matern nu=0.5)
     if (kind == KIND_MATERN15) {
         const double t = 1.7320508075688772 * r;          // sqrt(3) * dist
         return (1.0 + t) * expf_neg(-t);
@@ -41,6 +42,7 @@ __device__ __forceinline__ double kernel_profile(double s, int kind, EXPF expf_n
 // d profile / d log ell_a = grad_factor(s) * d2_a  with d2_a = ((x_a - y_a)/ell_a)^2   (sklearn Matern/RBF eval_gradient)
 __device__ __forceinline__ double kernel_grad_factor(double s, int kind) {
     if (kind == KIND_RBF) return exp(-0.5 * s);
+    if (kind == KIND_MATERN05) return s > 0.0 ? exp(-sqrt(s)) / sqrt(s) : 0.0;   // sklearn zeroes the 0/0 entries (kernels.py Matern nu=0.5)
     if (kind == KIND_MATERN15) return 3.0 * exp(-sqrt(3.0 * s));
     const double t = sqrt(5.0 * s);
     return 5.0 / 3.0 * (t + 1.0) * exp(-t);

@@ -315,7 +315,7 @@ extern "C" int gptb_set_variance_mode(gptb_handle* h, int mode, int slices) {
 
 extern "C" int gptb_set_kernel_kind(gptb_handle* h, int kind) {
     if (!h) return -1;
-    if (kind < 0 || kind > 2) GPTB_FAIL(h, -1, "unknown kernel kind %d", kind);
+    if (kind < 0 || kind > 3) GPTB_FAIL(h, -1, "unknown kernel kind %d", kind);
     if (kind != h->kp.kind) h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = false;
     h->kp.kind = kind;
     return 0;

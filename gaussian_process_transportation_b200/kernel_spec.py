@@ -19,19 +19,19 @@ def check_supported(kernel):
     # exact types: sklearn's Matern subclasses RBF but has a different radial profile
     ok = (type(kernel) is Sum and type(kernel.k1) is Product and type(kernel.k1.k1) is ConstantKernel
           and type(kernel.k2) is WhiteKernel
-          and (type(kernel.k1.k2) is RBF or (type(kernel.k1.k2) is Matern and kernel.k1.k2.nu in (1.5, 2.5))))
+          and (type(kernel.k1.k2) is RBF or (type(kernel.k1.k2) is Matern and kernel.k1.k2.nu in (0.5, 1.5, 2.5))))
     if not ok:
         raise UnsupportedKernel(
-            "gaussian_process_transportation_b200 implements ConstantKernel * {RBF | Matern(nu=1.5|2.5)} + WhiteKernel only "
+            "gaussian_process_transportation_b200 implements ConstantKernel * {RBF | Matern(nu=0.5|1.5|2.5)} + WhiteKernel only "
             f"(got {kernel!r}); there is no CPU fallback for other kernels")
 
 
 def kernel_kind(kernel):
-    """Engine code of the stationary factor's radial profile: 0 RBF, 1 Matern-1.5, 2 Matern-2.5."""
+    """Engine code of the stationary factor's radial profile: 0 RBF, 1 Matern-1.5, 2 Matern-2.5, 3 Matern-0.5."""
     k = kernel.k1.k2
     if type(k) is RBF:
         return 0
-    return 1 if k.nu == 1.5 else 2
+    return {0.5: 3, 1.5: 1, 2.5: 2}[k.nu]
 
 
 def read_params(kernel, d):

@@ -51,7 +51,8 @@ int  gptb_version(void);
  * X is (N,d), Y is (N,p).  Limits: 1 <= d <= 4, 1 <= p <= 4. */
 int gptb_set_train(gptb_handle* h, const double* X, const double* Y, int64_t N, int d, int p);
 
-/* ---- radial profile of the stationary factor: 0 = RBF (default), 1 = Matern nu=1.5, 2 = Matern nu=2.5
+/* ---- radial profile of the stationary factor: 0 = RBF (default), 1 = Matern nu=1.5, 2 = Matern nu=2.5, 3 = Matern nu=0.5
+ * (exponential; example/comparisons/multi_reference_frames/multiple_source_same_target_with_gpt.py:46)
  * (sklearn:kernels.py Matern.__call__; the dynamics GPs of the reference's demos use C*Matern(nu=2.5)+White,
  * example/2D/surface_generalization.py:49).  Applies to every later factorize / lml / query call.
  * Note: `derivative` keeps the reference's closed form dk = k (X - x)/ell^2 for every profile (gaussian_process.py:82-87). */

@@ -52,8 +52,9 @@ def test_kernel_parsing_and_gradient_mapping():
     assert kernel_kind(k) == 0
     assert kernel_kind(C(0.1) * Matern(0.1, nu=1.5) + WhiteKernel(1e-4)) == 1
     assert kernel_kind(C(0.1) * Matern([0.1, 0.2], nu=2.5) + WhiteKernel(1e-4)) == 2
+    assert kernel_kind(C(0.1) * Matern(0.1, nu=0.5) + WhiteKernel(1e-4)) == 3
     with pytest.raises(UnsupportedKernel):
-        check_supported(C(0.1) * Matern(0.1, nu=0.5) + WhiteKernel(1e-4))
+        check_supported(C(0.1) * Matern(0.1, nu=3.5) + WhiteKernel(1e-4))
     with pytest.raises(UnsupportedKernel):
         check_supported(RBF(0.1))
     with pytest.raises(ValueError):
