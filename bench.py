@@ -254,6 +254,9 @@ def main():
                     help="evaluation of the predictive-variance products: FP64 DMMA tile engine, or the INT8-sliced tcgen05 path "
                          "(exact int32 digit-plane GEMMs, FP64 recombination): int8xS = S 7-bit digit planes (6 keep std within ~2e-9 "
                          "of the FP64 path), int8wS = S 8-bit digit planes (5 planes = 15 plane products keep it within ~1e-8)")
+    ap.add_argument("--spatial", type=int, default=1,
+                    help="1: Morton-ordered training points, Morton-sorted query batches and zero-digit-plane skipping in the int8w product "
+                         "kernel (exact; include/gptb200.h gptb_set_spatial); 0: natural order, every plane product issued")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -283,6 +286,7 @@ def main():
     eng = L.Engine(local_rank)
     if args.variance != "fp64":
         eng.set_variance_mode(args.variance)
+    eng.set_spatial(bool(args.spatial))
     S, T, xq = make_inputs(N, M, rank)
     fit_ms = prep_ms = bcast_ms = None
     if rank == 0:
@@ -482,7 +486,7 @@ def main():
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
                 "data": "synthetic",
                 "config": {"workload": wl["name"], "N": N, "queries_per_step_per_gpu": M, "mode": "A (mean+std+Jacobian)",
-                           "kernel": "C(0.1)*RBF([0.1]*3)+White(1e-4)", "parallelism": f"query-sharded x{world}", "variance": args.variance,
+                           "kernel": "C(0.1)*RBF([0.1]*3)+White(1e-4)", "parallelism": f"query-sharded x{world}", "variance": args.variance, "spatial": bool(args.spatial),
                            "l2_policy": "inputs larger than L2: each step streams a >=2 GiB k* workspace"},
                 "fit_ms": fit_ms, "prepare_variance_ms": prep_ms, "bcast_ms": bcast_ms,
                 "e2e": {"value": e2e_value, "unit": "query-points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -46,6 +46,7 @@ SYMBOLS = {
     "gptb_set_trailing_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "gptb_set_workspace_limit": (C.c_int, [C.c_void_p, C.c_int64]),
     "gptb_set_query_pipeline": (C.c_int, [C.c_void_p, C.c_int]),
+    "gptb_set_spatial": (C.c_int, [C.c_void_p, C.c_int]),
     "gptb_test_gemm_nt": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gptb_test_potrf_tile": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.POINTER(C.c_int)]),
 }
@@ -108,6 +109,7 @@ class Engine:
         self.h = h
         self.device = int(device)
         self.N = self.d = self.p = 0
+        self.spatial = False
 
     def close(self):
         if getattr(self, "h", None):
@@ -284,6 +286,11 @@ class Engine:
 
     def set_trailing_variant(self, variant):
         self._check(self.lib.gptb_set_trailing_variant(self.h, int(variant)), "gptb_set_trailing_variant")
+
+    def set_spatial(self, on):
+        """Morton-ordered training points + sorted query batches + zero-plane skipping (include/gptb200.h); before set_train."""
+        self._check(self.lib.gptb_set_spatial(self.h, int(on)), "gptb_set_spatial")
+        self.spatial = bool(on)
 
     def set_query_pipeline(self, on):
         """INT8-sliced path: overlap the generator of the next batch with the products of the current one (default off:

@@ -7,6 +7,10 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
+#include <numeric>
+
+#include <cub/device/device_radix_sort.cuh>   // library plumbing: radix sort of the query batch by Morton key (spatial mode)
 
 #include "query.cuh"
 #include "ozaki.cuh"
@@ -44,17 +48,25 @@ bool make_operand_map(CUtensorMap* m, const double* base, long long rows, long l
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// 3-D TMA view (k bytes, rows, plane) of int8 digit planes [S][rows][ncols]; box (64, box_rows, S), 64-byte swizzle
+// 3-D TMA view (k bytes, rows, plane) of int8 digit planes [S][rows][ncols]; box (64, box_rows, box_planes), 64-byte swizzle
 // (the K-major shared-memory layout tcgen05.mma expects).
-bool make_plane_map(CUtensorMap* m, const int8_t* base, long long rows, long long ncols, int S, int box_rows) {
+bool make_plane_map(CUtensorMap* m, const int8_t* base, long long rows, long long ncols, int S, int box_rows, int box_planes) {
     EncodeTiledFn enc = get_encoder();
     if (!enc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)ncols, (cuuint64_t)rows, (cuuint64_t)S};
     cuuint64_t strides[2] = {(cuuint64_t)ncols, (cuuint64_t)rows * (cuuint64_t)ncols};
-    cuuint32_t box[3] = {(cuuint32_t)oz::OKB, (cuuint32_t)box_rows, (cuuint32_t)S};
+    cuuint32_t box[3] = {(cuuint32_t)oz::OKB, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
     cuuint32_t es[3] = {1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// one view per box depth 1 .. S (oz::PlaneMaps): a chunk with leading zero planes loads only the planes it needs
+bool make_plane_maps(oz::PlaneMaps* pm, const int8_t* base, long long rows, long long ncols, int S, int box_rows) {
+    for (int n = 1; n <= S; ++n)
+        if (!make_plane_map(&pm->m[n - 1], base, rows, ncols, S, box_rows, n)) return false;
+    for (int n = S; n < 7; ++n) pm->m[n] = pm->m[S - 1];
+    return true;
 }
 
 }  // namespace
@@ -65,6 +77,14 @@ struct gptb_handle {
     cudaStream_t aux = nullptr;               // high-priority stream for the look-ahead diagonal tile
     cudaStream_t gen = nullptr;               // lowest-priority stream: the generator of batch i+1 runs under the int8 products of batch i
     cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_start = nullptr;
+    // spatial mode (gptb_set_spatial): training points in Morton order, query batches sorted by Morton key, zero digit planes
+    // skipped by the INT8-sliced product kernel
+    int spatial = 0;
+    std::vector<int> perm;                    // perm[i] = caller's index of internal training row i (empty: natural order)
+    bool perm_known = true;                   // false on a handle whose state arrived by broadcast (exports need the permutation)
+    MortonBox mbox{};
+    unsigned* flagsB = nullptr;               // [Npad/64][flags_stride] packed block masks of the digit planes of L^-1
+    int flags_stride = 0;                     // 32-bit words per mask row
     int pipeline = 0;                         // 1 overlaps the generator of batch i+1 with the products of batch i (opt-in: measured no gain, the
                                               // int8 products run at the 1 kW power cap, so the two kernels share one energy budget)
     std::vector<cudaEvent_t> ev_diag, ev_col; // per-step dependencies between the two streams
@@ -82,7 +102,7 @@ struct gptb_handle {
     int trailing_variant = 1;                // 0: 128x128 tiles, one CTA/SM; 1: 128x64 half tiles, two CTAs/SM
     int8_t* Bplanes = nullptr;
     double* scaleB = nullptr;
-    CUtensorMap mapBq;
+    oz::PlaneMaps mapsBq;
     bool have_bplanes = false;
     KParams kp{};
     Affine af{};
@@ -146,8 +166,10 @@ static void free_model(gptb_handle* h) {
     }
     if (h->Bplanes) cudaFree(h->Bplanes);
     if (h->scaleB) cudaFree(h->scaleB);
+    if (h->flagsB) cudaFree(h->flagsB);
     h->Bplanes = nullptr;
     h->scaleB = nullptr;
+    h->flagsB = nullptr;
     h->have_train = h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = h->have_bplanes = false;
 }
 
@@ -240,6 +262,14 @@ extern "C" int gptb_set_trailing_variant(gptb_handle* h, int variant) {
     h->trailing_variant = variant;
     return 0;
 }
+extern "C" int gptb_set_spatial(gptb_handle* h, int on) {
+    if (!h) return -1;
+    if ((on != 0) != (h->spatial != 0) && h->have_train)
+        GPTB_FAIL(h, -1, "gptb_set_spatial must be called before gptb_set_train (the training order is fixed there)");
+    if (on < 0 || on > 2) GPTB_FAIL(h, -1, "gptb_set_spatial: mode must be 0, 1 or 2");
+    h->spatial = on;          // 2 = Morton order and sorted batches, but every plane product issued (A/B of the skipping itself)
+    return 0;
+}
 extern "C" int gptb_set_query_pipeline(gptb_handle* h, int on) {
     if (!h) return -1;
     h->pipeline = on != 0;
@@ -327,9 +357,41 @@ extern "C" int gptb_set_train(gptb_handle* h, const double* X, const double* Y, 
     if (rc) return rc;
     const long long Npad = h->Npad;
     std::vector<double> xs((size_t)d * Npad, 0.0), ys((size_t)p * Npad, 0.0);
+    h->perm.clear();
+    h->perm_known = true;
+    if (h->spatial) {
+        // Morton (Z-order) permutation of the training points over their bounding box: neighbours in space become neighbours
+        // in the factor, so 64-point chunks are compact and k(x*, chunk) is uniformly tiny for far-away query tiles.  Internal
+        // order only: gptb_export_alpha / gptb_export_Kinv undo it; the posterior itself does not depend on the order.
+        MortonBox& mb = h->mbox;
+        mb.bits = (d <= 3) ? 10 : 8;
+        const double top = (double)((1u << mb.bits) - 1u);
+        for (int a = 0; a < MAXD; ++a) { mb.lo[a] = 0.0; mb.scale[a] = 0.0; }
+        for (int a = 0; a < d; ++a) {
+            double lo = X[a], hi = X[a];
+            for (long long n = 1; n < N; ++n) { lo = std::min(lo, X[n * d + a]); hi = std::max(hi, X[n * d + a]); }
+            mb.lo[a] = lo;
+            mb.scale[a] = (hi > lo) ? top / (hi - lo) : 0.0;
+        }
+        std::vector<unsigned> code((size_t)N);
+        for (long long n = 0; n < N; ++n) {
+            unsigned cd = 0;
+            for (int a = 0; a < d; ++a) {
+                double t = (X[n * d + a] - mb.lo[a]) * mb.scale[a];
+                t = (t > 0.0) ? ((t < top) ? t : top) : 0.0;
+                const unsigned cell = (unsigned)t;
+                for (int b = 0; b < mb.bits; ++b) cd |= ((cell >> b) & 1u) << (b * d + a);
+            }
+            code[(size_t)n] = cd;
+        }
+        h->perm.resize((size_t)N);
+        std::iota(h->perm.begin(), h->perm.end(), 0);
+        std::stable_sort(h->perm.begin(), h->perm.end(), [&](int i, int j) { return code[(size_t)i] < code[(size_t)j]; });
+    }
     for (long long n = 0; n < N; ++n) {
-        for (int a = 0; a < d; ++a) xs[(size_t)a * Npad + n] = X[n * d + a];
-        for (int o = 0; o < p; ++o) ys[(size_t)o * Npad + n] = Y[n * p + o];
+        const long long src = h->perm.empty() ? n : h->perm[(size_t)n];
+        for (int a = 0; a < d; ++a) xs[(size_t)a * Npad + n] = X[src * d + a];
+        for (int o = 0; o < p; ++o) ys[(size_t)o * Npad + n] = Y[src * p + o];
     }
     CU(h, cudaMemcpyAsync(h->X, xs.data(), sizeof(double) * d * Npad, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->Y, ys.data(), sizeof(double) * p * Npad, cudaMemcpyHostToDevice, h->stream));
@@ -558,8 +620,17 @@ static int build_bplanes(gptb_handle* h) {
     if (!h->scaleB) CU(h, cudaMalloc(&h->scaleB, sizeof(double) * Npad));
     unsigned long long* l1max = reinterpret_cast<unsigned long long*>(h->scal + 32);
     CU(h, cudaMemsetAsync(l1max, 0, sizeof(unsigned long long), h->stream));
+    // block masks of the non-zero digit planes (used by the product kernel in spatial mode; 8-bit planes only)
+    h->flags_stride = (int)((Npad / 64 + 3) / 4);
+    if (h->flagsB) { cudaFree(h->flagsB); h->flagsB = nullptr; }
+    if (h->var_bits == 8) {
+        if (h->flags_stride > FLAG_WORDS) GPTB_FAIL(h, -1, "INT8-sliced variance path: N=%lld exceeds the %d-chunk limit of the block masks", (long long)h->N, FLAG_WORDS * 4);
+        CU(h, cudaMalloc(&h->flagsB, sizeof(unsigned) * (size_t)(Npad / 64) * h->flags_stride));
+        CU(h, cudaMemsetAsync(h->flagsB, 0, sizeof(unsigned) * (size_t)(Npad / 64) * h->flags_stride, h->stream));
+    }
     dispatch_digits(S, h->var_bits, [&](auto SS, auto BB) {
-        oz::slice_rows_kernel<decltype(SS)::value, decltype(BB)::value><<<(unsigned)Npad, 256, 0, h->stream>>>(h->Minv, Npad, Npad, (int)Npad, 1, h->Bplanes, Npad * Npad, h->scaleB, l1max);
+        oz::slice_rows_kernel<decltype(SS)::value, decltype(BB)::value><<<(unsigned)Npad, 256, 0, h->stream>>>(h->Minv, Npad, Npad, (int)Npad, 1, h->Bplanes, Npad * Npad, h->scaleB, l1max,
+                                                                                                               h->flagsB, h->flags_stride);
     });
     LAUNCH_CHECK(h);
     if (!static_ok) {
@@ -570,7 +641,7 @@ static int build_bplanes(gptb_handle* h) {
             GPTB_FAIL(h, -1, "INT8-sliced variance path: N=%lld with %d 8-bit digit planes could overflow the int32 accumulators "
                              "(largest row sum of |digits| = %llu); use the 7-bit planes (mode 1)", (long long)h->N, S, l1);
     }
-    if (!make_plane_map(&h->mapBq, h->Bplanes, Npad, Npad, S, oz::ON)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
+    if (!make_plane_maps(&h->mapsBq, h->Bplanes, Npad, Npad, S, oz::ON)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
     h->have_bplanes = true;
     return 0;
 }
@@ -644,10 +715,19 @@ extern "C" int gptb_set_affine(gptb_handle* h, const double* R, double s, const 
 // ---------------------------------------------------------------------------------------------------------------
 static bool oz_fused_supported(int d, int p) { return d == p && (d == 2 || d == 3); }
 
+// scratch of the spatial mode for one batch: Morton keys / batch positions (radix-sort double buffers) and the block masks
+struct SpatialWs {
+    unsigned *keys_in, *keys_out, *vals_in, *vals_out;
+    void* cub_tmp;
+    size_t cub_bytes;
+    unsigned* flagsA;
+};
+
 template <int D, int P>
 static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_dev, int B, int Bpad, unsigned flags, int nrhs,
                        unsigned genflags, const QueryOut& out, long long q_off, long long Mtot, double* rhs, double* part,
-                       double* macc, double* xr, int nsplit, const CUtensorMap* mapR, void* oz_planes, double* oz_scale, int pipe_slot) {
+                       double* macc, double* xr, int nsplit, const CUtensorMap* mapR, void* oz_planes, double* oz_scale, int pipe_slot,
+                       const SpatialWs* sp) {
     const int T = h->T;
     // pipe_slot >= 0: this batch's generator runs on the low-priority stream into buffer set `pipe_slot`; the products and
     // the epilogue follow on the main stream once it has finished, so the NEXT batch's generator (FP64 pipe) overlaps them
@@ -661,8 +741,20 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
     // digit planes straight from the generator when the INT8-sliced path is on and this (d,p) has a fused instantiation
     const bool fused = (nrhs > 0 && h->var_mode == 1 && oz_fused_supported(D, P));
     int8_t* Aplanes = reinterpret_cast<int8_t*>(oz_planes);
+    const bool spatial = fused && sp != nullptr;
     if (fused) {
         DigitScales ds{};
+        if (spatial) {
+            // Morton keys of the (transformed) queries -> radix sort -> qperm; block masks start from zero
+            morton_keys_kernel<D><<<(unsigned)((B + 255) / 256), 256, 0, gs>>>(x_dev, B, af, h->mbox, sp->keys_in, sp->vals_in);
+            LAUNCH_CHECK(h);
+            size_t tmp_bytes = sp->cub_bytes;
+            CU(h, cub::DeviceRadixSort::SortPairs(sp->cub_tmp, tmp_bytes, sp->keys_in, sp->keys_out, sp->vals_in, sp->vals_out, B, 0, h->mbox.bits * D, gs));
+            CU(h, cudaMemsetAsync(sp->flagsA, 0, sizeof(unsigned) * (size_t)(rows_total / 128) * h->flags_stride, gs));
+            ds.qperm = sp->vals_out;
+            ds.flags = sp->flagsA;
+            ds.flags_stride = h->flags_stride;
+        }
         auto set = [&](int idx, double bound) {
             const int ex = digit_scale_exp(bound, h->var_bits);
             ds.down[idx] = std::ldexp(1.0, (h->var_bits == 8 ? 8 * h->var_slices : 0) - ex);   // 8-bit planes: digits8_pack4 wants 2^-e * 256^S
@@ -698,8 +790,8 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
         const int S = h->var_slices;
         const int rowtiles = (int)(rows_total / TS);
         const int T64 = (int)(h->Npad / oz::ON);
-        CUtensorMap mapAq;
-        if (!make_plane_map(&mapAq, Aplanes, rows_total, h->Npad, S, oz::OM)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
+        oz::PlaneMaps mapsAq;
+        if (!make_plane_maps(&mapsAq, Aplanes, rows_total, h->Npad, S, oz::OM)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
         if (!fused) {
             tic(h, 3);
             dispatch_digits(S, h->var_bits, [&](auto SS, auto BB) {
@@ -716,7 +808,8 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
             cudaMemsetAsync(h->info + 1, 0, sizeof(int), h->stream);      // dynamic tile counter
             oz::ozaki_trmm_kernel<SV><<<(unsigned)(ntiles < nsm ? ntiles : nsm), oz::OTHREADS, oz::Cfg<SV>::SMEM_BYTES, h->stream>>>(
-                mapAq, h->mapBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits);
+                mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits,
+                (spatial && h->spatial == 1) ? sp->flagsA : nullptr, (spatial && h->spatial == 1) ? h->flagsB : nullptr, h->flags_stride);
         });
         toc(h, 0);
         LAUNCH_CHECK(h);
@@ -728,13 +821,14 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
         toc(h, 0);
         LAUNCH_CHECK(h);
     }
-    finalize_kernel<D, P><<<(B + 127) / 128, 128, 0, h->stream>>>(macc, nsplit, part, Tpart, B, Bpad, rows_total, xr, vel_dev, h->kp, h->af, flags, out, q_off, Mtot);
+    finalize_kernel<D, P><<<(B + 127) / 128, 128, 0, h->stream>>>(macc, nsplit, part, Tpart, B, Bpad, rows_total, xr, vel_dev, h->kp, h->af, flags, out, q_off, Mtot,
+                                                                  spatial ? sp->vals_out : nullptr);
     LAUNCH_CHECK(h);
     return 0;
 }
 
 typedef int (*chunk_fn)(gptb_handle*, const double*, const double*, int, int, unsigned, int, unsigned, const QueryOut&, long long,
-                        long long, double*, double*, double*, double*, int, const CUtensorMap*, void*, double*, int);
+                        long long, double*, double*, double*, double*, int, const CUtensorMap*, void*, double*, int, const SpatialWs*);
 
 static chunk_fn pick_chunk_fn(int d, int p) {
     static const chunk_fn table[4][4] = {
@@ -788,8 +882,10 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     // INT8-sliced path with the fused generator: double-buffered batches so the generator of batch i+1 (FP64 pipe, gen stream)
     // runs under the digit-plane products of batch i (tensor pipe, main stream).  The stream is cut into >= 8 batches of
     // >= 8192 queries (enough 128 x 64 tiles to fill the persistent product kernel many times over).
+    // spatial mode (8-bit planes, fused generator): sorted batches + block masks; not combined with the overlap pipeline
+    const bool spatial_q = fused_planes && h->spatial && h->var_bits == 8;
     int nbuf = 1;
-    if (fused_planes && h->pipeline && M >= 2 * 8192) {
+    if (fused_planes && h->pipeline && !spatial_q && M >= 2 * 8192) {
         long long bp = (M / 8 + TS - 1) / TS * TS;
         if (bp < 8192) bp = 8192;
         const long long cap2 = batch_cap(2);
@@ -816,6 +912,16 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
         o_macc[b] = carve((size_t)nsplit * Bfirst * NACC);
         o_xr[b] = carve((size_t)Bfirst * d);
     }
+    SpatialWs sp{};
+    size_t o_sp[6] = {0, 0, 0, 0, 0, 0};
+    if (spatial_q) {
+        for (int i = 0; i < 4; ++i) o_sp[i] = carve(((size_t)Bfirst + 1) / 2);                 // Bfirst 32-bit words each
+        sp.cub_bytes = 0;
+        CU(h, cub::DeviceRadixSort::SortPairs(nullptr, sp.cub_bytes, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr,
+                                              (int)Bfirst, 0, h->mbox.bits * d, h->stream));
+        o_sp[4] = carve((sp.cub_bytes + 7) / 8);
+        o_sp[5] = carve(((size_t)(nrhs * Bfirst / 128) * h->flags_stride + 1) / 2);
+    }
     if (need > h->ws_bytes) {
         CU(h, cudaStreamSynchronize(h->stream));
         CU(h, cudaStreamSynchronize(h->gen));
@@ -827,6 +933,14 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     }
     char* base = reinterpret_cast<char*>(h->ws);
     double* rhs = reinterpret_cast<double*>(base + o_rhs);
+    if (spatial_q) {
+        sp.keys_in = reinterpret_cast<unsigned*>(base + o_sp[0]);
+        sp.keys_out = reinterpret_cast<unsigned*>(base + o_sp[1]);
+        sp.vals_in = reinterpret_cast<unsigned*>(base + o_sp[2]);
+        sp.vals_out = reinterpret_cast<unsigned*>(base + o_sp[3]);
+        sp.cub_tmp = base + o_sp[4];
+        sp.flagsA = reinterpret_cast<unsigned*>(base + o_sp[5]);
+    }
     QueryOut out{mean_dev, std_dev, jac_dev, jacvar_dev, xhat_dev, vhat_dev, vvar_dev, jphi_dev, dvar_dev};
     chunk_fn fn = pick_chunk_fn(d, p);
     CUtensorMap mapR_full, mapR_tail;
@@ -854,7 +968,7 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
         int rc = fn(h, x_dev + q0 * d, vel_dev ? vel_dev + q0 * d : nullptr, B, Bpad, flags, nrhs, genflags, out, q0, M, rhs,
                     reinterpret_cast<double*>(base + o_part[b]), reinterpret_cast<double*>(base + o_macc[b]),
                     reinterpret_cast<double*>(base + o_xr[b]), nsplit, mapR, base + o_ozp[b], reinterpret_cast<double*>(base + o_ozs[b]),
-                    nbuf == 2 ? b : -1);
+                    nbuf == 2 ? b : -1, spatial_q ? &sp : nullptr);
         if (rc) return rc;
         if (nbuf == 2) CU(h, cudaEventRecord(h->ev_done[b], h->stream));
     }
@@ -940,7 +1054,7 @@ static int cov_generate(gptb_handle* h, const double* x_dev, int M, int Mpad, do
     kstar_kernel<D, P, 1, 5><<<grid, 256, 0, h->stream>>>(x_dev, h->Xs, h->alpha, (int)h->N, (int)h->Npad, M, Mpad, h->kp, af, 1u, rhs, xr, macc, 1, nullptr, 0, nullptr, DigitScales{});
     LAUNCH_CHECK(h);
     QueryOut out{mean_dev, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    finalize_kernel<D, P><<<(M + 127) / 128, 128, 0, h->stream>>>(macc, 1, nullptr, h->T, M, Mpad, Mpad, xr, nullptr, h->kp, h->af, GPTB_MEAN, out, 0, M);
+    finalize_kernel<D, P><<<(M + 127) / 128, 128, 0, h->stream>>>(macc, 1, nullptr, h->T, M, Mpad, Mpad, xr, nullptr, h->kp, h->af, GPTB_MEAN, out, 0, M, nullptr);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -1111,6 +1225,7 @@ static int export_square(gptb_handle* h, const double* src, double* dst, bool lo
 extern "C" int gptb_export_L(gptb_handle* h, double* L) {
     if (!h || !L) return -1;
     if (!h->have_factor) GPTB_FAIL(h, -1, "gptb_export_L: model is not fitted");
+    if (h->spatial) GPTB_FAIL(h, -1, "gptb_export_L: in spatial mode the factor belongs to the Morton-ordered system; factorise on a handle without gptb_set_spatial for the caller's order");
     CU(h, cudaSetDevice(h->device));
     return export_square(h, h->Lbuf, L, true);
 }
@@ -1122,8 +1237,11 @@ extern "C" int gptb_export_alpha(gptb_handle* h, double* alpha) {
     std::vector<double> tmp((size_t)h->p * h->Npad);
     CU(h, cudaMemcpyAsync(tmp.data(), h->alpha, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    for (long long n = 0; n < h->N; ++n)
-        for (int o = 0; o < h->p; ++o) alpha[n * h->p + o] = tmp[(size_t)o * h->Npad + n];
+    if (h->spatial && !h->perm_known) GPTB_FAIL(h, -1, "gptb_export_alpha: this handle received its state by broadcast; export on the fitting rank");
+    for (long long n = 0; n < h->N; ++n) {
+        const long long dst = h->perm.empty() ? n : h->perm[(size_t)n];
+        for (int o = 0; o < h->p; ++o) alpha[dst * h->p + o] = tmp[(size_t)o * h->Npad + n];
+    }
     return 0;
 }
 
@@ -1133,7 +1251,15 @@ extern "C" int gptb_export_Kinv(gptb_handle* h, double* Kinv) {
     if (!h->have_factor) GPTB_FAIL(h, -1, "gptb_export_Kinv: model is not fitted");
     int rc = build_kinv(h);
     if (rc) return rc;
-    return export_square(h, h->Wbuf, Kinv, false);
+    if (h->perm.empty()) {
+        if (h->spatial && !h->perm_known) GPTB_FAIL(h, -1, "gptb_export_Kinv: this handle received its state by broadcast; export on the fitting rank");
+        return export_square(h, h->Wbuf, Kinv, false);
+    }
+    std::vector<double> tmp((size_t)h->N * h->N);
+    if ((rc = export_square(h, h->Wbuf, tmp.data(), false))) return rc;
+    for (long long i = 0; i < h->N; ++i)
+        for (long long j = 0; j < h->N; ++j) Kinv[(long long)h->perm[(size_t)i] * h->N + h->perm[(size_t)j]] = tmp[(size_t)(i * h->N + j)];
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1145,6 +1271,9 @@ static int write_header(gptb_handle* h) {
     for (int a = 0; a < MAXD; ++a) hd[6 + a] = h->kp.ell[a];
     hd[10] = h->have_minv ? 1.0 : 0.0;
     hd[11] = (double)h->kp.kind;
+    hd[12] = (double)h->spatial;
+    hd[13] = (double)h->mbox.bits;
+    for (int a = 0; a < MAXD; ++a) { hd[14 + a] = h->mbox.lo[a]; hd[18 + a] = h->mbox.scale[a]; }
     CU(h, cudaMemcpyAsync(h->header, hd, sizeof(hd), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
@@ -1183,6 +1312,11 @@ extern "C" int gptb_state_commit(gptb_handle* h) {
     CU(h, cudaMemcpy(hd, h->header, sizeof(hd), cudaMemcpyDeviceToHost));
     if ((long long)hd[0] != h->N || (int)hd[1] != h->d || (int)hd[2] != h->p) GPTB_FAIL(h, -1, "state header does not match the allocated shape");
     h->kp.kind = (int)hd[11];
+    h->spatial = (int)hd[12];
+    h->mbox.bits = (int)hd[13];
+    for (int a = 0; a < MAXD; ++a) { h->mbox.lo[a] = hd[14 + a]; h->mbox.scale[a] = hd[18 + a]; }
+    h->perm.clear();
+    h->perm_known = !h->spatial;
     int rc = set_params(h, hd[3], &hd[6], hd[4], hd[5]);
     if (rc) return rc;
     if ((rc = launch_scale(h))) return rc;

@@ -77,7 +77,8 @@ __device__ __forceinline__ void tma_load_3d_u8(void* dst, const CUtensorMap* m, 
 template <int S, int BITS>
 __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ src, long long ld, long long rows, int ncols,
                                                          int lower, int8_t* __restrict__ planes, long long plane_stride,
-                                                         double* __restrict__ scale, unsigned long long* __restrict__ l1max = nullptr) {
+                                                         double* __restrict__ scale, unsigned long long* __restrict__ l1max = nullptr,
+                                                         unsigned* __restrict__ flags = nullptr, int flags_stride = 0) {
     const long long row = blockIdx.x;
     const int kmax = lower ? (int)min((long long)ncols, row + 1) : ncols;
     const double* rp = src + row * ld;
@@ -110,6 +111,18 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
                 l1 += __vsadu4(__vabsss4(packed[t]), 0u);          // sum of |digit| over the four bytes (|-128| saturates to 127: +1 each below)
                 l1 += __popc(__vcmpeq4(packed[t], 0x80808080u) & 0x01010101u);
             }
+            if (flags != nullptr) {
+                // non-zero planes of the (64-row, 64-column) block this thread's four digits belong to (see DigitScales::flags)
+                unsigned m = 0;
+#pragma unroll
+                for (int t = 0; t < S; ++t) m |= (packed[t] != 0u ? 1u : 0u) << t;
+                m |= __shfl_xor_sync(0xffffffffu, m, 1);
+                m |= __shfl_xor_sync(0xffffffffu, m, 2);
+                m |= __shfl_xor_sync(0xffffffffu, m, 4);
+                m |= __shfl_xor_sync(0xffffffffu, m, 8);
+                const int chunk = k >> 6;
+                if ((threadIdx.x & 15) == 0 && m != 0u) atomicOr(flags + (row >> 6) * flags_stride + (chunk >> 2), m << ((chunk & 3) * 8));
+            }
         }
         if (l1max != nullptr) {
             // data-dependent exactness bound of the int32 accumulators: |sum_k a_k b_k| <= 128 * sum_k |b_k|, summed over this row's planes
@@ -141,6 +154,90 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
 // allocated once, the TMA producer streams straight into the next tile while the epilogue drains the accumulators
 // (the MMA thread only waits for that drain, ~1 us per ~20 us tile).
 // ------------------------------------------------------------------------------------------------------------
+// TMA views of one operand's digit planes with 1 .. 7 planes per box: m[n-1] loads n consecutive planes starting at the
+// plane coordinate, so a chunk whose leading planes are zero moves (and pays L2 bandwidth for) only the planes it needs.
+struct PlaneMaps {
+    CUtensorMap m[7];
+};
+
+// Block masks of one tile row (spatial mode): leading all-zero planes of A and B for chunk c.  The producer and the MMA thread
+// walk the same masks, so both skip the same chunks and planes.  Words are fetched four chunks ahead of their use.
+struct ZeroPlaneReader {
+    const unsigned *fa, *fb;
+    unsigned wa, wb, wa_next, wb_next;
+    int ti;
+    __device__ __forceinline__ void init(const unsigned* flagsA, const unsigned* flagsB, int stride, int rt, int ti_) {
+        fa = flagsA ? flagsA + (long long)rt * stride : nullptr;
+        fb = flagsA ? flagsB + (long long)ti_ * stride : nullptr;
+        ti = ti_;
+        wa = wb = wa_next = wb_next = 0u;
+        if (fa && ti >= 1) {
+            wa = __ldg(fa); wb = __ldg(fb);
+            if (ti >= 4) { wa_next = __ldg(fa + 1); wb_next = __ldg(fb + 1); }
+        }
+    }
+    template <int S>
+    __device__ __forceinline__ void get(int c, int& za, int& zb) {
+        za = 0; zb = 0;
+        if (!fa || c == 0) return;                          // chunk 0 is always dense: it zero-initialises the accumulators
+        if ((c & 3) == 0) {
+            wa = wa_next; wb = wb_next;
+            if (c + 4 <= ti) { wa_next = __ldg(fa + (c >> 2) + 1); wb_next = __ldg(fb + (c >> 2) + 1); }
+        }
+        const unsigned ma = (wa >> ((c & 3) * 8)) & 0xffu, mb = (wb >> ((c & 3) * 8)) & 0xffu;
+        za = ma ? (__ffs(ma) - 1) : S;
+        zb = mb ? (__ffs(mb) - 1) : S;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// MMA issue for one 64-byte k-chunk with the first ZA planes of A and the first ZB planes of B known to be all zero
+// (ZA = ZB = 0: the dense case).  Everything but the two base descriptors is a compile-time constant, so a wide MMA costs
+// the issuing thread a handful of instructions; a run-time (za, zb) version of this loop (descriptor arithmetic, loop
+// control and predicates recomputed per MMA by ONE thread) was issue-bound: 7.3 instead of 5.5 ms per launch.
+// For a fixed A plane a the partner planes b = ZB .. S-1-a accumulate into the diagonals a+b, i.e. into CONTIGUOUS TMEM
+// columns [64(a+ZB), 64 S), and those B planes are contiguous rows in shared memory: the pair products are issued as ONE
+// wide MMA (N = 64 (S-a-ZB); above 256 as two EQUAL halves, e.g. 320 = 160 + 160 rather than 256 + 64 -- a 64-wide MMA
+// re-reads the 4 KB A tile for 32 cycles of work and is operand-port bound).  With per-pair N = 64 MMAs the operand fetch
+// (6 KB per 32-cycle MMA = 192 B/clk) exceeded the 128 B/clk shared-memory port and capped the kernel at 2/3 of the
+// tensor rate (ncu: sm__throughput 88 %, tensor pipe 42 %).
+// ------------------------------------------------------------------------------------------------------------
+template <int S, int ZA, int ZB>
+__device__ __forceinline__ void oz_issue_chunk(uint64_t adesc0, uint64_t bdesc0, uint32_t tmem_base, uint32_t idesc_base, uint32_t first) {
+#pragma unroll
+    for (int a = ZA; a < S; ++a) {
+        const int nbp = S - a - ZB;                                     // B planes ZB .. S-1-a
+        if (nbp <= 0) continue;
+        const int ncols = ON * nbp;
+        const int nhalf = (ncols > 256) ? 2 : 1;
+        const int nw = ncols / nhalf;                                   // multiple of 32
+        const uint64_t ad = adesc0 + (uint64_t)(((a - ZA) * OM * OKB) >> 4);      // the stage holds A planes ZA.. and B planes ZB.. from slot 0
+#pragma unroll
+        for (int hf = 0; hf < nhalf; ++hf) {
+            const uint64_t bd = bdesc0 + (uint64_t)(((hf * nw) * OKB) >> 4);
+            const uint32_t dcol = tmem_base + (uint32_t)((a + ZB) * ON + hf * nw);
+            const uint32_t idn = idesc_base | ((uint32_t)(nw >> 3) << 17);
+#pragma unroll
+            for (int kk = 0; kk < OKB / 32; ++kk)
+                umma_i8(dcol, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idn, (a == 0 && kk == 0) ? (first ? 0u : 1u) : 1u);
+        }
+    }
+}
+template <int S, int ZA, int ZB>
+__device__ __forceinline__ void oz_dispatch_zb(int zb, uint64_t adesc0, uint64_t bdesc0, uint32_t tmem_base, uint32_t idesc_base) {
+    if constexpr (ZA + ZB < S) {
+        if (zb == ZB) oz_issue_chunk<S, ZA, ZB>(adesc0, bdesc0, tmem_base, idesc_base, 0u);
+        else oz_dispatch_zb<S, ZA, ZB + 1>(zb, adesc0, bdesc0, tmem_base, idesc_base);
+    }
+}
+template <int S, int ZA>
+__device__ __forceinline__ void oz_dispatch_za(int za, int zb, uint64_t adesc0, uint64_t bdesc0, uint32_t tmem_base, uint32_t idesc_base) {
+    if constexpr (ZA < S) {
+        if (za == ZA) oz_dispatch_zb<S, ZA, 0>(zb, adesc0, bdesc0, tmem_base, idesc_base);
+        else oz_dispatch_za<S, ZA + 1>(za, zb, adesc0, bdesc0, tmem_base, idesc_base);
+    }
+}
+
 __device__ __forceinline__ void oz_tile_decode(long long idx, int T64, int rowtiles, int& rt, int& ti) {
     constexpr int GR = 12, GI = 24;     // groups of 12 row tiles x 24 factor-row tiles (same span as the DMMA kernel's 12 x 12)
     const long long per_tib = (long long)rowtiles * GI;
@@ -154,11 +251,13 @@ __device__ __forceinline__ void oz_tile_decode(long long idx, int T64, int rowti
 }
 
 template <int S>
-__global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                const __grid_constant__ CUtensorMap mapB,
+__global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_constant__ PlaneMaps mapsA,
+                                                                const __grid_constant__ PlaneMaps mapsB,
                                                                 const double* __restrict__ scaleA, const double* __restrict__ scaleB,
                                                                 int T64, int rowtiles, long long rows_total,
-                                                                double* __restrict__ part, int* __restrict__ tile_counter, int digit_bits) {
+                                                                double* __restrict__ part, int* __restrict__ tile_counter, int digit_bits,
+                                                                const unsigned* __restrict__ flagsA, const unsigned* __restrict__ flagsB,
+                                                                int flags_stride) {
     using C = Cfg<S>;
     constexpr int NST = C::NST;
     extern __shared__ uint8_t smem_raw[];
@@ -202,14 +301,21 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                 if (t < 0) break;
                 int rt, ti;
                 oz_tile_decode(t, T64, rowtiles, rt, ti);
-                for (int c = 0; c <= ti; ++c, ++gs) {
+                ZeroPlaneReader zr;
+                zr.init(flagsA, flagsB, flags_stride, rt, ti);
+                for (int c = 0; c <= ti; ++c) {
+                    int za, zb;
+                    zr.template get<S>(c, za, zb);
+                    const int n = S - za - zb;                  // planes za .. za+n-1 of A meet planes zb .. zb+n-1 of B
+                    if (n <= 0) continue;                       // nothing but zeros in this chunk: no stage, no load
                     const int st = gs % NST;
                     if (gs >= NST) mbar_wait(&empty[st], ((gs / NST) - 1) & 1);
                     uint8_t* sA = smem + st * C::STAGE_BYTES;
                     uint8_t* sB = sA + S * OM * OKB;
-                    mbar_expect_tx(&full[st], C::STAGE_BYTES);
-                    tma_load_3d_u8(sA, &mapA, c * OKB, rt * OM, 0, &full[st]);
-                    tma_load_3d_u8(sB, &mapB, c * OKB, ti * ON, 0, &full[st]);
+                    mbar_expect_tx(&full[st], n * (OM + ON) * OKB);
+                    tma_load_3d_u8(sA, &mapsA.m[n - 1], c * OKB, rt * OM, za, &full[st]);
+                    tma_load_3d_u8(sB, &mapsB.m[n - 1], c * OKB, ti * ON, zb, &full[st]);
+                    ++gs;
                 }
             }
         }
@@ -229,37 +335,26 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                     mbar_wait(&acc_empty, (lt - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 }
-                for (int c = 0; c <= ti; ++c, ++gs) {
+                // spatial mode: per (row tile, chunk) / (factor-row tile, chunk) masks of the non-zero digit planes.  Leading zero
+                // planes (small values: far-away training points, far-off-diagonal entries of L^-1) are neither loaded nor
+                // multiplied -- exact, the skipped products are sums of zeros.
+                ZeroPlaneReader zr;
+                zr.init(flagsA, flagsB, flags_stride, rt, ti);
+                for (int c = 0; c <= ti; ++c) {
+                    int za, zb;
+                    zr.template get<S>(c, za, zb);
+                    if (S - za - zb <= 0) continue;
                     const int st = gs % NST;
                     mbar_wait(&full[st], (gs / NST) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     const uint8_t* sA = smem + st * C::STAGE_BYTES;
                     const uint8_t* sB = sA + S * OM * OKB;
-                    // For a fixed A plane a the partner planes b = 0 .. S-1-a accumulate into the diagonals a+b = a .. S-1,
-                    // i.e. into CONTIGUOUS TMEM columns [64a, 64S); and those B planes are contiguous rows in shared memory.
-                    // So the S-a pair products are issued as ONE wide MMA (N = 64(S-a), split at 256): the A tile is read
-                    // from shared memory once per wide MMA instead of once per pair.  With per-pair N = 64 MMAs the operand
-                    // fetch (6 KB per 32-cycle MMA = 192 B/clk) exceeded the 128 B/clk shared-memory port and capped the
-                    // kernel at 2/3 of the tensor rate (ncu: sm__throughput 88 %, tensor pipe 42 %).
-#pragma unroll
-                    for (int a = 0; a < S; ++a) {
-                        const uint64_t ad = smem_desc_sw64(sA + a * OM * OKB);
-                        // N = 64 (S-a) columns; above 256 the product is issued as two EQUAL halves (e.g. 320 = 160 + 160, not
-                        // 256 + 64: a 64-wide MMA re-reads the 4 KB A tile for 32 cycles of work and is operand-port bound)
-                        const int ncols = ON * (S - a);
-                        const int nhalf = (ncols > 256) ? 2 : 1;
-                        const int nw = ncols / nhalf;                                   // multiple of 32
-#pragma unroll
-                        for (int hf = 0; hf < nhalf; ++hf) {
-                            const uint64_t bd = smem_desc_sw64(sB + hf * nw * OKB);    // nw rows further down the stacked B planes
-                            const uint32_t dcol = tmem_base + (uint32_t)(a * ON + hf * nw);
-                            const uint32_t idn = idesc_base | ((uint32_t)(nw >> 3) << 17);
-#pragma unroll
-                            for (int kk = 0; kk < OKB / 32; ++kk)
-                                umma_i8(dcol, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idn, (a == 0 && c == 0 && kk == 0) ? 0u : 1u);
-                        }
-                    }
+                    const uint64_t adesc0 = smem_desc_sw64(sA), bdesc0 = smem_desc_sw64(sB);
+                    if (c == 0) oz_issue_chunk<S, 0, 0>(adesc0, bdesc0, tmem_base, idesc_base, 1u);       // zero-initialises every column
+                    else if ((za | zb) == 0) oz_issue_chunk<S, 0, 0>(adesc0, bdesc0, tmem_base, idesc_base, 0u);
+                    else oz_dispatch_za<S, 0>(za, zb, adesc0, bdesc0, tmem_base, idesc_base);
                     umma_commit(&empty[st]);        // the stage is free once these MMAs have read it
+                    ++gs;
                 }
                 umma_commit(&acc_full);
             }

@@ -70,11 +70,61 @@ __device__ __forceinline__ double exp_neg(double x, const double* tab) {
 struct DigitScales {
     double down[1 + 2 * MAXD];     // 2^-e per row type: 0 = k*, 1+a = dk*/dx_a, 1+D+a = k* + dk*/dx_a
     double scale[1 + 2 * MAXD];    // 2^e
+    // spatial mode (gptb_set_spatial): queries are processed in Morton order (qperm[sorted position] = position in the batch) and
+    // the generator records, per (128-query row tile, 64-point chunk), which digit planes hold a non-zero digit (one byte per
+    // block, bit t = plane t; rows of `flags` are flags_stride 32-bit words long) so the product kernel can skip zero planes.
+    const unsigned* qperm;
+    unsigned* flags;
+    int flags_stride;
 };
+constexpr int FLAG_WORDS = 128;    // 512 chunks of 64 training points = N <= 32768
+
+// Morton code of the (affine-transformed) query positions relative to the bounding box of the training inputs; keys are sorted
+// with a radix sort, vals carries the position in the batch.
+struct MortonBox {
+    double lo[MAXD], scale[MAXD];
+    int bits;
+};
+template <int D>
+__global__ void __launch_bounds__(256) morton_keys_kernel(const double* __restrict__ xq, int B, Affine af, MortonBox mb, unsigned* __restrict__ keys,
+                                                          unsigned* __restrict__ vals) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= B) return;
+    double xin[D], xe[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) xin[a] = xq[(long long)q * D + a];
+    if (af.on) {
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int b = 0; b < D; ++b) sacc += af.R[a][b] * (xin[b] - af.Sbar[b]);
+            xe[a] = af.s * sacc + af.Tbar[a];
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < D; ++a) xe[a] = xin[a];
+    }
+    const double top = (double)((1u << mb.bits) - 1u);
+    unsigned cell[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        double t = (xe[a] - mb.lo[a]) * mb.scale[a];
+        t = (t > 0.0) ? ((t < top) ? t : top) : 0.0;              // clamps NaN to 0 as well
+        cell[a] = (unsigned)t;
+    }
+    unsigned code = 0;
+    for (int b = 0; b < mb.bits; ++b)
+#pragma unroll
+        for (int a = 0; a < D; ++a) code |= ((cell[a] >> b) & 1u) << (b * D + a);
+    keys[q] = code;
+    vals[q] = (unsigned)q;
+}
+
 
 template <int S, int BITS>
 __device__ __forceinline__ void emit_digits(const double (&val)[4], double down, int8_t* __restrict__ planes, long long plane_stride,
-                                            long long off) {
+                                            long long off, unsigned* smask_row = nullptr, int chunk = 0) {
     unsigned packed[S];
     if constexpr (BITS == 8) {
         digits8_pack4<S>(val, down, packed);          // here `down` already carries the 256^S factor (DigitScales)
@@ -94,6 +144,17 @@ __device__ __forceinline__ void emit_digits(const double (&val)[4], double down,
     }
 #pragma unroll
     for (int t = 0; t < S; ++t) *reinterpret_cast<unsigned*>(planes + (long long)t * plane_stride + off) = packed[t];
+    if (smask_row != nullptr) {
+        // non-zero planes of this lane's four digits, OR-ed over the 16 lanes that share a 64-point chunk, into the CTA's mask
+        unsigned m = 0;
+#pragma unroll
+        for (int t = 0; t < S; ++t) m |= (packed[t] != 0u ? 1u : 0u) << t;
+        m |= __shfl_xor_sync(0xffffffffu, m, 1);
+        m |= __shfl_xor_sync(0xffffffffu, m, 2);
+        m |= __shfl_xor_sync(0xffffffffu, m, 4);
+        m |= __shfl_xor_sync(0xffffffffu, m, 8);
+        if ((threadIdx.x & 15) == 0 && m != 0u) atomicOr(smask_row + (chunk >> 2), m << ((chunk & 3) * 8));
+    }
 }
 
 template <int D, int P, int MODE, int S, int BITS = 7>
@@ -105,16 +166,21 @@ __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ x
                                                     DigitScales ds) {
     constexpr int NACC = P + P * D;
     __shared__ double etab[16];
+    __shared__ unsigned smask[(MODE == 2 && BITS == 8) ? (1 + 2 * D) : 1][(MODE == 2 && BITS == 8) ? FLAG_WORDS : 1];
+    const bool use_flags = (MODE == 2 && BITS == 8) && ds.flags != nullptr;
     if (threadIdx.x < 16) etab[threadIdx.x] = c_exp2_16[threadIdx.x];
+    if (use_flags)
+        for (int e = threadIdx.x; e < (1 + 2 * D) * FLAG_WORDS; e += 256) (&smask[0][0])[e] = 0u;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x * QPB + warp;             // one query per warp; lanes run over training points (4 each)
     const bool valid = q < B;
+    const long long qsrc = (MODE == 2 && ds.qperm != nullptr && valid) ? (long long)ds.qperm[q] : (long long)q;   // spatial mode: sorted order
     double xs[D];
     {
         double xin[D], xe[D];
 #pragma unroll
-        for (int a = 0; a < D; ++a) xin[a] = valid ? xq[(long long)q * D + a] : 0.0;
+        for (int a = 0; a < D; ++a) xin[a] = valid ? xq[qsrc * D + a] : 0.0;
         if (af.on) {
 #pragma unroll
             for (int a = 0; a < D; ++a) {
@@ -219,13 +285,18 @@ __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ x
             }
         } else if (MODE == 2) {
             const long long off = (long long)q * Npad + n0;
-            if (st_k) emit_digits<S, BITS>(kv, ds.down[0], planes, plane_stride, off);
+            const int chunk = n0 >> 6;
+            constexpr bool FL = (BITS == 8);
+            if (st_k) emit_digits<S, BITS>(kv, ds.down[0], planes, plane_stride, off, (FL && use_flags) ? smask[0] : nullptr, chunk);
 #pragma unroll
             for (int a = 0; a < D; ++a) {
-                if (st_g) emit_digits<S, BITS>(gv[a], ds.down[1 + a], planes, plane_stride, (long long)(1 + a) * Bpad * Npad + off);
+                if (st_g)
+                    emit_digits<S, BITS>(gv[a], ds.down[1 + a], planes, plane_stride, (long long)(1 + a) * Bpad * Npad + off,
+                                         (FL && use_flags) ? smask[FL ? 1 + a : 0] : nullptr, chunk);
                 if (st_kg) {
                     const double kg[4] = {kv[0] + gv[a][0], kv[1] + gv[a][1], kv[2] + gv[a][2], kv[3] + gv[a][3]};
-                    emit_digits<S, BITS>(kg, ds.down[1 + D + a], planes, plane_stride, (long long)(1 + D + a) * Bpad * Npad + off);
+                    emit_digits<S, BITS>(kg, ds.down[1 + D + a], planes, plane_stride, (long long)(1 + D + a) * Bpad * Npad + off,
+                                         (FL && use_flags) ? smask[FL ? 1 + D + a : 0] : nullptr, chunk);
                 }
             }
         }
@@ -236,6 +307,19 @@ __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ x
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
         acc[v] = x;
+    }
+    if (use_flags) {
+        // flush the CTA's block masks: its 8 queries sit in one 128-query row tile per row type
+        __syncthreads();
+        const int words = (Npad / 64 + 3) / 4;
+        for (int e = threadIdx.x; e < (1 + 2 * D) * words; e += 256) {
+            const int r = e / words, w = e % words;
+            const unsigned m = smask[r][w];
+            if (m != 0u) {
+                const long long rowtile = ((long long)r * Bpad + (long long)blockIdx.x * QPB) / 128;
+                atomicOr(ds.flags + rowtile * ds.flags_stride + w, m);
+            }
+        }
     }
     if (lane == 0) {
         double* dst = macc + ((long long)blockIdx.y * Bpad + q) * NACC;
@@ -392,11 +476,12 @@ template <int D, int P>
 __global__ void __launch_bounds__(128) finalize_kernel(const double* __restrict__ macc, int nsplit, const double* __restrict__ part,
                                                        int T, int B, int Bpad, long long rows_total, const double* __restrict__ xr,
                                                        const double* __restrict__ vel, KParams kp, Affine af, unsigned qflags,
-                                                       QueryOut out, long long q_off, long long Mtot) {
+                                                       QueryOut out, long long q_off, long long Mtot, const unsigned* __restrict__ qperm) {
     constexpr int NACC = P + P * D;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= B) return;
-    const long long gq = q_off + q;
+    const long long qsrc = qperm ? (long long)qperm[q] : (long long)q;    // spatial mode: row q of the batch is query qsrc
+    const long long gq = q_off + qsrc;
     double m[NACC];
 #pragma unroll
     for (int v = 0; v < NACC; ++v) m[v] = 0.0;
@@ -470,7 +555,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const double* __restrict_
             if (qflags & 0x040u) {
                 double v[D], rv[D];
 #pragma unroll
-                for (int a = 0; a < D; ++a) v[a] = vel[(long long)q * D + a];
+                for (int a = 0; a < D; ++a) v[a] = vel[qsrc * D + a];
 #pragma unroll
                 for (int i = 0; i < D; ++i) {
                     double s = 0.0, s2 = 0.0;

@@ -37,7 +37,23 @@ class _Regressor:
 
     @property
     def L_(self):
-        return self._o._engine.export_L()
+        o = self._o
+        if o._engine.spatial:
+            # the handle holds the factor of the Morton-ordered system; sklearn's L_ is the factor in the caller's order:
+            # factorise once more on a scratch handle in natural order (attribute access only, not on any hot path)
+            scratch = _lib.Engine(o._engine.device)
+            try:
+                scratch.set_kernel_kind(kernel_kind(self.kernel_))
+                scratch.set_train(o.X, o.Y)
+                c, ell, s2 = read_params(self.kernel_, scratch.d)
+                info, _ = scratch.factorize(c, ell, s2, self.alpha, want_lml=False)
+                if info > 0:
+                    raise np.linalg.LinAlgError("kernel matrix is not positive definite")
+                return scratch.export_L()
+            finally:
+                scratch.close()
+        o._ensure_fitted_factor()
+        return o._engine.export_L()
 
     @property
     def alpha_(self):
@@ -73,7 +89,7 @@ class _Regressor:
 
 class GaussianProcess:
     def __init__(self, kernel, alpha=1e-10, optimizer='fmin_l_bfgs_b', n_restarts_optimizer=5, n_targets=None, device=None,
-                 variance_mode=None):
+                 variance_mode=None, spatial=None):
         check_supported(kernel)
         if optimizer is None:
             n_restarts_optimizer = 0                     # gaussian_process.py:18-21 (sklearn default)
@@ -86,6 +102,8 @@ class GaussianProcess:
         # the environment variable GPTB_VARIANCE_MODE sets the default for objects that do not say
         import os as _os
         self._variance_mode = variance_mode or _os.environ.get("GPTB_VARIANCE_MODE", "fp64")
+        # spatial mode (include/gptb200.h: Morton-ordered training points, sorted query batches, zero-plane skipping); GPTB_SPATIAL=1
+        self._spatial = bool(int(_os.environ.get("GPTB_SPATIAL", "0"))) if spatial is None else bool(spatial)
         self._engine_obj = None
         self._factor_theta = None
         self._K_inv = None
@@ -102,6 +120,8 @@ class GaussianProcess:
             vm = str(self._variance_mode).lower()
             if vm != "fp64":
                 self._engine_obj.set_variance_mode(*_lib.parse_variance_mode(vm))
+            if self._spatial:
+                self._engine_obj.set_spatial(True)
         return self._engine_obj
 
     # -- fit -------------------------------------------------------------------------------------------------------

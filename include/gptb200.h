@@ -81,6 +81,17 @@ int gptb_lml(gptb_handle* h, double c, const double* ell, double s2, double jitt
  * bound (128 * largest row sum of |digit| of the inverse factor < 2^31) decides, and the call fails if that does not hold either. */
 int gptb_set_variance_mode(gptb_handle* h, int mode, int slices);
 
+/* ---- spatial mode (call before gptb_set_train; off by default).  The training points are kept in Morton (Z-curve) order
+ * inside the handle, every query batch of the INT8-sliced path with 8-bit planes is processed in Morton order too (radix sort
+ * of the batch by key, results scattered back to the caller's order), and the generator / the slicer record per
+ * (128-query tile | 64-row tile of L^-1, 64-point chunk) which digit planes hold a non-zero digit.  The product kernel skips
+ * leading all-zero planes: for a compact kernel most (tile, chunk) pairs are far apart, k(x*, X) and the entries of L^-1 there
+ * are tiny and their top digit planes vanish.  Exact -- the skipped products are sums of zeros; only the summation ORDER of
+ * the training points changes with respect to the natural order (1e-13-level differences).  gptb_export_alpha/_Kinv return
+ * the caller's order; gptb_export_L is refused (the factor belongs to the permuted system).
+ * on = 2 keeps the ordering and the sorted batches but issues every plane product (bit-identical results: A/B of the skipping). */
+int gptb_set_spatial(gptb_handle* h, int on);
+
 /* ---- explicit inverse factor for the variance queries (built lazily by gptb_query when needed). */
 int gptb_prepare_variance(gptb_handle* h);
 

@@ -461,3 +461,62 @@ def test_refit_invalidates_cached_inverse_factor_and_digit_planes():
         m, sd = ora.predict(xq, return_std=True)
         assert rel(o["mean"], m) < TOL_MEAN
         assert np.max(np.abs(o["std"] - sd)) / np.sqrt(0.2 + 1e-3) < TOL_STD
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# spatial mode: Morton-ordered training points, sorted query batches, zero-plane skipping (include/gptb200.h gptb_set_spatial)
+# ---------------------------------------------------------------------------------------------------------------
+def test_spatial_mode_is_exact_and_order_free():
+    """(a) skipping all-zero digit planes changes no bit (spatial 1 vs 2); (b) against the natural order only the summation order
+    differs; (c) alpha / K_inv come back in the caller's order; (d) ragged batches, velocity inputs and the Jacobian-variance rows
+    follow the sorted order correctly."""
+    from gaussian_process_transportation_b200 import _lib as L
+    from oracle.gp_oracle import synthetic_pairs
+    S, T = synthetic_pairs(1500, 3, seed=8)
+    rng = np.random.default_rng(12)
+    xq = np.vstack([-0.1 + 1.2 * rng.random((3000, 3)), S[:500] + 1e-4])       # 3500 queries: ragged last tile
+    vel = rng.normal(size=xq.shape)
+    fl = L.MEAN | L.STD | L.JAC | L.JACVAR | L.VELOCITY
+    outs = {}
+    for mode in (0, 1, 2):
+        eng = L.Engine(0)
+        eng.set_variance_mode("int8w5")
+        eng.set_spatial(mode)
+        eng.set_train(S, T - S)
+        assert eng.factorize(0.1, [0.07] * 3, 1e-4, 1e-10)[0] == 0
+        outs[mode] = (eng.query(xq, fl, vel), eng.export_alpha(), eng.export_Kinv())
+        if mode:
+            with pytest.raises(L.GptbError):
+                eng.export_L()
+        eng.close()
+    for k in outs[1][0]:
+        assert np.array_equal(outs[1][0][k], outs[2][0][k]), k                   # (a)
+    sc = np.sqrt(0.1 + 1e-4)
+    o0, o1 = outs[0][0], outs[1][0]
+    assert rel(o1["mean"], o0["mean"]) < 1e-11 and rel(o1["jac"], o0["jac"]) < 1e-11 and rel(o1["vhat"], o0["vhat"]) < 1e-11   # (b)
+    assert np.max(np.abs(o1["std"] - o0["std"])) / sc < 2e-8 and rel(o1["jacvar"], o0["jacvar"]) < 1e-7 and rel(o1["vvar"], o0["vvar"]) < 1e-7
+    assert rel(outs[1][1], outs[0][1]) < 1e-8 and rel(outs[1][2], outs[0][2]) < 1e-7                                               # (c)
+
+
+@pytest.mark.parametrize("name", ["syn_ard1000.npz", "c2_clouds3d_fixed.npz"])
+def test_spatial_mode_vs_reference_golden(pkg, golden_dir, name):
+    g = load(golden_dir, name)
+    sc = np.sqrt(float(g["c"]) + float(g["s2"]))
+    if "X" in g.files:
+        gp = pkg.GaussianProcess(kernel=kernel_of(g), optimizer=None, variance_mode="int8w5", spatial=True)
+        gp.fit(g["X"], g["Y"])
+        mean, std = gp.predict(g["xq"], return_std=True)
+        J, Jv = gp.derivative(g["xq"], return_var=True)
+        assert rel(mean, g["mean"]) < TOL_MEAN and rel(J, g["J"]) < TOL_MEAN
+        assert np.max(np.abs(std - g["std"])) / sc < TOL_STD and rel(Jv, g["Jvar"]) < TOL_STD
+        assert rel(gp.gp.alpha_, g["alpha_"]) < 1e-8 and rel(np.diag(gp.gp.L_), g["Ldiag"]) < 1e-12
+        assert rel(np.diag(gp.K_inv), g["K_inv_diag"]) < 1e-8
+    else:
+        t = pkg.GaussianProcessTransportation(kernel_transport=kernel_of(g))
+        t.method = pkg.PolicyTransportation(pkg.GaussianProcess(kernel=kernel_of(g), optimizer=None, variance_mode="int8w5", spatial=True))
+        t.source_distribution, t.target_distribution = g["S"], g["T"]
+        t.training_traj, t.training_delta = g["traj_in"], g["delta_in"]
+        t.fit_transportation()
+        t.apply_transportation()
+        assert rel(t.training_traj, g["traj_out"]) < TOL_MEAN and rel(t.training_delta, g["delta_out"]) < TOL_MEAN
+        assert np.max(np.abs(t.std - g["std"])) / sc < TOL_STD and rel(t.var_vel_transported, g["var_vel"]) < 1e-6
