@@ -464,6 +464,19 @@ def main():
                         "algorithmic_flops_per_query": Npad * (Npad + 128.0), "share_of_step": trmm_ms / ms_total,
                         "generator_share_of_step": gen_ms / ms_total}
             other_out = None
+        # accuracy of the timed variance mode against the exact FP64 DMMA path of the same engine, on 4096 queries of which half sit
+        # next to training inputs (where the variance nearly cancels): runs at every workload size, the CPU oracle only up to N = 16384
+        parity64 = None
+        if int8:
+            rngp = np.random.default_rng(7)
+            xp = np.vstack([-0.1 + 1.2 * rngp.random((2048, 3)), S[rngp.choice(N, 2048, replace=False)] + 1e-3 * rngp.standard_normal((2048, 3))])
+            o8 = eng.query(xp, L.MEAN | L.STD | L.JAC | L.AFFINE_IN)
+            eng.set_variance_mode(0)
+            o64 = eng.query(xp, L.MEAN | L.STD | L.JAC | L.AFFINE_IN)
+            eng.set_variance_mode(args.variance)
+            parity64 = {"std_abs_over_sqrt_prior": float(np.max(np.abs(o8["std"] - o64["std"])) / np.sqrt(KERNEL["c"] + KERNEL["s2"])),
+                        "mean_identical": bool(np.array_equal(o8["mean"], o64["mean"])), "jac_identical": bool(np.array_equal(o8["jac"], o64["jac"])),
+                        "tolerance_std": 1e-7, "queries": 4096, "near_training_points": 2048}
         cpu = None
         if not args.no_cpu_baseline:
             nq = {4096: 4096, 16384: 1024}.get(N, 8192)
@@ -491,7 +504,8 @@ def main():
                 "fit_ms": fit_ms, "prepare_variance_ms": prep_ms, "bcast_ms": bcast_ms,
                 "e2e": {"value": e2e_value, "unit": "query-points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / Ke, "steps": Ke},
-                "gpu_launches": int(launches), "roofline": roofline, "fp64_dmma_variance": other_out, "cpu_baseline": cpu,
+                "gpu_launches": int(launches), "roofline": roofline, "fp64_dmma_variance": other_out, "parity_vs_fp64_path": parity64,
+                "cpu_baseline": cpu,
                 "clocks": dict(sampler.summary(windows), scope="samples inside the two timed regions (device-resident and e2e), 100 ms period",
                                whole_run=sampler.summary()) if sampler else None}
         print(json.dumps(line))

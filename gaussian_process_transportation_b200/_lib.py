@@ -57,12 +57,15 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("GPTB_LIB_PATH", LIB_PATH)       # developer override: A/B of two builds of the same library
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()). "
+            f"{path} is missing: build it with `make` (or __graft_entry__.build()). "
             "gaussian_process_transportation_b200 has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
+        if not hasattr(lib, name) and path != LIB_PATH:
+            continue                                      # an older build may lack newer entry points
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

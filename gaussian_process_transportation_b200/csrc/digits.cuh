@@ -70,6 +70,12 @@ __device__ __forceinline__ void digits8_pack4(const double (&val)[4], double mul
     }
 }
 
+// 8-bit planes do not need a power-of-two scale: Q = rint(x * mul) is a single correctly-rounded FMA for ANY mul, the digits
+// represent Q exactly, and x = Q / mul up to one more rounding (1e-16, far below the 256^-S truncation).  Using the tightest
+// scale -- the row maximum lands exactly on the 0.498 head-room limit -- wins 0.5 bit on average per operand over the next
+// power of two (std error 1.2e-8 -> 5.9e-9 in the N = 2048 Morton-ordered simulation).  Returns the scale (x = y0 * scale).
+__host__ __device__ inline double digit_scale8(double bound) { return (bound > 0.0) ? bound / 0.498 : 1.0; }
+
 // exponent e of the power-of-two row scale: |bound| * 2^-e fits the first digit's range (see above)
 __host__ __device__ inline int digit_scale_exp(double bound, int bits) {
     if (!(bound > 0.0)) return 0;

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -80,6 +81,7 @@ struct gptb_handle {
     // spatial mode (gptb_set_spatial): training points in Morton order, query batches sorted by Morton key, zero digit planes
     // skipped by the INT8-sliced product kernel
     int spatial = 0;
+    int spatial_shuffle = 1;                  // chunk order shuffled (GPTB_SPATIAL_SHUFFLE=0 keeps the plain Z-order: A/B only)
     std::vector<int> perm;                    // perm[i] = caller's index of internal training row i (empty: natural order)
     bool perm_known = true;                   // false on a handle whose state arrived by broadcast (exports need the permutation)
     MortonBox mbox{};
@@ -182,10 +184,14 @@ static int set_kernel_attrs(gptb_handle* h) {
     CU(h, cudaFuncSetAttribute(trtri_level_p2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(kinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(trmm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<4>::SMEM_BYTES));
-    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<5>::SMEM_BYTES));
-    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<6>::SMEM_BYTES));
-    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<7>::SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<4>::SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<4>::SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<5>::SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<5>::SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<6>::SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<6>::SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<7>::SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<7>::SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(trmm_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(cov_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(cov_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -267,6 +273,7 @@ extern "C" int gptb_set_spatial(gptb_handle* h, int on) {
     if ((on != 0) != (h->spatial != 0) && h->have_train)
         GPTB_FAIL(h, -1, "gptb_set_spatial must be called before gptb_set_train (the training order is fixed there)");
     if (on < 0 || on > 2) GPTB_FAIL(h, -1, "gptb_set_spatial: mode must be 0, 1 or 2");
+    if (const char* e = getenv("GPTB_SPATIAL_SHUFFLE")) h->spatial_shuffle = atoi(e) != 0;
     h->spatial = on;          // 2 = Morton order and sorted batches, but every plane product issued (A/B of the skipping itself)
     return 0;
 }
@@ -387,6 +394,30 @@ extern "C" int gptb_set_train(gptb_handle* h, const double* X, const double* Y, 
         h->perm.resize((size_t)N);
         std::iota(h->perm.begin(), h->perm.end(), 0);
         std::stable_sort(h->perm.begin(), h->perm.end(), [&](int i, int j) { return code[(size_t)i] < code[(size_t)j]; });
+        // The skipping works per 64-point chunk, so only the chunks have to be compact -- their ORDER is free.  A fully
+        // Z-ordered factor puts every point right behind its neighbours: the conditional variances L_ii shrink, the row
+        // maxima of L^-1 (= the digit scales) grow exactly on the rows that carry the weight of near-training-point
+        // queries, and the 40-bit products lose a decimal (std error 1.2e-7 at N = 32768).  Shuffling the chunk order
+        // (fixed seed) keeps the compactness and gives back most of the conditioning of a random order.
+        if (h->spatial_shuffle) {
+            const long long nchunk = (N + 63) / 64;
+            std::vector<long long> order((size_t)nchunk);
+            std::iota(order.begin(), order.end(), 0LL);
+            unsigned long long st = 0x9E3779B97F4A7C15ULL;
+            for (long long i = nchunk - 1; i > 0; --i) {          // Fisher-Yates with a splitmix64 stream (deterministic)
+                st += 0x9E3779B97F4A7C15ULL;
+                unsigned long long z = st;
+                z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+                z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+                z ^= z >> 31;
+                std::swap(order[(size_t)i], order[(size_t)(z % (unsigned long long)(i + 1))]);
+            }
+            std::vector<int> shuffled;
+            shuffled.reserve((size_t)N);
+            for (long long cidx : order)
+                for (long long n = cidx * 64; n < std::min<long long>(N, (cidx + 1) * 64); ++n) shuffled.push_back(h->perm[(size_t)n]);
+            h->perm.swap(shuffled);
+        }
     }
     for (long long n = 0; n < N; ++n) {
         const long long src = h->perm.empty() ? n : h->perm[(size_t)n];
@@ -756,9 +787,14 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
             ds.flags_stride = h->flags_stride;
         }
         auto set = [&](int idx, double bound) {
-            const int ex = digit_scale_exp(bound, h->var_bits);
-            ds.down[idx] = std::ldexp(1.0, (h->var_bits == 8 ? 8 * h->var_slices : 0) - ex);   // 8-bit planes: digits8_pack4 wants 2^-e * 256^S
-            ds.scale[idx] = std::ldexp(1.0, ex);
+            if (h->var_bits == 8) {                     // tightest scale; digits8_pack4 wants 256^S / scale
+                ds.scale[idx] = digit_scale8(bound);
+                ds.down[idx] = std::ldexp(1.0, 8 * h->var_slices) / ds.scale[idx];
+            } else {
+                const int ex = digit_scale_exp(bound, h->var_bits);
+                ds.down[idx] = std::ldexp(1.0, -ex);
+                ds.scale[idx] = std::ldexp(1.0, ex);
+            }
         };
         set(0, h->kp.c);                                               // k* <= c
         for (int a = 0; a < D; ++a) {
@@ -807,9 +843,14 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
             int nsm = 148;
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
             cudaMemsetAsync(h->info + 1, 0, sizeof(int), h->stream);      // dynamic tile counter
-            oz::ozaki_trmm_kernel<SV><<<(unsigned)(ntiles < nsm ? ntiles : nsm), oz::OTHREADS, oz::Cfg<SV>::SMEM_BYTES, h->stream>>>(
-                mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits,
-                (spatial && h->spatial == 1) ? sp->flagsA : nullptr, (spatial && h->spatial == 1) ? h->flagsB : nullptr, h->flags_stride);
+            const bool skipping = spatial && h->spatial == 1;
+            const unsigned grid_oz = (unsigned)(ntiles < nsm ? ntiles : nsm);
+            if (skipping)
+                oz::ozaki_trmm_kernel<SV, true><<<grid_oz, oz::OTHREADS, oz::Cfg<SV>::SMEM_BYTES, h->stream>>>(
+                    mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, sp->flagsA, h->flagsB, h->flags_stride);
+            else
+                oz::ozaki_trmm_kernel<SV, false><<<grid_oz, oz::OTHREADS, oz::Cfg<SV>::SMEM_BYTES, h->stream>>>(
+                    mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, nullptr, nullptr, h->flags_stride);
         });
         toc(h, 0);
         LAUNCH_CHECK(h);

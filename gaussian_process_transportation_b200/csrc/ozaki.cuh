@@ -59,6 +59,18 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
         : "memory");
 }
+// One elected lane of a CONVERGED warp (the same lane every time for a full mask).  The issuing warps below stay converged and
+// make their control values warp-uniform with a redux (its result lives in a uniform register), so that shared-memory
+// addresses, descriptors and TMA coordinates are computed on the uniform datapath and UTCIMMA / UTMALDG take them directly.
+// With `if (lane == 0)` around the whole loop the compiler could not prove uniformity and wrapped EVERY tcgen05.mma and TMA
+// issue in an ELECT / R2UR.BROADCAST / BRA waterfall loop (~12 instructions per MMA by one thread).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int warp_uniform(int v) { return (int)__reduce_max_sync(0xffffffffu, v); }
+
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -94,10 +106,11 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
     mx = red[0];
     const int ex = digit_scale_exp(mx, BITS);           // |x| * 2^-ex fits the first digit for the whole row
     const double down = ldexp(1.0, -ex);
-    if (threadIdx.x == 0) scale[row] = ldexp(1.0, ex);
+    const double sc8 = digit_scale8(mx);                // 8-bit planes: tightest scale instead of the next power of two
+    if (threadIdx.x == 0) scale[row] = (BITS == 8) ? sc8 : ldexp(1.0, ex);
     if constexpr (BITS == 8) {
         // four columns per thread, one 32-bit store per plane (ncols is a multiple of 128)
-        const double mul = ldexp(1.0, 8 * S - ex);
+        const double mul = ldexp(1.0, 8 * S) / sc8;
         unsigned long long l1 = 0;
         for (int k = 4 * threadIdx.x; k < ncols; k += 1024) {
             double v[4];
@@ -250,7 +263,13 @@ __device__ __forceinline__ void oz_tile_decode(long long idx, int T64, int rowti
     ti = T64 - 1 - (tib * GI + rem2 % ti_cnt);
 }
 
-template <int S>
+// SKIP = false: every plane product of every chunk (natural order, or spatial mode 2); SKIP = true: block masks consulted.
+// The two variants keep separate producer / MMA loops on purpose.  Same-box A/B (profiles/r01_dense_vs_skip_loops.log): the
+// skipping loops run the DENSE case 20 % slower than the original loops (N = 16384: 102 vs 85 ms per launch) although they
+// issue the same TMA loads and the same MMAs -- and neither the templated issue code, nor the run-time tensor-map index,
+// nor the converged-warp issue (which does remove the ELECT / R2UR waterfall around every UTCIMMA / UTMALDG) accounts for it.
+// Unexplained at the end of round 1; the dense path therefore stays on the loops it was tuned with.
+template <int S, bool SKIP>
 __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_constant__ PlaneMaps mapsA,
                                                                 const __grid_constant__ PlaneMaps mapsB,
                                                                 const double* __restrict__ scaleA, const double* __restrict__ scaleB,
@@ -264,7 +283,7 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full[NST], empty[NST], acc_full, acc_empty, slot_full[2], slot_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ long long tile_slot[2];     // dynamic tile scheduler: the producer claims tiles, the other roles follow
+    __shared__ int tile_slot[2];           // dynamic tile scheduler: the producer claims tiles, the other roles follow
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long ntiles = (long long)rowtiles * T64;
 
@@ -287,46 +306,41 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
     if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(OREG_LIGHT));
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(OREG_EPI));
 
-    if (warp == 0) {
+    if (!SKIP && warp == 0) {
+        // dense variant (no block masks): the single-lane loops of the kernel before the spatial mode, kept verbatim -- see the
+        // note at the template head
         if (lane == 0) {
             int gs = 0;                                          // chunks issued so far (ring position)
             for (int lt = 0;; ++lt) {
                 // claim the next tile in the global L2-blocked order (all SMs stay inside one window of ~#SM tiles, which is
                 // what keeps the operand slabs L2-resident; a static stride let the CTAs drift apart and cost 25 %)
                 if (lt >= 2) mbar_wait(&slot_empty[lt & 1], ((lt >> 1) - 1) & 1);
-                long long t = (long long)atomicAdd(tile_counter, 1);
+                int t = atomicAdd(tile_counter, 1);
                 if (t >= ntiles) t = -1;
                 tile_slot[lt & 1] = t;
                 mbar_arrive(&slot_full[lt & 1]);
                 if (t < 0) break;
                 int rt, ti;
                 oz_tile_decode(t, T64, rowtiles, rt, ti);
-                ZeroPlaneReader zr;
-                zr.init(flagsA, flagsB, flags_stride, rt, ti);
-                for (int c = 0; c <= ti; ++c) {
-                    int za, zb;
-                    zr.template get<S>(c, za, zb);
-                    const int n = S - za - zb;                  // planes za .. za+n-1 of A meet planes zb .. zb+n-1 of B
-                    if (n <= 0) continue;                       // nothing but zeros in this chunk: no stage, no load
+                for (int c = 0; c <= ti; ++c, ++gs) {
                     const int st = gs % NST;
                     if (gs >= NST) mbar_wait(&empty[st], ((gs / NST) - 1) & 1);
                     uint8_t* sA = smem + st * C::STAGE_BYTES;
                     uint8_t* sB = sA + S * OM * OKB;
-                    mbar_expect_tx(&full[st], n * (OM + ON) * OKB);
-                    tma_load_3d_u8(sA, &mapsA.m[n - 1], c * OKB, rt * OM, za, &full[st]);
-                    tma_load_3d_u8(sB, &mapsB.m[n - 1], c * OKB, ti * ON, zb, &full[st]);
-                    ++gs;
+                    mbar_expect_tx(&full[st], C::STAGE_BYTES);
+                    tma_load_3d_u8(sA, &mapsA.m[S - 1], c * OKB, rt * OM, 0, &full[st]);
+                    tma_load_3d_u8(sB, &mapsB.m[S - 1], c * OKB, ti * ON, 0, &full[st]);
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (!SKIP && warp == 1) {
         if (lane == 0) {
             // instruction descriptor: D = S32, A = B = INT8, both K-major, M = 128
             const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OM >> 4) << 24);   // N is or-ed in per MMA
             int gs = 0;
             for (int lt = 0;; ++lt) {
                 mbar_wait(&slot_full[lt & 1], (lt >> 1) & 1);
-                const long long t = tile_slot[lt & 1];
+                const int t = tile_slot[lt & 1];
                 mbar_arrive(&slot_empty[lt & 1]);
                 if (t < 0) break;
                 int rt, ti;
@@ -335,29 +349,132 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                     mbar_wait(&acc_empty, (lt - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 }
-                // spatial mode: per (row tile, chunk) / (factor-row tile, chunk) masks of the non-zero digit planes.  Leading zero
-                // planes (small values: far-away training points, far-off-diagonal entries of L^-1) are neither loaded nor
-                // multiplied -- exact, the skipped products are sums of zeros.
-                ZeroPlaneReader zr;
-                zr.init(flagsA, flagsB, flags_stride, rt, ti);
-                for (int c = 0; c <= ti; ++c) {
-                    int za, zb;
-                    zr.template get<S>(c, za, zb);
-                    if (S - za - zb <= 0) continue;
+                for (int c = 0; c <= ti; ++c, ++gs) {
                     const int st = gs % NST;
                     mbar_wait(&full[st], (gs / NST) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     const uint8_t* sA = smem + st * C::STAGE_BYTES;
                     const uint8_t* sB = sA + S * OM * OKB;
-                    const uint64_t adesc0 = smem_desc_sw64(sA), bdesc0 = smem_desc_sw64(sB);
+                    // For a fixed A plane a the partner planes b = 0 .. S-1-a accumulate into the diagonals a+b = a .. S-1,
+                    // i.e. into CONTIGUOUS TMEM columns [64a, 64S); and those B planes are contiguous rows in shared memory.
+                    // So the S-a pair products are issued as ONE wide MMA (N = 64(S-a), split at 256): the A tile is read
+                    // from shared memory once per wide MMA instead of once per pair.  With per-pair N = 64 MMAs the operand
+                    // fetch (6 KB per 32-cycle MMA = 192 B/clk) exceeded the 128 B/clk shared-memory port and capped the
+                    // kernel at 2/3 of the tensor rate (ncu: sm__throughput 88 %, tensor pipe 42 %).
+#pragma unroll
+                    for (int a = 0; a < S; ++a) {
+                        const uint64_t ad = smem_desc_sw64(sA + a * OM * OKB);
+                        // N = 64 (S-a) columns; above 256 the product is issued as two EQUAL halves (e.g. 320 = 160 + 160, not
+                        // 256 + 64: a 64-wide MMA re-reads the 4 KB A tile for 32 cycles of work and is operand-port bound)
+                        const int ncols = ON * (S - a);
+                        const int nhalf = (ncols > 256) ? 2 : 1;
+                        const int nw = ncols / nhalf;                                   // multiple of 32
+#pragma unroll
+                        for (int hf = 0; hf < nhalf; ++hf) {
+                            const uint64_t bd = smem_desc_sw64(sB + hf * nw * OKB);    // nw rows further down the stacked B planes
+                            const uint32_t dcol = tmem_base + (uint32_t)(a * ON + hf * nw);
+                            const uint32_t idn = idesc_base | ((uint32_t)(nw >> 3) << 17);
+#pragma unroll
+                            for (int kk = 0; kk < OKB / 32; ++kk)
+                                umma_i8(dcol, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idn, (a == 0 && c == 0 && kk == 0) ? 0u : 1u);
+                        }
+                    }
+                    umma_commit(&empty[st]);        // the stage is free once these MMAs have read it
+                }
+                umma_commit(&acc_full);
+            }
+        }
+    } else if (SKIP && warp == 0) {
+        // ---------------- TMA producer: converged warp, one elected lane issues (see elect_one_sync) ----------------
+        int gs = 0;                                          // chunks issued so far (ring position)
+        for (int lt = 0;; ++lt) {
+            // claim the next tile in the global L2-blocked order (all SMs stay inside one window of ~#SM tiles, which is
+            // what keeps the operand slabs L2-resident; a static stride let the CTAs drift apart and cost 25 %)
+            if (lt >= 2) mbar_wait(&slot_empty[lt & 1], ((lt >> 1) - 1) & 1);
+            int t = 0;
+            if (lane == 0) {
+                t = atomicAdd(tile_counter, 1);
+                if (t >= ntiles) t = -1;
+                tile_slot[lt & 1] = t;
+                mbar_arrive(&slot_full[lt & 1]);
+            }
+            t = warp_uniform(lane == 0 ? t : (int)0x80000000);
+            if (t < 0) break;
+            int rt, ti;
+            oz_tile_decode(t, T64, rowtiles, rt, ti);
+            ZeroPlaneReader zr;
+            zr.init(flagsA, flagsB, flags_stride, rt, ti);
+            for (int c = 0; c <= ti; ++c) {
+                int za, zb;
+                zr.template get<S>(c, za, zb);
+                if (flagsA != nullptr) {
+                    const int zz = warp_uniform(za | (zb << 8));
+                    za = zz & 0xff;
+                    zb = zz >> 8;
+                }
+                const int n = S - za - zb;                  // planes za .. za+n-1 of A meet planes zb .. zb+n-1 of B
+                if (n <= 0) continue;                       // nothing but zeros in this chunk: no stage, no load
+                const int st = gs % NST;
+                if (gs >= NST) mbar_wait(&empty[st], ((gs / NST) - 1) & 1);
+                uint8_t* sA = smem + st * C::STAGE_BYTES;
+                uint8_t* sB = sA + S * OM * OKB;
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&full[st], n * (OM + ON) * OKB);
+                    tma_load_3d_u8(sA, &mapsA.m[n - 1], c * OKB, rt * OM, za, &full[st]);
+                    tma_load_3d_u8(sB, &mapsB.m[n - 1], c * OKB, ti * ON, zb, &full[st]);
+                }
+                __syncwarp();
+                ++gs;
+            }
+        }
+    } else if (SKIP && warp == 1) {
+        // ---------------- MMA issue: the whole warp walks the loop converged, one elected lane issues ----------------
+        // instruction descriptor: D = S32, A = B = INT8, both K-major, M = 128
+        const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OM >> 4) << 24);   // N is or-ed in per MMA
+        int gs = 0;
+        for (int lt = 0;; ++lt) {
+            mbar_wait(&slot_full[lt & 1], (lt >> 1) & 1);
+            const int t = warp_uniform((int)tile_slot[lt & 1]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slot_empty[lt & 1]);
+            if (t < 0) break;
+            int rt, ti;
+            oz_tile_decode(t, T64, rowtiles, rt, ti);
+            if (lt > 0) {                                    // accumulators of the previous tile must be drained
+                mbar_wait(&acc_empty, (lt - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            }
+            // spatial mode: per (row tile, chunk) / (factor-row tile, chunk) masks of the non-zero digit planes.  Leading zero
+            // planes (small values: far-away training points, far-off-diagonal entries of L^-1) are neither loaded nor
+            // multiplied -- exact, the skipped products are sums of zeros.
+            ZeroPlaneReader zr;
+            zr.init(flagsA, flagsB, flags_stride, rt, ti);
+            for (int c = 0; c <= ti; ++c) {
+                int za, zb;
+                zr.template get<S>(c, za, zb);
+                if (flagsA != nullptr) {
+                    const int zz = warp_uniform(za | (zb << 8));
+                    za = zz & 0xff;
+                    zb = zz >> 8;
+                }
+                if (S - za - zb <= 0) continue;
+                const int st = gs % NST;
+                mbar_wait(&full[st], (gs / NST) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint8_t* sA = smem + st * C::STAGE_BYTES;
+                const uint8_t* sB = sA + S * OM * OKB;
+                const uint64_t adesc0 = smem_desc_sw64(sA), bdesc0 = smem_desc_sw64(sB);
+                if (elect_one_sync()) {
                     if (c == 0) oz_issue_chunk<S, 0, 0>(adesc0, bdesc0, tmem_base, idesc_base, 1u);       // zero-initialises every column
                     else if ((za | zb) == 0) oz_issue_chunk<S, 0, 0>(adesc0, bdesc0, tmem_base, idesc_base, 0u);
                     else oz_dispatch_za<S, 0>(za, zb, adesc0, bdesc0, tmem_base, idesc_base);
                     umma_commit(&empty[st]);        // the stage is free once these MMAs have read it
-                    ++gs;
                 }
-                umma_commit(&acc_full);
+                __syncwarp();
+                ++gs;
             }
+            if (elect_one_sync()) umma_commit(&acc_full);
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ---------------- epilogue warps 4..7: TMEM lane quarter = warp % 4 ----------------
@@ -368,7 +485,7 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
         for (int d = 0; d < S; ++d) wgt[d] = ldexp(1.0, -digit_bits * (d + 2));
         for (int lt = 0;; ++lt) {
             mbar_wait(&slot_full[lt & 1], (lt >> 1) & 1);
-            const long long t = tile_slot[lt & 1];
+            const int t = tile_slot[lt & 1];
             __syncwarp();
             if (lane == 0) mbar_arrive(&slot_empty[lt & 1]);
             if (t < 0) break;
