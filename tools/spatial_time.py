@@ -1,0 +1,26 @@
+"""Two query_dev calls of the spatial INT8-sliced path (developer tool; the second launch of the product kernel is the one ncu captures)."""
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gaussian_process_transportation_b200 import _lib as L
+from oracle.gp_oracle import synthetic_pairs
+import torch
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+M = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+S, T = synthetic_pairs(N, 3, seed=0)
+eng = L.Engine(0)
+eng.set_variance_mode("int8w5")
+eng.set_spatial(1)
+eng.set_train(S, T - S)
+eng.factorize(0.1, [0.1] * 3, 1e-4, 1e-10)
+xq = -0.1 + 1.2 * np.random.default_rng(0).random((M, 3))
+xd = torch.from_numpy(xq).cuda()
+mean = torch.empty(M, 3, dtype=torch.float64, device="cuda"); std = torch.empty_like(mean)
+jac = torch.empty(M, 3, 3, dtype=torch.float64, device="cuda")
+kw = dict(mean=mean.data_ptr(), std=std.data_ptr(), jac=jac.data_ptr())
+fl = L.MEAN | L.STD | L.JAC
+eng.query_dev(xd.data_ptr(), M, fl, **kw)
+eng.timing(True); eng.timing_reset()
+eng.query_dev(xd.data_ptr(), M, fl, **kw)
+t0, n0 = eng.kernel_time(0); t1, n1 = eng.kernel_time(1)
+print(json.dumps({"N": N, "M": M, "mode": "int8w5 spatial", "products_ms": t0, "launches": n0, "generator_sort_ms": t1}))
