@@ -1,9 +1,5 @@
 set -x
-for w in c3 c4 c5; do
-timeout 400 python bench.py --workload $w > gpurun_out/bench_${w}_spatial.json 2> gpurun_out/bench_${w}_spatial.err; python - <<PY
-import json
-d=json.loads(open("gpurun_out/bench_${w}_spatial.json").read().strip().splitlines()[-1])
-print("$w spatial: value %.4g ms/step %.1f e2e %.4g share %.3f gen %.3f launch_ms %.3f"%(d["value"],d["ms_per_step"],d["e2e"]["value"],d["roofline"]["share_of_step"],d["roofline"]["generator_share_of_step"],d["roofline"]["launch_ms"]), d["clocks"]["sm_mhz"], d["clocks"]["power_w"], d["parity_vs_fp64_path"], d["cpu_baseline"]["parity_vs_gpu"]["std_abs_over_sqrt_prior"] if d["cpu_baseline"] else None)
-PY
-done
-bash tools/ncu_r1c.sh
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+timeout 400 python bench.py > gpurun_out/bench_default_final.json 2> gpurun_out/bench_default_final.err; tail -c 700 gpurun_out/bench_default_final.json
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | head -c 250
