@@ -420,20 +420,25 @@ def main():
             int8_peak, int8_src = measure_int8_peak(torch, dev)
             traffic = None
             try:   # DRAM bytes per launch from the committed ncu capture, only when it is the same launch shape
-                tf = os.path.join(ROOT, "profiles", f"r01_ozaki_traffic_{args.variance}.json")
+                tf = os.path.join(ROOT, "profiles", f"r01_ozaki_traffic_{args.variance}{'_spatial' if args.spatial else ''}.json")
                 tr = json.load(open(tf if os.path.exists(tf) else os.path.join(ROOT, "profiles", "r01_ozaki_traffic.json")))
-                if tr["N"] == N and abs(tr["queries_per_launch"] - q_per_launch) < 1 and tr.get("variance", "int8x6") == args.variance:
+                if tr["N"] == N and abs(tr["queries_per_launch"] - q_per_launch) < 1 and tr.get("variance", "int8x6") == args.variance \
+                        and bool(tr.get("spatial", False)) == bool(args.spatial):
                     traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             except Exception:
                 pass
             bits = 8 if args.variance[4] == "w" else 7
-            roofline = {"bound": "tensor", "kernel": f"ozaki_trmm_kernel<{S_}> (tcgen05.mma kind::i8, TMEM accumulators, {pairs} products of {bits}-bit digit planes)",
+            roofline = {"bound": "tensor", "kernel": f"ozaki_trmm_kernel<{S_}, {'true' if args.spatial else 'false'}> (tcgen05.mma kind::i8, TMEM accumulators, {pairs} products of {bits}-bit digit planes)",
                         "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": achieved / int8_peak, "traffic": traffic,
                         "traffic_unit": "bytes/launch (ncu dram read+write)",
                         "peak_source": int8_src, "peak_sustained": getattr(measure_int8_peak, "sustained", None),
                         "frac_of_sustained": (achieved / measure_int8_peak.sustained) if getattr(measure_int8_peak, "sustained", None) else None,
                         "peak_sustained_source": "the same cuBLASLt int8 GEMM back to back for ~1.5 s under the power cap (this kernel is timed inside a long step)",
                         "algorithmic_ops_per_launch": ops_per_launch, "launch_ms": avg_launch_ms,
+                        "note": ("achieved = algorithmic ops of the scheme (all S(S+1)/2 plane products over the lower triangle) / launch time; "
+                                 "in spatial mode the kernel neither loads nor multiplies digit planes that are zero in a block, so the tensor "
+                                 "pipe is busy for less than this figure suggests (ncu at N=4096: 39.8 % of elapsed cycles, "
+                                 "profiles/r01_ozaki_v6_spatial_ncu_key_metrics.txt)") if args.spatial else None,
                         "fp64_equivalent_tflops": q_per_launch * Npad * (Npad + 64.0) / (avg_launch_ms * 1e-3) * 1e-12,
                         "fp64_dgemm_peak_tflops": dgemm_peak, "share_of_step": trmm_ms / ms_total,
                         "generator_share_of_step": gen_ms / ms_total}
