@@ -513,7 +513,12 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
 #pragma unroll
                 for (int d = 0; d < S; ++d) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fma((double)(int)r[d][j], wgt[d], v[j]);
+                    for (int j = 0; j < 16; ++j) {
+                        // int32 -> double without the conversion pipe (I2F.F64 issues at a quarter of the DFMA rate and there are
+                        // S of them per output): 2^52 + 2^31 + r sits exactly in the mantissa, one DADD removes the offset
+                        const double dr = __hiloint2double(0x43300000, (int)(r[d][j] ^ 0x80000000u)) - 4503601774854144.0;
+                        v[j] = fma(dr, wgt[d], v[j]);
+                    }
                 }
                 if (cb == ON / 16 - 1) {
                     // every accumulator column of this tile has been read: let the MMA thread start the next tile

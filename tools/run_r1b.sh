@@ -1,5 +1,6 @@
 set -x
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-timeout 400 python bench.py > gpurun_out/bench_default_final.json 2> gpurun_out/bench_default_final.err; tail -c 700 gpurun_out/bench_default_final.json
-timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | head -c 250
+timeout 600 python -m pytest tests -m gpu -x -q -k "int8 or spatial or refit or overlap or diffeo_apply" 2>&1 | tail -3
+timeout 120 python tools/spatial_time.py 4096 65536 2>&1 | tail -1
+timeout 120 python tools/spatial_time.py 16384 65536 2>&1 | tail -1
+timeout 120 python tools/ozaki_time.py 4096 262144 2>&1 | tail -1
+timeout 120 python tools/ozaki_time.py 16384 65536 2>&1 | tail -1
