@@ -498,7 +498,7 @@ def test_spatial_mode_is_exact_and_order_free():
     assert rel(outs[1][1], outs[0][1]) < 1e-8 and rel(outs[1][2], outs[0][2]) < 1e-7                                               # (c)
 
 
-@pytest.mark.parametrize("name", ["syn_ard1000.npz", "c2_clouds3d_fixed.npz"])
+@pytest.mark.parametrize("name", ["syn_ard1000.npz", "c2_clouds3d_fixed.npz", "syn_ard2d200.npz", "c1_demo2d_fixed.npz"])
 def test_spatial_mode_vs_reference_golden(pkg, golden_dir, name):
     g = load(golden_dir, name)
     sc = np.sqrt(float(g["c"]) + float(g["s2"]))
@@ -520,3 +520,28 @@ def test_spatial_mode_vs_reference_golden(pkg, golden_dir, name):
         t.apply_transportation()
         assert rel(t.training_traj, g["traj_out"]) < TOL_MEAN and rel(t.training_delta, g["delta_out"]) < TOL_MEAN
         assert np.max(np.abs(t.std - g["std"])) / sc < TOL_STD and rel(t.var_vel_transported, g["var_vel"]) < 1e-6
+
+
+def test_spatial_mode_edge_shapes(pkg):
+    """Spatial mode on degenerate shapes: fewer training points than one tile, a coordinate that is constant over the training
+    set, a single query, queries far outside the training box, and d != p (no fused generator: the mode must be a no-op)."""
+    from oracle.gp_oracle import ChoGP
+    rng = np.random.default_rng(21)
+    for (n, d, p, m) in [(7, 3, 3, 1), (50, 2, 2, 300), (130, 3, 3, 129), (90, 3, 1, 40), (60, 1, 1, 20)]:
+        X = rng.random((n, d))
+        if d == 3:
+            X[:, 2] = 0.25                                   # constant coordinate: zero-width bounding box along z
+        Y = np.sin(3.0 * X[:, :1]) + 0.1 * rng.standard_normal((n, p))
+        from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+        k = C(0.5) * RBF([0.3] * d) + WhiteKernel(1e-3)
+        gp = pkg.GaussianProcess(k, optimizer=None, variance_mode="int8w5", spatial=True)
+        gp.fit(X, Y)
+        xq = np.vstack([rng.random((m - 1, d)), 50.0 * np.ones((1, d))]) if m > 1 else rng.random((1, d))
+        ora = ChoGP(0.5, [0.3] * d, 1e-3).fit(X, Y)
+        mean, std = gp.predict(xq, return_std=True)
+        m0, s0 = ora.predict(xq, return_std=True)
+        m0 = np.reshape(m0, np.shape(mean)); s0 = np.reshape(s0, np.shape(std))
+        assert rel(mean, m0) < TOL_MEAN, (n, d, p, m)
+        assert np.max(np.abs(std - s0)) / np.sqrt(0.5 + 1e-3) < TOL_STD, (n, d, p, m)
+        J = gp.derivative(xq)
+        assert rel(J, np.reshape(ora.derivative(xq), np.shape(J))) < TOL_MEAN, (n, d, p, m)
