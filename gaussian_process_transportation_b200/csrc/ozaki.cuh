@@ -74,6 +74,44 @@ __device__ __forceinline__ int warp_uniform(int v) { return (int)__reduce_max_sy
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
+// Address-based twins for the issuing warps of the skipping variant.  A shared-memory address on sm_100 carries the CTA's rank in
+// its upper bits, and the compiler re-derived it (S2R SR_CgaCtaId, a ~50-cycle special-register read) in front of every
+// tcgen05.commit / TMA issue inside the chunk loop -- 15 % of the MMA warp's samples sat on the R2UR that waits for it.  Here the
+// base addresses are taken once per role (through an opaque mov, so they cannot be rematerialised, and a redux, so they stay on
+// the uniform datapath) and everything else is integer offsets.
+__device__ __forceinline__ uint32_t pinned_uniform_addr(const void* p) {
+    uint32_t a;
+    asm volatile("mov.u32 %0, %1;\n" : "=r"(a) : "r"(smem_u32(p)));
+    return (uint32_t)__reduce_max_sync(0xffffffffu, a);
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_u8_a(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(dst),
+        "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t smem_desc_sw64_a(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);          // start address
+    d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(512 >> 4) << 32;                  // stride byte offset: 8 rows x 64 B
+    d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+    d |= (uint64_t)4 << 61;                           // SWIZZLE_64B
+    return d;
+}
 __device__ __forceinline__ void tma_load_3d_u8(void* dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(smem_u32(dst)),
@@ -387,6 +425,7 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
     } else if (SKIP && warp == 0) {
         // ---------------- TMA producer: converged warp, one elected lane issues (see elect_one_sync) ----------------
         int gs = 0;                                          // chunks issued so far (ring position)
+        const uint32_t full0 = pinned_uniform_addr(&full[0]), empty0 = pinned_uniform_addr(&empty[0]), smem0 = pinned_uniform_addr(smem);
         for (int lt = 0;; ++lt) {
             // claim the next tile in the global L2-blocked order (all SMs stay inside one window of ~#SM tiles, which is
             // what keeps the operand slabs L2-resident; a static stride let the CTAs drift apart and cost 25 %)
@@ -415,13 +454,12 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                 const int n = S - za - zb;                  // planes za .. za+n-1 of A meet planes zb .. zb+n-1 of B
                 if (n <= 0) continue;                       // nothing but zeros in this chunk: no stage, no load
                 const int st = gs % NST;
-                if (gs >= NST) mbar_wait(&empty[st], ((gs / NST) - 1) & 1);
-                uint8_t* sA = smem + st * C::STAGE_BYTES;
-                uint8_t* sB = sA + S * OM * OKB;
+                if (gs >= NST) mbar_wait_a(empty0 + 8u * st, ((gs / NST) - 1) & 1);
+                const uint32_t sA = smem0 + st * C::STAGE_BYTES, sB = sA + S * OM * OKB, fbar = full0 + 8u * st;
                 if (elect_one_sync()) {
-                    mbar_expect_tx(&full[st], n * (OM + ON) * OKB);
-                    tma_load_3d_u8(sA, &mapsA.m[n - 1], c * OKB, rt * OM, za, &full[st]);
-                    tma_load_3d_u8(sB, &mapsB.m[n - 1], c * OKB, ti * ON, zb, &full[st]);
+                    mbar_expect_tx_a(fbar, n * (OM + ON) * OKB);
+                    tma_load_3d_u8_a(sA, &mapsA.m[n - 1], c * OKB, rt * OM, za, fbar);
+                    tma_load_3d_u8_a(sB, &mapsB.m[n - 1], c * OKB, ti * ON, zb, fbar);
                 }
                 __syncwarp();
                 ++gs;
@@ -432,6 +470,8 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
         // instruction descriptor: D = S32, A = B = INT8, both K-major, M = 128
         const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OM >> 4) << 24);   // N is or-ed in per MMA
         int gs = 0;
+        const uint32_t full0 = pinned_uniform_addr(&full[0]), empty0 = pinned_uniform_addr(&empty[0]), smem0 = pinned_uniform_addr(smem);
+        const uint32_t accf = pinned_uniform_addr(&acc_full);
         for (int lt = 0;; ++lt) {
             mbar_wait(&slot_full[lt & 1], (lt >> 1) & 1);
             const int t = warp_uniform((int)tile_slot[lt & 1]);
@@ -459,21 +499,20 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                 }
                 if (S - za - zb <= 0) continue;
                 const int st = gs % NST;
-                mbar_wait(&full[st], (gs / NST) & 1);
+                mbar_wait_a(full0 + 8u * st, (gs / NST) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint8_t* sA = smem + st * C::STAGE_BYTES;
-                const uint8_t* sB = sA + S * OM * OKB;
-                const uint64_t adesc0 = smem_desc_sw64(sA), bdesc0 = smem_desc_sw64(sB);
+                const uint32_t sA = smem0 + st * C::STAGE_BYTES, sB = sA + S * OM * OKB;
+                const uint64_t adesc0 = smem_desc_sw64_a(sA), bdesc0 = smem_desc_sw64_a(sB);
                 if (elect_one_sync()) {
                     if (c == 0) oz_issue_chunk<S, 0, 0>(adesc0, bdesc0, tmem_base, idesc_base, 1u);       // zero-initialises every column
                     else if ((za | zb) == 0) oz_issue_chunk<S, 0, 0>(adesc0, bdesc0, tmem_base, idesc_base, 0u);
                     else oz_dispatch_za<S, 0>(za, zb, adesc0, bdesc0, tmem_base, idesc_base);
-                    umma_commit(&empty[st]);        // the stage is free once these MMAs have read it
+                    umma_commit_a(empty0 + 8u * st);        // the stage is free once these MMAs have read it
                 }
                 __syncwarp();
                 ++gs;
             }
-            if (elect_one_sync()) umma_commit(&acc_full);
+            if (elect_one_sync()) umma_commit_a(accf);
             __syncwarp();
         }
     } else if (warp >= 4) {
