@@ -215,29 +215,43 @@ struct PlaneMaps {
 // walk the same masks, so both skip the same chunks and planes.  Words are fetched four chunks ahead of their use.
 struct ZeroPlaneReader {
     const unsigned *fa, *fb;
-    unsigned wa, wb, wa_next, wb_next;
+    unsigned wa_next, wb_next;     // raw masks of the NEXT four chunks (in flight while the current four are consumed)
+    unsigned code4;                // (za*8 + zb) of the current four chunks, one byte each, warp-uniform
     int ti;
     __device__ __forceinline__ void init(const unsigned* flagsA, const unsigned* flagsB, int stride, int rt, int ti_) {
         fa = flagsA ? flagsA + (long long)rt * stride : nullptr;
         fb = flagsA ? flagsB + (long long)ti_ * stride : nullptr;
         ti = ti_;
-        wa = wb = wa_next = wb_next = 0u;
+        wa_next = wb_next = 0u;
+        code4 = 0u;
         if (fa && ti >= 1) {
-            wa = __ldg(fa); wb = __ldg(fb);
-            if (ti >= 4) { wa_next = __ldg(fa + 1); wb_next = __ldg(fb + 1); }
+            wa_next = __ldg(fa); wb_next = __ldg(fb);
         }
     }
+    // leading all-zero planes of the four chunks of one mask word, packed (za*8 + zb) per byte; `first` = chunk 0 of the tile is in it
+    template <int S>
+    __device__ __forceinline__ static unsigned decode4(unsigned wa, unsigned wb, bool first) {
+        unsigned out = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned ma = (wa >> (8 * k)) & 0xffu, mb = (wb >> (8 * k)) & 0xffu;
+            const unsigned za = ma ? (unsigned)(__ffs(ma) - 1) : (unsigned)S, zb = mb ? (unsigned)(__ffs(mb) - 1) : (unsigned)S;
+            out |= (za * 8u + zb) << (8 * k);
+        }
+        return first ? (out & 0xffffff00u) : out;              // chunk 0 is always dense: it zero-initialises the accumulators
+    }
+    // call for every chunk in order; every fourth call decodes a word (and starts the load of the next one), the others cost a shift
     template <int S>
     __device__ __forceinline__ void get(int c, int& za, int& zb) {
-        za = 0; zb = 0;
-        if (!fa || c == 0) return;                          // chunk 0 is always dense: it zero-initialises the accumulators
+        if (!fa) { za = 0; zb = 0; return; }
         if ((c & 3) == 0) {
-            wa = wa_next; wb = wb_next;
+            const unsigned wa = wa_next, wb = wb_next;
             if (c + 4 <= ti) { wa_next = __ldg(fa + (c >> 2) + 1); wb_next = __ldg(fb + (c >> 2) + 1); }
+            code4 = __reduce_max_sync(0xffffffffu, decode4<S>(wa, wb, c == 0));     // warp-uniform (see elect_one_sync)
         }
-        const unsigned ma = (wa >> ((c & 3) * 8)) & 0xffu, mb = (wb >> ((c & 3) * 8)) & 0xffu;
-        za = ma ? (__ffs(ma) - 1) : S;
-        zb = mb ? (__ffs(mb) - 1) : S;
+        const unsigned z = (code4 >> ((c & 3) * 8)) & 0xffu;
+        za = (int)(z >> 3);
+        zb = (int)(z & 7u);
     }
 };
 
@@ -274,19 +288,20 @@ __device__ __forceinline__ void oz_issue_chunk(uint64_t adesc0, uint64_t bdesc0,
         }
     }
 }
-template <int S, int ZA, int ZB>
-__device__ __forceinline__ void oz_dispatch_zb(int zb, uint64_t adesc0, uint64_t bdesc0, uint32_t tmem_base, uint32_t idesc_base) {
-    if constexpr (ZA + ZB < S) {
-        if (zb == ZB) oz_issue_chunk<S, ZA, ZB>(adesc0, bdesc0, tmem_base, idesc_base, 0u);
-        else oz_dispatch_zb<S, ZA, ZB + 1>(zb, adesc0, bdesc0, tmem_base, idesc_base);
+// (za, zb) -> specialised issue code through one indexed branch
+template <int S>
+__device__ __forceinline__ void oz_dispatch(int za, int zb, uint64_t adesc0, uint64_t bdesc0, uint32_t tmem_base, uint32_t idesc_base) {
+#define OZ_CASE(ZA, ZB)                                                                                     \
+    case (ZA) * 8 + (ZB):                                                                                   \
+        if constexpr ((ZA) + (ZB) < S) oz_issue_chunk<S, (ZA), (ZB)>(adesc0, bdesc0, tmem_base, idesc_base, 0u); \
+        break;
+#define OZ_ROW(ZA) OZ_CASE(ZA, 0) OZ_CASE(ZA, 1) OZ_CASE(ZA, 2) OZ_CASE(ZA, 3) OZ_CASE(ZA, 4) OZ_CASE(ZA, 5) OZ_CASE(ZA, 6)
+    switch (za * 8 + zb) {
+        OZ_ROW(0) OZ_ROW(1) OZ_ROW(2) OZ_ROW(3) OZ_ROW(4) OZ_ROW(5) OZ_ROW(6)
+        default: break;
     }
-}
-template <int S, int ZA>
-__device__ __forceinline__ void oz_dispatch_za(int za, int zb, uint64_t adesc0, uint64_t bdesc0, uint32_t tmem_base, uint32_t idesc_base) {
-    if constexpr (ZA < S) {
-        if (za == ZA) oz_dispatch_zb<S, ZA, 0>(zb, adesc0, bdesc0, tmem_base, idesc_base);
-        else oz_dispatch_za<S, ZA + 1>(za, zb, adesc0, bdesc0, tmem_base, idesc_base);
-    }
+#undef OZ_ROW
+#undef OZ_CASE
 }
 
 __device__ __forceinline__ void oz_tile_decode(long long idx, int T64, int rowtiles, int& rt, int& ti) {
@@ -424,7 +439,8 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
         }
     } else if (SKIP && warp == 0) {
         // ---------------- TMA producer: converged warp, one elected lane issues (see elect_one_sync) ----------------
-        int gs = 0;                                          // chunks issued so far (ring position)
+        int st = 0;                                          // ring position
+        unsigned empty_par = 0xffffffffu;                    // bit i: parity to wait for on empty[i] (a fresh barrier passes parity 1)
         const uint32_t full0 = pinned_uniform_addr(&full[0]), empty0 = pinned_uniform_addr(&empty[0]), smem0 = pinned_uniform_addr(smem);
         for (int lt = 0;; ++lt) {
             // claim the next tile in the global L2-blocked order (all SMs stay inside one window of ~#SM tiles, which is
@@ -446,30 +462,25 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
             for (int c = 0; c <= ti; ++c) {
                 int za, zb;
                 zr.template get<S>(c, za, zb);
-                if (flagsA != nullptr) {
-                    const int zz = warp_uniform(za | (zb << 8));
-                    za = zz & 0xff;
-                    zb = zz >> 8;
-                }
                 const int n = S - za - zb;                  // planes za .. za+n-1 of A meet planes zb .. zb+n-1 of B
                 if (n <= 0) continue;                       // nothing but zeros in this chunk: no stage, no load
-                const int st = gs % NST;
-                if (gs >= NST) mbar_wait_a(empty0 + 8u * st, ((gs / NST) - 1) & 1);
+                mbar_wait_a(empty0 + 8u * st, (empty_par >> st) & 1u);
                 const uint32_t sA = smem0 + st * C::STAGE_BYTES, sB = sA + S * OM * OKB, fbar = full0 + 8u * st;
                 if (elect_one_sync()) {
                     mbar_expect_tx_a(fbar, n * (OM + ON) * OKB);
                     tma_load_3d_u8_a(sA, &mapsA.m[n - 1], c * OKB, rt * OM, za, fbar);
                     tma_load_3d_u8_a(sB, &mapsB.m[n - 1], c * OKB, ti * ON, zb, fbar);
                 }
-                __syncwarp();
-                ++gs;
+                empty_par ^= 1u << st;
+                st = (st + 1 == NST) ? 0 : st + 1;
             }
         }
     } else if (SKIP && warp == 1) {
         // ---------------- MMA issue: the whole warp walks the loop converged, one elected lane issues ----------------
         // instruction descriptor: D = S32, A = B = INT8, both K-major, M = 128
         const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OM >> 4) << 24);   // N is or-ed in per MMA
-        int gs = 0;
+        int st = 0;
+        unsigned full_par = 0u;                              // bit i: parity to wait for on full[i]
         const uint32_t full0 = pinned_uniform_addr(&full[0]), empty0 = pinned_uniform_addr(&empty[0]), smem0 = pinned_uniform_addr(smem);
         const uint32_t accf = pinned_uniform_addr(&acc_full);
         for (int lt = 0;; ++lt) {
@@ -492,28 +503,20 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
             for (int c = 0; c <= ti; ++c) {
                 int za, zb;
                 zr.template get<S>(c, za, zb);
-                if (flagsA != nullptr) {
-                    const int zz = warp_uniform(za | (zb << 8));
-                    za = zz & 0xff;
-                    zb = zz >> 8;
-                }
                 if (S - za - zb <= 0) continue;
-                const int st = gs % NST;
-                mbar_wait_a(full0 + 8u * st, (gs / NST) & 1);
+                mbar_wait_a(full0 + 8u * st, (full_par >> st) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint32_t sA = smem0 + st * C::STAGE_BYTES, sB = sA + S * OM * OKB;
                 const uint64_t adesc0 = smem_desc_sw64_a(sA), bdesc0 = smem_desc_sw64_a(sB);
                 if (elect_one_sync()) {
                     if (c == 0) oz_issue_chunk<S, 0, 0>(adesc0, bdesc0, tmem_base, idesc_base, 1u);       // zero-initialises every column
-                    else if ((za | zb) == 0) oz_issue_chunk<S, 0, 0>(adesc0, bdesc0, tmem_base, idesc_base, 0u);
-                    else oz_dispatch_za<S, 0>(za, zb, adesc0, bdesc0, tmem_base, idesc_base);
+                    else oz_dispatch<S>(za, zb, adesc0, bdesc0, tmem_base, idesc_base);
                     umma_commit_a(empty0 + 8u * st);        // the stage is free once these MMAs have read it
                 }
-                __syncwarp();
-                ++gs;
+                full_par ^= 1u << st;
+                st = (st + 1 == NST) ? 0 : st + 1;
             }
             if (elect_one_sync()) umma_commit_a(accf);
-            __syncwarp();
         }
     } else if (warp >= 4) {
         // ---------------- epilogue warps 4..7: TMEM lane quarter = warp % 4 ----------------
