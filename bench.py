@@ -159,6 +159,15 @@ def measure_int8_peak(torch, dev, n=8192):
             return 2.0 * 1590.0, "2 x fallback bf16 peak (1.59 PFLOP/s)"
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 for its workers; the CPU arms are meant to use every host core (only one rank runs them)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
+
+
 def cpu_baseline_sample(N, n_queries, threads_note=True):
     """The CPU path (oracle port over the real sklearn regressor) on a bounded sample: fit(optimizer=None) at N, then mode A
     = predict(return_std) + derivative() on `n_queries` points, chunked like BASELINE.md section 3."""
@@ -166,6 +175,7 @@ def cpu_baseline_sample(N, n_queries, threads_note=True):
     from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
     from oracle.gp_oracle import SkGaussianProcess
     warnings.filterwarnings("ignore")
+    use_all_host_threads()
     S, T, xq = make_inputs(N, n_queries)
     _, Sr, D = affine_and_delta(S, T)
     kern = C(KERNEL["c"]) * RBF(KERNEL["ell"]) + WhiteKernel(KERNEL["s2"])
@@ -200,6 +210,7 @@ def run_reference(args):
     from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
     from oracle.gp_oracle import SkGaussianProcess
     warnings.filterwarnings("ignore")
+    use_all_host_threads()
     wl = WORKLOADS[args.workload]
     N = wl["N"]
     nq = {4096: 4096, 16384: 1024}.get(N, 8192)
