@@ -843,11 +843,13 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
             int nsm = 148;
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
             cudaMemsetAsync(h->info + 1, 0, sizeof(int), h->stream);      // dynamic tile counter
-            const bool skipping = spatial && h->spatial == 1;
+            const bool use_masks = spatial && h->spatial == 1;
+            static const bool force_skip_variant = getenv("GPTB_OZ_FORCE_SKIP_VARIANT") != nullptr;    // A/B of the two loop versions on the dense case
+            const bool skipping = use_masks || force_skip_variant;
             const unsigned grid_oz = (unsigned)(ntiles < nsm ? ntiles : nsm);
             if (skipping)
                 oz::ozaki_trmm_kernel<SV, true><<<grid_oz, oz::OTHREADS, oz::Cfg<SV>::SMEM_BYTES, h->stream>>>(
-                    mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, sp->flagsA, h->flagsB, h->flags_stride);
+                    mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, use_masks ? sp->flagsA : nullptr, use_masks ? h->flagsB : nullptr, h->flags_stride);
             else
                 oz::ozaki_trmm_kernel<SV, false><<<grid_oz, oz::OTHREADS, oz::Cfg<SV>::SMEM_BYTES, h->stream>>>(
                     mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, nullptr, nullptr, h->flags_stride);
