@@ -149,3 +149,24 @@ def test_oracle_active_learning_gp_matches_reference_golden(golden_dir):
     dy, ds = al.derivative(g["xq"])
     assert np.allclose(mean, g["mean"], rtol=1e-11, atol=1e-13) and np.allclose(std, g["std"], rtol=0, atol=1e-10)
     assert np.allclose(dy, g["dy_dx"], rtol=1e-10, atol=1e-12) and np.allclose(ds, g["dsigma_dx"], rtol=1e-7, atol=1e-12)
+
+
+def test_digit_plane_identity_and_truncation_bound():
+    """The 8-bit digit split of csrc/digits.cuh restated in numpy: digits stay in int8, they reproduce Q exactly (carries included), and a
+    sliced dot product with S = 5 planes is within the 40-bit truncation bound of the FP64 one."""
+    from oracle.digit_planes import combine8, digit_scale8, sliced_dot, split8
+    rng = np.random.default_rng(0)
+    for S in (4, 5, 6):
+        x = np.concatenate([rng.standard_normal(4000) * 10.0 ** rng.integers(-12, 1, 4000), [0.0, 1.0, -1.0, 0.999999, -0.999999]])
+        scale = digit_scale8(np.abs(x).max())
+        planes, q = split8(x, S, scale)
+        assert planes.dtype == np.int8 and planes.shape == (S, x.size)
+        assert np.array_equal(combine8(planes), q)                                  # exact, including the byte carries
+        assert np.max(np.abs(q * (scale / 256.0 ** S) - x)) <= 0.5 * scale / 256.0 ** S + 4e-16 * scale          # half a unit of the last digit (+ FP64 rounding)
+    a = rng.random(4096) * 0.1
+    b = rng.standard_normal(4096) * np.exp(-rng.random(4096) * 20)
+    sa, sb = digit_scale8(0.1), digit_scale8(np.abs(b).max())
+    pa, _ = split8(a, 5, sa)
+    pb, _ = split8(b, 5, sb)
+    ref = float(np.dot(a, b))
+    assert abs(sliced_dot(pa, pb, sa, sb) - ref) < 4096 * 8 * 2.0 ** -40 * sa * sb
