@@ -44,8 +44,21 @@ KERNEL = dict(c=0.1, ell=[0.1, 0.1, 0.1], s2=1e-4, jitter=1e-10)
 METRIC = "GP transport query-points/sec (mean+std+Jacobian) @N train"
 
 
+def synthetic_pairs(n, d=3, seed=0):
+    """source points uniform in the unit cube; target = rigid motion (20 degrees about z + offset) + a smooth
+    residual 0.05 sin(4 S) + 0.01 N(0,1).  (Same generator as oracle.gp_oracle.synthetic_pairs, kept here so that the GPU arm
+    imports nothing from oracle/.)"""
+    rng = np.random.default_rng(seed)
+    S = rng.random((n, d))
+    th = np.radians(20.0)
+    R0 = np.eye(d)
+    R0[0, 0], R0[0, 1], R0[1, 0], R0[1, 1] = np.cos(th), -np.sin(th), np.sin(th), np.cos(th)
+    t0 = np.linspace(0.3, -0.2, d)
+    T = S @ R0.T + t0 + 0.05 * np.sin(4.0 * S) + 0.01 * rng.standard_normal((n, d))
+    return S, T
+
+
 def make_inputs(N, M, rank=0):
-    from oracle.gp_oracle import synthetic_pairs  # input generator only (shared with the tests); no oracle compute here
     S, T = synthetic_pairs(N, 3, seed=0)
     rng = np.random.default_rng(1000 + rank)
     xq = -0.1 + 1.2 * rng.random((M, 3))

@@ -47,6 +47,8 @@ SYMBOLS = {
     "gptb_set_workspace_limit": (C.c_int, [C.c_void_p, C.c_int64]),
     "gptb_set_query_pipeline": (C.c_int, [C.c_void_p, C.c_int]),
     "gptb_set_spatial": (C.c_int, [C.c_void_p, C.c_int]),
+    "gptb_executed_products": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
+    "gptb_set_debug_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "gptb_test_gemm_nt": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gptb_test_potrf_tile": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.POINTER(C.c_int)]),
 }
@@ -299,6 +301,15 @@ class Engine:
         """INT8-sliced path: overlap the generator of the next batch with the products of the current one (default off:
         no gain under the power cap, see include/gptb200.h)."""
         self._check(self.lib.gptb_set_query_pipeline(self.h, int(bool(on))), "gptb_set_query_pipeline")
+
+    def executed_products(self, reset=False):
+        """(plane pair, k-chunk, tile) products issued by the INT8-sliced product kernel since the last reset (include/gptb200.h)."""
+        n = C.c_int64(0)
+        self._check(self.lib.gptb_executed_products(self.h, C.byref(n), int(bool(reset))), "gptb_executed_products")
+        return int(n.value)
+
+    def set_debug_option(self, name, value):
+        self._check(self.lib.gptb_set_debug_option(self.h, str(name).encode(), int(value)), "gptb_set_debug_option")
 
     def set_workspace_limit(self, nbytes):
         self._check(self.lib.gptb_set_workspace_limit(self.h, int(nbytes)), "gptb_set_workspace_limit")

@@ -81,7 +81,10 @@ struct gptb_handle {
     // spatial mode (gptb_set_spatial): training points in Morton order, query batches sorted by Morton key, zero digit planes
     // skipped by the INT8-sliced product kernel
     int spatial = 0;
-    int spatial_shuffle = 1;                  // chunk order shuffled (GPTB_SPATIAL_SHUFFLE=0 keeps the plain Z-order: A/B only)
+    int spatial_shuffle = 1;                  // chunk order shuffled (gptb_set_debug_option "spatial_shuffle" 0 keeps the plain Z-order: A/B only)
+    int oz_force_skip = 0;                    // debug option "oz_force_skip_variant": dense case through the skipping loops (A/B of the two loop versions)
+    int oz_whatif = 0;                        // debug option "oz_whatif" (only acts in a -DGPTB_OZ_WHATIF build)
+    unsigned long long exec_pairs_host = 0;   // plane-pair x chunk products issued by the dense product kernel (counted on the host)
     std::vector<int> perm;                    // perm[i] = caller's index of internal training row i (empty: natural order)
     bool perm_known = true;                   // false on a handle whose state arrived by broadcast (exports need the permutation)
     MortonBox mbox{};
@@ -227,6 +230,7 @@ extern "C" int gptb_create(int device, gptb_handle** out) {
         delete h;
         return -2;
     }
+    if (cudaMemset(h->scal, 0, 64 * sizeof(double)) != cudaSuccess) { delete h; return -2; }
     int rc = set_kernel_attrs(h);
     if (rc) { delete h; return rc; }
     h->af.on = 0;
@@ -273,8 +277,30 @@ extern "C" int gptb_set_spatial(gptb_handle* h, int on) {
     if ((on != 0) != (h->spatial != 0) && h->have_train)
         GPTB_FAIL(h, -1, "gptb_set_spatial must be called before gptb_set_train (the training order is fixed there)");
     if (on < 0 || on > 2) GPTB_FAIL(h, -1, "gptb_set_spatial: mode must be 0, 1 or 2");
-    if (const char* e = getenv("GPTB_SPATIAL_SHUFFLE")) h->spatial_shuffle = atoi(e) != 0;
     h->spatial = on;          // 2 = Morton order and sorted batches, but every plane product issued (A/B of the skipping itself)
+    return 0;
+}
+extern "C" int gptb_set_debug_option(gptb_handle* h, const char* name, int value) {
+    if (!h || !name) return -1;
+    if (!strcmp(name, "spatial_shuffle")) h->spatial_shuffle = value != 0;
+    else if (!strcmp(name, "oz_force_skip_variant")) h->oz_force_skip = value != 0;
+    else if (!strcmp(name, "oz_whatif")) h->oz_whatif = value;
+    else GPTB_FAIL(h, -1, "gptb_set_debug_option: unknown option '%s'", name);
+    return 0;
+}
+// device counter of the skipping product kernel + the host-side count of the dense one
+static unsigned long long* exec_counter(gptb_handle* h) { return reinterpret_cast<unsigned long long*>(h->scal + 40); }
+extern "C" int gptb_executed_products(gptb_handle* h, int64_t* pairs, int reset) {
+    if (!h || !pairs) return -1;
+    CU(h, cudaSetDevice(h->device));
+    unsigned long long dev = 0;
+    CU(h, cudaMemcpyAsync(&dev, exec_counter(h), sizeof(dev), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    *pairs = (int64_t)(dev + h->exec_pairs_host);
+    if (reset) {
+        CU(h, cudaMemsetAsync(exec_counter(h), 0, sizeof(dev), h->stream));
+        h->exec_pairs_host = 0;
+    }
     return 0;
 }
 extern "C" int gptb_set_query_pipeline(gptb_handle* h, int on) {
@@ -334,7 +360,7 @@ static int alloc_model(gptb_handle* h, long long N, int d, int p, bool train) {
         }
     }
     h->N = N;
-    h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = false;
+    h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = h->have_bplanes = false;
     return 0;
 }
 
@@ -748,10 +774,11 @@ static bool oz_fused_supported(int d, int p) { return d == p && (d == 2 || d == 
 
 // scratch of the spatial mode for one batch: Morton keys / batch positions (radix-sort double buffers) and the block masks
 struct SpatialWs {
-    unsigned *keys_in, *keys_out, *vals_in, *vals_out;
+    unsigned *keys_in, *keys_out, *vals_in;      // used by the generator stream only: shared by the two pipeline slots
+    unsigned* vals_out[2];                       // qperm of the batch in slot b (read by the generator AND by finalize)
     void* cub_tmp;
     size_t cub_bytes;
-    unsigned* flagsA;
+    unsigned* flagsA[2];                         // block masks of the batch in slot b (written by the generator, read by the products)
 };
 
 template <int D, int P>
@@ -773,6 +800,9 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
     const bool fused = (nrhs > 0 && h->var_mode == 1 && oz_fused_supported(D, P));
     int8_t* Aplanes = reinterpret_cast<int8_t*>(oz_planes);
     const bool spatial = fused && sp != nullptr;
+    const int slot = pipe_slot >= 0 ? pipe_slot : 0;
+    unsigned* const vals_out_slot = spatial ? sp->vals_out[slot] : nullptr;
+    unsigned* const flagsA_slot = spatial ? sp->flagsA[slot] : nullptr;
     if (fused) {
         DigitScales ds{};
         if (spatial) {
@@ -780,10 +810,10 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
             morton_keys_kernel<D><<<(unsigned)((B + 255) / 256), 256, 0, gs>>>(x_dev, B, af, h->mbox, sp->keys_in, sp->vals_in);
             LAUNCH_CHECK(h);
             size_t tmp_bytes = sp->cub_bytes;
-            CU(h, cub::DeviceRadixSort::SortPairs(sp->cub_tmp, tmp_bytes, sp->keys_in, sp->keys_out, sp->vals_in, sp->vals_out, B, 0, h->mbox.bits * D, gs));
-            CU(h, cudaMemsetAsync(sp->flagsA, 0, sizeof(unsigned) * (size_t)(rows_total / 128) * h->flags_stride, gs));
-            ds.qperm = sp->vals_out;
-            ds.flags = sp->flagsA;
+            CU(h, cub::DeviceRadixSort::SortPairs(sp->cub_tmp, tmp_bytes, sp->keys_in, sp->keys_out, sp->vals_in, vals_out_slot, B, 0, h->mbox.bits * D, gs));
+            CU(h, cudaMemsetAsync(flagsA_slot, 0, sizeof(unsigned) * (size_t)(rows_total / 128) * h->flags_stride, gs));
+            ds.qperm = vals_out_slot;
+            ds.flags = flagsA_slot;
             ds.flags_stride = h->flags_stride;
         }
         auto set = [&](int idx, double bound) {
@@ -844,15 +874,17 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
             cudaMemsetAsync(h->info + 1, 0, sizeof(int), h->stream);      // dynamic tile counter
             const bool use_masks = spatial && h->spatial == 1;
-            static const bool force_skip_variant = getenv("GPTB_OZ_FORCE_SKIP_VARIANT") != nullptr;    // A/B of the two loop versions on the dense case
-            const bool skipping = use_masks || force_skip_variant;
+            const bool skipping = use_masks || h->oz_force_skip;
             const unsigned grid_oz = (unsigned)(ntiles < nsm ? ntiles : nsm);
-            if (skipping)
+            if (skipping) {
                 oz::ozaki_trmm_kernel<SV, true><<<grid_oz, oz::OTHREADS, oz::Cfg<SV>::SMEM_BYTES, h->stream>>>(
-                    mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, use_masks ? sp->flagsA : nullptr, use_masks ? h->flagsB : nullptr, h->flags_stride);
-            else
+                    mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, use_masks ? flagsA_slot : nullptr, use_masks ? h->flagsB : nullptr, h->flags_stride,
+                    exec_counter(h), h->oz_whatif);
+            } else {
                 oz::ozaki_trmm_kernel<SV, false><<<grid_oz, oz::OTHREADS, oz::Cfg<SV>::SMEM_BYTES, h->stream>>>(
-                    mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, nullptr, nullptr, h->flags_stride);
+                    mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, nullptr, nullptr, h->flags_stride, nullptr, 0);
+                h->exec_pairs_host += (unsigned long long)rowtiles * ((unsigned long long)T64 * (T64 + 1) / 2) * (unsigned long long)(SV * (SV + 1) / 2);
+            }
         });
         toc(h, 0);
         LAUNCH_CHECK(h);
@@ -865,7 +897,7 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
         LAUNCH_CHECK(h);
     }
     finalize_kernel<D, P><<<(B + 127) / 128, 128, 0, h->stream>>>(macc, nsplit, part, Tpart, B, Bpad, rows_total, xr, vel_dev, h->kp, h->af, flags, out, q_off, Mtot,
-                                                                  spatial ? sp->vals_out : nullptr);
+                                                                  vals_out_slot);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -925,10 +957,11 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     // INT8-sliced path with the fused generator: double-buffered batches so the generator of batch i+1 (FP64 pipe, gen stream)
     // runs under the digit-plane products of batch i (tensor pipe, main stream).  The stream is cut into >= 8 batches of
     // >= 8192 queries (enough 128 x 64 tiles to fill the persistent product kernel many times over).
-    // spatial mode (8-bit planes, fused generator): sorted batches + block masks; not combined with the overlap pipeline
+    // spatial mode (8-bit planes, fused generator): sorted batches + block masks; with the overlap pipeline the per-batch sort
+    // permutation and block masks are double-buffered like the digit planes
     const bool spatial_q = fused_planes && h->spatial && h->var_bits == 8;
     int nbuf = 1;
-    if (fused_planes && h->pipeline && !spatial_q && M >= 2 * 8192) {
+    if (fused_planes && h->pipeline && M >= 2 * 8192) {
         long long bp = (M / 8 + TS - 1) / TS * TS;
         if (bp < 8192) bp = 8192;
         const long long cap2 = batch_cap(2);
@@ -956,14 +989,14 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
         o_xr[b] = carve((size_t)Bfirst * d);
     }
     SpatialWs sp{};
-    size_t o_sp[6] = {0, 0, 0, 0, 0, 0};
+    size_t o_sp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (spatial_q) {
-        for (int i = 0; i < 4; ++i) o_sp[i] = carve(((size_t)Bfirst + 1) / 2);                 // Bfirst 32-bit words each
+        for (int i = 0; i < 5; ++i) o_sp[i] = carve(((size_t)Bfirst + 1) / 2);                 // Bfirst 32-bit words each (3 shared + vals_out per slot)
         sp.cub_bytes = 0;
         CU(h, cub::DeviceRadixSort::SortPairs(nullptr, sp.cub_bytes, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr,
                                               (int)Bfirst, 0, h->mbox.bits * d, h->stream));
-        o_sp[4] = carve((sp.cub_bytes + 7) / 8);
-        o_sp[5] = carve(((size_t)(nrhs * Bfirst / 128) * h->flags_stride + 1) / 2);
+        o_sp[5] = carve((sp.cub_bytes + 7) / 8);
+        for (int b = 0; b < 2; ++b) o_sp[6 + b] = carve(((size_t)(nrhs * Bfirst / 128) * h->flags_stride + 1) / 2);
     }
     if (need > h->ws_bytes) {
         CU(h, cudaStreamSynchronize(h->stream));
@@ -980,9 +1013,11 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
         sp.keys_in = reinterpret_cast<unsigned*>(base + o_sp[0]);
         sp.keys_out = reinterpret_cast<unsigned*>(base + o_sp[1]);
         sp.vals_in = reinterpret_cast<unsigned*>(base + o_sp[2]);
-        sp.vals_out = reinterpret_cast<unsigned*>(base + o_sp[3]);
-        sp.cub_tmp = base + o_sp[4];
-        sp.flagsA = reinterpret_cast<unsigned*>(base + o_sp[5]);
+        sp.vals_out[0] = reinterpret_cast<unsigned*>(base + o_sp[3]);
+        sp.vals_out[1] = reinterpret_cast<unsigned*>(base + o_sp[4]);
+        sp.cub_tmp = base + o_sp[5];
+        sp.flagsA[0] = reinterpret_cast<unsigned*>(base + o_sp[6]);
+        sp.flagsA[1] = reinterpret_cast<unsigned*>(base + o_sp[7]);
     }
     QueryOut out{mean_dev, std_dev, jac_dev, jacvar_dev, xhat_dev, vhat_dev, vvar_dev, jphi_dev, dvar_dev};
     chunk_fn fn = pick_chunk_fn(d, p);
@@ -1367,6 +1402,7 @@ extern "C" int gptb_state_commit(gptb_handle* h) {
     h->have_alpha = true;                                   // mean / Jacobian queries are served from (X, alpha)
     h->have_minv = (hd[10] != 0.0) && (h->Minv != nullptr);  // variance queries need the inverse factor
     h->have_kinv = false;
+    h->have_bplanes = false;                                 // digit planes of a previous model's inverse factor are stale
     return 0;
 }
 

@@ -25,7 +25,7 @@ namespace oz {
 constexpr int OM = 128;      // queries per tile (UMMA M)
 constexpr int ON = 64;       // inverse-factor rows per tile (UMMA N)
 constexpr int OKB = 64;      // k bytes (= k elements) per pipeline chunk, one 64-byte swizzle row
-constexpr int OTHREADS = 256;   // warp group 0: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner (2, 3 idle); warp group 1: epilogue
+constexpr int OTHREADS = 256;   // warp group 0: warp 0 = TMA producer, warps 1..NST = MMA issuers (warp 1 owns TMEM); warp group 1: epilogue
 // Register budget (setmaxnreg): __launch_bounds__(256, 2) launches the CTA with 128 registers per thread; warp group 0
 // gives back down to 80 and the epilogue warp group grows to 176 (128*80 + 128*176 = 256*128; ptxas compiles each
 // branch against its own budget, no spills).  What matters is the LAUNCH footprint: 2 warps x 128 x 32 = 8 K of the 16 K
@@ -90,6 +90,9 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, unsigned parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar), "r"(parity)
         : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
@@ -329,12 +332,23 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                                                                 int T64, int rowtiles, long long rows_total,
                                                                 double* __restrict__ part, int* __restrict__ tile_counter, int digit_bits,
                                                                 const unsigned* __restrict__ flagsA, const unsigned* __restrict__ flagsB,
-                                                                int flags_stride) {
+                                                                int flags_stride, unsigned long long* __restrict__ exec_pairs, int whatif) {
+    // exec_pairs (may be null): number of (plane pair, 64-byte chunk) products this launch really issued, one atomicAdd per tile --
+    // the executed-work figure of the roofline (the dense variant issues S(S+1)/2 per chunk by construction, counted on the host).
+    // whatif: developer builds only (-DGPTB_OZ_WHATIF, tools/whatif.py): bit 0 = no TMA loads, bit 1 = no MMA issue, bit 2 = no
+    // epilogue arithmetic -- which resource bounds the launch; compiled out of the product library.
+#ifndef GPTB_OZ_WHATIF
+    (void)whatif;
+    constexpr int wi = 0;
+#else
+    const int wi = whatif;
+#endif
     using C = Cfg<S>;
     constexpr int NST = C::NST;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t full[NST], empty[NST], acc_full, acc_empty, slot_full[2], slot_empty[2];
+    __shared__ __align__(8) uint64_t full[NST], empty[NST], acc_full, acc_empty, slot_full[2], slot_empty[2], tile_go;
+    constexpr int NMMA = SKIP ? NST : 1;   // issuing warps (skipping variant: one per ring stage)
     __shared__ uint32_t tmem_base_s;
     __shared__ int tile_slot[2];           // dynamic tile scheduler: the producer claims tiles, the other roles follow
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -342,9 +356,10 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
 
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(&acc_full, 1);
+        mbar_init(&acc_full, NMMA);        // one tcgen05.commit per issuing warp
         mbar_init(&acc_empty, 4);          // one arrival per epilogue warp
-        for (int i = 0; i < 2; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 5); }   // MMA thread + 4 epilogue warps
+        mbar_init(&tile_go, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], NMMA + 4); }   // issuing warps + 4 epilogue warps
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {
@@ -467,22 +482,37 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                 mbar_wait_a(empty0 + 8u * st, (empty_par >> st) & 1u);
                 const uint32_t sA = smem0 + st * C::STAGE_BYTES, sB = sA + S * OM * OKB, fbar = full0 + 8u * st;
                 if (elect_one_sync()) {
-                    mbar_expect_tx_a(fbar, n * (OM + ON) * OKB);
-                    tma_load_3d_u8_a(sA, &mapsA.m[n - 1], c * OKB, rt * OM, za, fbar);
-                    tma_load_3d_u8_a(sB, &mapsB.m[n - 1], c * OKB, ti * ON, zb, fbar);
+                    if (wi & 1) {
+                        mbar_expect_tx_a(fbar, 0);
+                    } else {
+                        mbar_expect_tx_a(fbar, n * (OM + ON) * OKB);
+                        tma_load_3d_u8_a(sA, &mapsA.m[n - 1], c * OKB, rt * OM, za, fbar);
+                        tma_load_3d_u8_a(sB, &mapsB.m[n - 1], c * OKB, ti * ON, zb, fbar);
+                    }
                 }
                 empty_par ^= 1u << st;
                 st = (st + 1 == NST) ? 0 : st + 1;
             }
         }
-    } else if (SKIP && warp == 1) {
-        // ---------------- MMA issue: the whole warp walks the loop converged, one elected lane issues ----------------
+    } else if (SKIP && warp >= 1 && warp <= NST) {
+        // ---------------- MMA issue: NST warps, warp w owns ring stage w-1 (converged warps, one elected lane issues) ----------------
+        // Measured (tools/whatif.py, profiles/r02_whatif_*.log): with ONE issuing warp the launch time was the SUM of the control path
+        // (barrier wait, mask decode, descriptor arithmetic, indexed branch: ~670 cycles per chunk) and the MMA time -- the tensor
+        // pipe's instruction queue is shallow, the issuing warp blocks in UTCIMMA until earlier MMAs have drained, and its next
+        // control path then runs with the pipe idle.  Executed chunk e uses stage e % NST, so giving every stage its own issuing
+        // warp puts the control path of chunks e+1, e+2 under the MMAs of chunk e; every warp sees every phase of its own
+        // full/empty barriers, no phase is skipped.  int32 accumulation is exact, so the order in which the warps' MMAs reach the
+        // pipe does not matter -- except that the chunk-0 products (accumulate = 0) must be issued first: the stage owner of a
+        // tile's first chunk signals tile_go after issuing them, the others wait for it before their first issue of the tile.
         // instruction descriptor: D = S32, A = B = INT8, both K-major, M = 128
         const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OM >> 4) << 24);   // N is or-ed in per MMA
-        int st = 0;
-        unsigned full_par = 0u;                              // bit i: parity to wait for on full[i]
-        const uint32_t full0 = pinned_uniform_addr(&full[0]), empty0 = pinned_uniform_addr(&empty[0]), smem0 = pinned_uniform_addr(smem);
-        const uint32_t accf = pinned_uniform_addr(&acc_full);
+        const int my = warp - 1;                             // the ring stage this warp owns
+        int st = 0;                                          // ring position of the next executed chunk (all issuing warps count alike)
+        unsigned my_par = 0u;                                // parity to wait for on full[my]
+        const uint32_t full_my = pinned_uniform_addr(&full[my]), empty_my = pinned_uniform_addr(&empty[my]);
+        const uint32_t sA = pinned_uniform_addr(smem + my * C::STAGE_BYTES), sB = sA + S * OM * OKB;
+        const uint64_t adesc0 = smem_desc_sw64_a(sA), bdesc0 = smem_desc_sw64_a(sB);
+        const uint32_t accf = pinned_uniform_addr(&acc_full), tgo = pinned_uniform_addr(&tile_go);
         for (int lt = 0;; ++lt) {
             mbar_wait(&slot_full[lt & 1], (lt >> 1) & 1);
             const int t = warp_uniform((int)tile_slot[lt & 1]);
@@ -495,28 +525,46 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                 mbar_wait(&acc_empty, (lt - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             }
+            const bool leader = (st == my);                  // chunk 0 of this tile lands on my stage
+            bool go_seen = leader;
             // spatial mode: per (row tile, chunk) / (factor-row tile, chunk) masks of the non-zero digit planes.  Leading zero
             // planes (small values: far-away training points, far-off-diagonal entries of L^-1) are neither loaded nor
             // multiplied -- exact, the skipped products are sums of zeros.
             ZeroPlaneReader zr;
             zr.init(flagsA, flagsB, flags_stride, rt, ti);
+            unsigned npairs = 0;                             // plane-pair products issued by this warp for this tile
             for (int c = 0; c <= ti; ++c) {
                 int za, zb;
                 zr.template get<S>(c, za, zb);
                 if (S - za - zb <= 0) continue;
-                mbar_wait_a(full0 + 8u * st, (full_par >> st) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint32_t sA = smem0 + st * C::STAGE_BYTES, sB = sA + S * OM * OKB;
-                const uint64_t adesc0 = smem_desc_sw64_a(sA), bdesc0 = smem_desc_sw64_a(sB);
-                if (elect_one_sync()) {
-                    if (c == 0) oz_issue_chunk<S, 0, 0>(adesc0, bdesc0, tmem_base, idesc_base, 1u);       // zero-initialises every column
-                    else oz_dispatch<S>(za, zb, adesc0, bdesc0, tmem_base, idesc_base);
-                    umma_commit_a(empty0 + 8u * st);        // the stage is free once these MMAs have read it
-                }
-                full_par ^= 1u << st;
+                const bool mine = (st == my);
                 st = (st + 1 == NST) ? 0 : st + 1;
+                if (!mine) continue;
+                {
+                    const int n = (c == 0) ? S : S - za - zb;
+                    npairs += (unsigned)(n * (n + 1) / 2);
+                }
+                mbar_wait_a(full_my, my_par);
+                my_par ^= 1u;
+                if (!go_seen) {
+                    mbar_wait_a(tgo, (unsigned)(lt & 1));
+                    go_seen = true;
+                }
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                if (elect_one_sync()) {
+                    if (!(wi & 2)) {
+                        if (c == 0) oz_issue_chunk<S, 0, 0>(adesc0, bdesc0, tmem_base, idesc_base, 1u);   // zero-initialises every column
+                        else oz_dispatch<S>(za, zb, adesc0, bdesc0, tmem_base, idesc_base);
+                    }
+                    umma_commit_a(empty_my);                // the stage is free once these MMAs have read it
+                    if (c == 0) mbar_arrive_a(tgo);         // the zero-initialising products are in the pipe: the other warps may issue
+                }
             }
-            if (elect_one_sync()) umma_commit_a(accf);
+            if (!go_seen) mbar_wait_a(tgo, (unsigned)(lt & 1));     // keep this warp's phase count of tile_go in step
+            if (elect_one_sync()) {
+                umma_commit_a(accf);                         // acc_full completes when all NST warps' products of the tile are done
+                if (exec_pairs != nullptr && npairs != 0u) atomicAdd(exec_pairs, (unsigned long long)npairs);
+            }
         }
     } else if (warp >= 4) {
         // ---------------- epilogue warps 4..7: TMEM lane quarter = warp % 4 ----------------
@@ -536,8 +584,13 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
             mbar_wait(&acc_full, lt & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             double ssum = 0.0;
+            if (wi & 4) {
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty);
+            }
 #pragma unroll 1
-            for (int cb = 0; cb < ON / 16; ++cb) {
+            for (int cb = (wi & 4) ? ON / 16 : 0; cb < ON / 16; ++cb) {
                 double v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = 0.0;

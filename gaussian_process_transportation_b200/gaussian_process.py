@@ -57,6 +57,7 @@ class _Regressor:
 
     @property
     def alpha_(self):
+        self._o._ensure_fitted_factor()     # an LML evaluation at another theta may have overwritten the handle's factor
         return self._o._engine.export_alpha()
 
     @property

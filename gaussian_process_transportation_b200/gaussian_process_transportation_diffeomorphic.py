@@ -10,8 +10,6 @@ Differences to `GaussianProcessTransportation` that are reproduced on purpose (t
 the Jacobian of the orientation branch is evaluated at the ROTATED positions and composed as
 quat(I + J) * (quat(R) * q) (file:97-101) instead of quat(R + J R) * q at the un-rotated ones.
 """
-import pickle
-
 import numpy as np
 from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
 
@@ -25,25 +23,6 @@ class GaussianProcessTransportationDiffeo():
     def __init__(self, kernel_transport=C(0.1) * RBF(length_scale=[0.1]) + WhiteKernel(0.0001)):
         super(GaussianProcessTransportationDiffeo, self).__init__()
         self.kernel_transport = kernel_transport
-
-    # -- distributions on disk (file:20-47) ---------------------------------------------------------------------
-    def save_distributions(self):
-        with open("distributions/source.pkl", "wb") as f:
-            pickle.dump(self.source_distribution, f)
-        with open("distributions/target.pkl", "wb") as f:
-            pickle.dump(self.target_distribution, f)
-
-    def load_distributions(self):
-        try:
-            with open("distributions/source.pkl", "rb") as source:
-                self.source_distribution = pickle.load(source)
-        except Exception:
-            print("No source distribution saved")
-        try:
-            with open("distributions/target.pkl", "rb") as target:
-                self.target_distribution = pickle.load(target)
-        except Exception:
-            print("No target distribution saved")
 
     # -- fit (file:50-66) ----------------------------------------------------------------------------------------
     def fit_transportation(self, optimize=True, do_scale=False, do_rotation=True):
@@ -129,11 +108,7 @@ class GaussianProcessTransportationDiffeo():
                               "diffeomorphism_error(trial) is available without it") from exc
         study = optuna.create_study(direction="minimize")
         study.optimize(self.diffeomorphism_error, n_trials=n_trials)
-        print("Number of finished trials: {}".format(len(study.trials)))
         trial = study.best_trial
-        print("Best trial:\n  Value: {}\n  Params: ".format(trial.value))
-        for key, value in trial.params.items():
-            print("    {}: {}".format(key, value))
         self.kernel_transport = C(0.1) * RBF(length_scale=np.ones(self.training_traj.shape[1]),
                                              length_scale_bounds=[1, trial.params['max_lengthscale']]) + WhiteKernel(0.0001)
         self.fit_transportation()

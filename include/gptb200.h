@@ -168,6 +168,15 @@ int gptb_set_workspace_limit(gptb_handle* h, int64_t bytes);
  * step is no faster than the serialised one (profiles/r01_pipeline_ab.log).  Results are bit-identical either way. */
 int gptb_set_query_pipeline(gptb_handle* h, int on);
 
+/* number of (digit-plane pair, 64-byte k-chunk, 128 x 64 tile) products the INT8-sliced product kernel has issued since the last
+ * reset (each is 2 * 128 * 64 * 64 int8 operations): the EXECUTED work of the roofline -- in spatial mode the kernel skips
+ * products of all-zero planes, so this is below the algorithmic S(S+1)/2 per chunk.  Synchronises the handle's stream. */
+int gptb_executed_products(gptb_handle* h, int64_t* pairs, int reset);
+/* developer switches, none of them on a hot path (A/B measurements only): "spatial_shuffle" (1 default; 0 keeps the plain Z-order,
+ * before gptb_set_train), "oz_force_skip_variant" (1: the dense case runs through the skipping loops), "oz_whatif" (bit mask, acts
+ * only in a -DGPTB_OZ_WHATIF build of the library: tools/whatif.py). */
+int gptb_set_debug_option(gptb_handle* h, const char* name, int value);
+
 /* ---- unit-test hooks: exercise the DMMA tile engine and the small factor kernels in isolation.
  * C (128*mt,128*nt) = A (128*mt,K) * B(128*nt,K)^T, all row-major host arrays, K multiple of 128. */
 int gptb_test_gemm_nt(gptb_handle* h, const double* A, const double* B, double* C, int mt, int nt, int K,
