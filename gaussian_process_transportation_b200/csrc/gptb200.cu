@@ -188,13 +188,13 @@ static int set_kernel_attrs(gptb_handle* h) {
     CU(h, cudaFuncSetAttribute(kinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(trmm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<4>::SMEM_BYTES));
-    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<4>::SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<4>::SMEM_SKIP_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<5>::SMEM_BYTES));
-    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<5>::SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<5>::SMEM_SKIP_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<6>::SMEM_BYTES));
-    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<6>::SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<6>::SMEM_SKIP_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<7>::SMEM_BYTES));
-    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<7>::SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<7>::SMEM_SKIP_BYTES));
     CU(h, cudaFuncSetAttribute(trmm_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(cov_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(cov_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -877,7 +877,7 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
             const bool skipping = use_masks || h->oz_force_skip;
             const unsigned grid_oz = (unsigned)(ntiles < nsm ? ntiles : nsm);
             if (skipping) {
-                oz::ozaki_trmm_kernel<SV, true><<<grid_oz, oz::OTHREADS, oz::Cfg<SV>::SMEM_BYTES, h->stream>>>(
+                oz::ozaki_trmm_kernel<SV, true><<<grid_oz, oz::OTHREADS, oz::Cfg<SV>::SMEM_SKIP_BYTES, h->stream>>>(
                     mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, use_masks ? flagsA_slot : nullptr, use_masks ? h->flagsB : nullptr, h->flags_stride,
                     exec_counter(h), h->oz_whatif);
             } else {

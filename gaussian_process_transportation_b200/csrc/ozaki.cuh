@@ -41,6 +41,11 @@ template <int S> struct Cfg {
     static constexpr int NST = (3 * STAGE_BYTES <= 222 * 1024) ? 3 : 2;
     static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 1024;   // + alignment slack
     static constexpr int TMEM_COLS = 512;                          // S * 64 <= 448 columns used
+    // skipping variant: plane-granular operand ring (one slot = one A plane 128 x 64 B + one B plane 64 x 64 B)
+    static constexpr int SLOT_A = OM * OKB, SLOT_B = ON * OKB;
+    static constexpr int NSLOT = (216 * 1024) / (SLOT_A + SLOT_B);                 // 18
+    static constexpr int NE = 12;                                                  // chunks in flight (barrier ring), a multiple of the 3 issuing warps
+    static constexpr int SMEM_SKIP_BYTES = NSLOT * (SLOT_A + SLOT_B) + 1024;
 };
 
 __device__ __forceinline__ uint64_t smem_desc_sw64(const void* p) {
@@ -347,15 +352,16 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
     constexpr int NST = C::NST;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t full[NST], empty[NST], acc_full, acc_empty, slot_full[2], slot_empty[2], tile_go;
-    constexpr int NMMA = SKIP ? NST : 1;   // issuing warps (skipping variant: one per ring stage)
+    constexpr int NBAR = SKIP ? C::NE : NST;
+    __shared__ __align__(8) uint64_t full[NBAR], empty[NBAR], acc_full, acc_empty, slot_full[2], slot_empty[2], tile_go;
+    constexpr int NMMA = SKIP ? 3 : 1;     // issuing warps (skipping variant: warps 1..3, chunk entry e belongs to warp 1 + e % 3)
     __shared__ uint32_t tmem_base_s;
     __shared__ int tile_slot[2];           // dynamic tile scheduler: the producer claims tiles, the other roles follow
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long ntiles = (long long)rowtiles * T64;
 
     if (tid == 0) {
-        for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < NBAR; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(&acc_full, NMMA);        // one tcgen05.commit per issuing warp
         mbar_init(&acc_empty, 4);          // one arrival per epilogue warp
         mbar_init(&tile_go, 1);
@@ -454,9 +460,20 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
         }
     } else if (SKIP && warp == 0) {
         // ---------------- TMA producer: converged warp, one elected lane issues (see elect_one_sync) ----------------
-        int st = 0;                                          // ring position
-        unsigned empty_par = 0xffffffffu;                    // bit i: parity to wait for on empty[i] (a fresh barrier passes parity 1)
-        const uint32_t full0 = pinned_uniform_addr(&full[0]), empty0 = pinned_uniform_addr(&empty[0]), smem0 = pinned_uniform_addr(smem);
+        // Operand ring of NSLOT plane slots (slot = one A plane + one B plane of a 64-byte k-chunk): a chunk with n live planes takes n
+        // CONSECUTIVE slots (the wide MMAs need its B planes stacked, the TMA box its A planes), so up to NE chunks are in flight
+        // instead of three fixed 5-plane stages.  Measured with the what-if build (profiles/r02_whatif_b_*.log): with three stages
+        // the launch was bound by the per-stage round trip (empty -> TMA issue -> TMA latency -> full -> MMA issue -> MMAs ->
+        // commit, ~2000 cycles + the chunk's MMAs) divided by 3, far above the ~350 cycles of MMA work an average chunk carries.
+        // Slots are released in FIFO order: the producer retires the oldest chunk (waits for its empty barrier) until the next
+        // allocation fits.  The issuing warps replay the same allocation arithmetic, so no addresses travel between the roles.
+        constexpr int NE = C::NE, NSLOT = C::NSLOT;
+        int head = 0, free_slots = NSLOT;                    // next slot to hand out / slots not held by a chunk in flight
+        int ej = 0, tj = 0, inflight = 0;                    // barrier index of the next chunk / of the oldest chunk in flight
+        unsigned tpar = 0u;                                  // parity of empty[tj] that retires the oldest chunk
+        unsigned long long used = 0ull;                      // 4 bits per barrier index: slots held by that chunk (incl. wrap padding)
+        const uint32_t full0 = pinned_uniform_addr(&full[0]), empty0 = pinned_uniform_addr(&empty[0]);
+        const uint32_t smemA = pinned_uniform_addr(smem), smemB = smemA + NSLOT * C::SLOT_A;
         for (int lt = 0;; ++lt) {
             // claim the next tile in the global L2-blocked order (all SMs stay inside one window of ~#SM tiles, which is
             // what keeps the operand slabs L2-resident; a static stride let the CTAs drift apart and cost 25 %)
@@ -478,40 +495,51 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                 int za, zb;
                 zr.template get<S>(c, za, zb);
                 const int n = S - za - zb;                  // planes za .. za+n-1 of A meet planes zb .. zb+n-1 of B
-                if (n <= 0) continue;                       // nothing but zeros in this chunk: no stage, no load
-                mbar_wait_a(empty0 + 8u * st, (empty_par >> st) & 1u);
-                const uint32_t sA = smem0 + st * C::STAGE_BYTES, sB = sA + S * OM * OKB, fbar = full0 + 8u * st;
+                if (n <= 0) continue;                       // nothing but zeros in this chunk: no slot, no load
+                int base = head, need = n;
+                if (head + n > NSLOT) { need += NSLOT - head; base = 0; }      // no wrap inside a chunk: the tail slots ride along as padding
+                while (free_slots < need || inflight == NE) {                  // retire the oldest chunk(s)
+                    mbar_wait_a(empty0 + 8u * tj, tpar);
+                    free_slots += (int)((used >> (4 * tj)) & 15ull);
+                    --inflight;
+                    if (++tj == NE) { tj = 0; tpar ^= 1u; }
+                }
+                free_slots -= need;
+                head = base + n;
+                used = (used & ~(15ull << (4 * ej))) | ((unsigned long long)need << (4 * ej));
+                const uint32_t fbar = full0 + 8u * ej;
                 if (elect_one_sync()) {
                     if (wi & 1) {
                         mbar_expect_tx_a(fbar, 0);
                     } else {
                         mbar_expect_tx_a(fbar, n * (OM + ON) * OKB);
-                        tma_load_3d_u8_a(sA, &mapsA.m[n - 1], c * OKB, rt * OM, za, fbar);
-                        tma_load_3d_u8_a(sB, &mapsB.m[n - 1], c * OKB, ti * ON, zb, fbar);
+                        tma_load_3d_u8_a(smemA + base * C::SLOT_A, &mapsA.m[n - 1], c * OKB, rt * OM, za, fbar);
+                        tma_load_3d_u8_a(smemB + base * C::SLOT_B, &mapsB.m[n - 1], c * OKB, ti * ON, zb, fbar);
                     }
                 }
-                empty_par ^= 1u << st;
-                st = (st + 1 == NST) ? 0 : st + 1;
+                ++inflight;
+                if (++ej == NE) ej = 0;
             }
         }
-    } else if (SKIP && warp >= 1 && warp <= NST) {
-        // ---------------- MMA issue: NST warps, warp w owns ring stage w-1 (converged warps, one elected lane issues) ----------------
-        // Measured (tools/whatif.py, profiles/r02_whatif_*.log): with ONE issuing warp the launch time was the SUM of the control path
+    } else if (SKIP && warp >= 1 && warp <= 3) {
+        // ---------------- MMA issue: three warps, chunk entry e belongs to warp 1 + e % 3 (converged warps, one elected lane issues) ----
+        // Measured (tools/whatif.py, profiles/r02_whatif_a_*.log): with ONE issuing warp the launch time was the SUM of the control path
         // (barrier wait, mask decode, descriptor arithmetic, indexed branch: ~670 cycles per chunk) and the MMA time -- the tensor
         // pipe's instruction queue is shallow, the issuing warp blocks in UTCIMMA until earlier MMAs have drained, and its next
-        // control path then runs with the pipe idle.  Executed chunk e uses stage e % NST, so giving every stage its own issuing
-        // warp puts the control path of chunks e+1, e+2 under the MMAs of chunk e; every warp sees every phase of its own
-        // full/empty barriers, no phase is skipped.  int32 accumulation is exact, so the order in which the warps' MMAs reach the
-        // pipe does not matter -- except that the chunk-0 products (accumulate = 0) must be issued first: the stage owner of a
-        // tile's first chunk signals tile_go after issuing them, the others wait for it before their first issue of the tile.
+        // control path then runs with the pipe idle.  With three issuing warps the control path of chunks e+1, e+2 runs under the
+        // MMAs of chunk e.  NE is a multiple of 3, so barrier j always belongs to warp 1 + j % 3 and every warp sees every phase of
+        // its own barriers.  int32 accumulation is exact, so the order in which the warps' MMAs reach the pipe does not matter --
+        // except that the chunk-0 products (accumulate = 0) must be issued first: the owner of a tile's first chunk signals tile_go
+        // after issuing them, the others wait for it before their first issue of the tile.
         // instruction descriptor: D = S32, A = B = INT8, both K-major, M = 128
+        constexpr int NE = C::NE, NSLOT = C::NSLOT;
         const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OM >> 4) << 24);   // N is or-ed in per MMA
-        const int my = warp - 1;                             // the ring stage this warp owns
-        int st = 0;                                          // ring position of the next executed chunk (all issuing warps count alike)
-        unsigned my_par = 0u;                                // parity to wait for on full[my]
-        const uint32_t full_my = pinned_uniform_addr(&full[my]), empty_my = pinned_uniform_addr(&empty[my]);
-        const uint32_t sA = pinned_uniform_addr(smem + my * C::STAGE_BYTES), sB = sA + S * OM * OKB;
-        const uint64_t adesc0 = smem_desc_sw64_a(sA), bdesc0 = smem_desc_sw64_a(sB);
+        const int my = warp - 1;
+        int head = 0, ej = 0, e3 = 0;                        // the producer's allocation replayed: next slot, barrier index, e % 3
+        unsigned epar = 0u;                                  // parity of full[ej] for the current lap of the barrier ring
+        const uint32_t full0 = pinned_uniform_addr(&full[0]), empty0 = pinned_uniform_addr(&empty[0]);
+        const uint32_t smemA = pinned_uniform_addr(smem), smemB = smemA + NSLOT * C::SLOT_A;
+        const uint64_t adescA = smem_desc_sw64_a(smemA), bdescB = smem_desc_sw64_a(smemB);
         const uint32_t accf = pinned_uniform_addr(&acc_full), tgo = pinned_uniform_addr(&tile_go);
         for (int lt = 0;; ++lt) {
             mbar_wait(&slot_full[lt & 1], (lt >> 1) & 1);
@@ -525,8 +553,7 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                 mbar_wait(&acc_empty, (lt - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             }
-            const bool leader = (st == my);                  // chunk 0 of this tile lands on my stage
-            bool go_seen = leader;
+            bool go_seen = (e3 == my);                       // chunk 0 of this tile is mine: I open the tile
             // spatial mode: per (row tile, chunk) / (factor-row tile, chunk) masks of the non-zero digit planes.  Leading zero
             // planes (small values: far-away training points, far-off-diagonal entries of L^-1) are neither loaded nor
             // multiplied -- exact, the skipped products are sums of zeros.
@@ -536,16 +563,19 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
             for (int c = 0; c <= ti; ++c) {
                 int za, zb;
                 zr.template get<S>(c, za, zb);
-                if (S - za - zb <= 0) continue;
-                const bool mine = (st == my);
-                st = (st + 1 == NST) ? 0 : st + 1;
+                const int n = S - za - zb;
+                if (n <= 0) continue;
+                const int base = (head + n > NSLOT) ? 0 : head;
+                head = base + n;
+                const bool mine = (e3 == my);
+                const uint32_t fbar = full0 + 8u * ej, ebar = empty0 + 8u * ej;
+                const unsigned par = epar;
+                if (++e3 == 3) e3 = 0;
+                if (++ej == NE) { ej = 0; epar ^= 1u; }
                 if (!mine) continue;
-                {
-                    const int n = (c == 0) ? S : S - za - zb;
-                    npairs += (unsigned)(n * (n + 1) / 2);
-                }
-                mbar_wait_a(full_my, my_par);
-                my_par ^= 1u;
+                npairs += (unsigned)(n * (n + 1) / 2);
+                const uint64_t adesc0 = adescA + (uint64_t)((base * C::SLOT_A) >> 4), bdesc0 = bdescB + (uint64_t)((base * C::SLOT_B) >> 4);
+                mbar_wait_a(fbar, par);
                 if (!go_seen) {
                     mbar_wait_a(tgo, (unsigned)(lt & 1));
                     go_seen = true;
@@ -556,13 +586,13 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                         if (c == 0) oz_issue_chunk<S, 0, 0>(adesc0, bdesc0, tmem_base, idesc_base, 1u);   // zero-initialises every column
                         else oz_dispatch<S>(za, zb, adesc0, bdesc0, tmem_base, idesc_base);
                     }
-                    umma_commit_a(empty_my);                // the stage is free once these MMAs have read it
+                    umma_commit_a(ebar);                    // the slots are free once these MMAs have read them
                     if (c == 0) mbar_arrive_a(tgo);         // the zero-initialising products are in the pipe: the other warps may issue
                 }
             }
             if (!go_seen) mbar_wait_a(tgo, (unsigned)(lt & 1));     // keep this warp's phase count of tile_go in step
             if (elect_one_sync()) {
-                umma_commit_a(accf);                         // acc_full completes when all NST warps' products of the tile are done
+                umma_commit_a(accf);                         // acc_full completes when all three warps' products of the tile are done
                 if (exec_pairs != nullptr && npairs != 0u) atomicAdd(exec_pairs, (unsigned long long)npairs);
             }
         }
