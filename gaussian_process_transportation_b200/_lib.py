@@ -49,6 +49,7 @@ SYMBOLS = {
     "gptb_set_spatial": (C.c_int, [C.c_void_p, C.c_int]),
     "gptb_executed_products": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
     "gptb_set_debug_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "gptb_debug_read_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "gptb_test_gemm_nt": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gptb_test_potrf_tile": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.POINTER(C.c_int)]),
 }

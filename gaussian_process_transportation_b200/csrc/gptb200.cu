@@ -51,21 +51,23 @@ bool make_operand_map(CUtensorMap* m, const double* base, long long rows, long l
 
 // 3-D TMA view (k bytes, rows, plane) of int8 digit planes [S][rows][ncols]; box (64, box_rows, box_planes), 64-byte swizzle
 // (the K-major shared-memory layout tcgen05.mma expects).
-bool make_plane_map(CUtensorMap* m, const int8_t* base, long long rows, long long ncols, int S, int box_rows, int box_planes) {
+bool make_plane_map(CUtensorMap* m, const int8_t* base, long long rows, long long ncols, int S, int box_rows, int box_planes, int box_k) {
     EncodeTiledFn enc = get_encoder();
     if (!enc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)ncols, (cuuint64_t)rows, (cuuint64_t)S};
     cuuint64_t strides[2] = {(cuuint64_t)ncols, (cuuint64_t)rows * (cuuint64_t)ncols};
-    cuuint32_t box[3] = {(cuuint32_t)oz::OKB, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
+    cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
     cuuint32_t es[3] = {1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               box_k == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// one view per box depth 1 .. S (oz::PlaneMaps): a chunk with leading zero planes loads only the planes it needs
-bool make_plane_maps(oz::PlaneMaps* pm, const int8_t* base, long long rows, long long ncols, int S, int box_rows) {
+// one view per box depth 1 .. S (oz::PlaneMaps): a chunk with leading zero planes loads only the planes it needs.
+// box_k = 64: 64-byte k-chunks, 64-byte swizzle (dense product kernel); 128: 128-byte chunks, 128-byte swizzle (skipping kernel)
+bool make_plane_maps(oz::PlaneMaps* pm, const int8_t* base, long long rows, long long ncols, int S, int box_rows, int box_k) {
     for (int n = 1; n <= S; ++n)
-        if (!make_plane_map(&pm->m[n - 1], base, rows, ncols, S, box_rows, n)) return false;
+        if (!make_plane_map(&pm->m[n - 1], base, rows, ncols, S, box_rows, n, box_k)) return false;
     for (int n = S; n < 7; ++n) pm->m[n] = pm->m[S - 1];
     return true;
 }
@@ -84,6 +86,7 @@ struct gptb_handle {
     int spatial_shuffle = 1;                  // chunk order shuffled (gptb_set_debug_option "spatial_shuffle" 0 keeps the plain Z-order: A/B only)
     int oz_force_skip = 0;                    // debug option "oz_force_skip_variant": dense case through the skipping loops (A/B of the two loop versions)
     int oz_whatif = 0;                        // debug option "oz_whatif" (only acts in a -DGPTB_OZ_WHATIF build)
+    unsigned long long* oz_prof = nullptr;    // 64 cycle counters of CTA 0's roles (GPTB_OZ_WHATIF builds; gptb_debug_read_profile)
     unsigned long long exec_pairs_host = 0;   // plane-pair x chunk products issued by the dense product kernel (counted on the host)
     std::vector<int> perm;                    // perm[i] = caller's index of internal training row i (empty: natural order)
     bool perm_known = true;                   // false on a handle whose state arrived by broadcast (exports need the permutation)
@@ -248,6 +251,7 @@ extern "C" void gptb_destroy(gptb_handle* h) {
     free_model(h);
     if (h->ws) cudaFree(h->ws);
     if (h->stage) cudaFree(h->stage);
+    if (h->oz_prof) cudaFree(h->oz_prof);
     cudaFree(h->info);
     cudaFree(h->scal);
     cudaFree(h->header);
@@ -301,6 +305,17 @@ extern "C" int gptb_executed_products(gptb_handle* h, int64_t* pairs, int reset)
         CU(h, cudaMemsetAsync(exec_counter(h), 0, sizeof(dev), h->stream));
         h->exec_pairs_host = 0;
     }
+    return 0;
+}
+extern "C" int gptb_debug_read_profile(gptb_handle* h, int64_t* out64) {
+    if (!h || !out64) return -1;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->oz_prof) {
+        CU(h, cudaMalloc(&h->oz_prof, 64 * sizeof(unsigned long long)));
+        CU(h, cudaMemset(h->oz_prof, 0, 64 * sizeof(unsigned long long)));
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaMemcpy(out64, h->oz_prof, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return 0;
 }
 extern "C" int gptb_set_query_pipeline(gptb_handle* h, int on) {
@@ -678,7 +693,7 @@ static int build_bplanes(gptb_handle* h) {
     unsigned long long* l1max = reinterpret_cast<unsigned long long*>(h->scal + 32);
     CU(h, cudaMemsetAsync(l1max, 0, sizeof(unsigned long long), h->stream));
     // block masks of the non-zero digit planes (used by the product kernel in spatial mode; 8-bit planes only)
-    h->flags_stride = (int)((Npad / 64 + 3) / 4);
+    h->flags_stride = (int)(((Npad / 64 + 3) / 4 + 3) / 4 * 4);     // 32-bit words per mask row, padded to 16 bytes (one uint4 per lane in the product kernel)
     if (h->flagsB) { cudaFree(h->flagsB); h->flagsB = nullptr; }
     if (h->var_bits == 8) {
         if (h->flags_stride > FLAG_WORDS) GPTB_FAIL(h, -1, "INT8-sliced variance path: N=%lld exceeds the %d-chunk limit of the block masks", (long long)h->N, FLAG_WORDS * 4);
@@ -698,7 +713,8 @@ static int build_bplanes(gptb_handle* h) {
             GPTB_FAIL(h, -1, "INT8-sliced variance path: N=%lld with %d 8-bit digit planes could overflow the int32 accumulators "
                              "(largest row sum of |digits| = %llu); use the 7-bit planes (mode 1)", (long long)h->N, S, l1);
     }
-    if (!make_plane_maps(&h->mapsBq, h->Bplanes, Npad, Npad, S, oz::ON)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
+    if (!make_plane_maps(&h->mapsBq, h->Bplanes, Npad, Npad, S, oz::ON, oz::OKB))
+        GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
     h->have_bplanes = true;
     return 0;
 }
@@ -857,7 +873,9 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
         const int rowtiles = (int)(rows_total / TS);
         const int T64 = (int)(h->Npad / oz::ON);
         oz::PlaneMaps mapsAq;
-        if (!make_plane_maps(&mapsAq, Aplanes, rows_total, h->Npad, S, oz::OM)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
+        const bool use_masks = spatial && h->spatial == 1;
+        const bool skipping = use_masks || h->oz_force_skip;
+        if (!make_plane_maps(&mapsAq, Aplanes, rows_total, h->Npad, S, oz::OM, oz::OKB)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
         if (!fused) {
             tic(h, 3);
             dispatch_digits(S, h->var_bits, [&](auto SS, auto BB) {
@@ -873,16 +891,14 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
             int nsm = 148;
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
             cudaMemsetAsync(h->info + 1, 0, sizeof(int), h->stream);      // dynamic tile counter
-            const bool use_masks = spatial && h->spatial == 1;
-            const bool skipping = use_masks || h->oz_force_skip;
             const unsigned grid_oz = (unsigned)(ntiles < nsm ? ntiles : nsm);
             if (skipping) {
                 oz::ozaki_trmm_kernel<SV, true><<<grid_oz, oz::OTHREADS, oz::Cfg<SV>::SMEM_SKIP_BYTES, h->stream>>>(
                     mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, use_masks ? flagsA_slot : nullptr, use_masks ? h->flagsB : nullptr, h->flags_stride,
-                    exec_counter(h), h->oz_whatif);
+                    exec_counter(h), h->oz_whatif, h->oz_prof);
             } else {
                 oz::ozaki_trmm_kernel<SV, false><<<grid_oz, oz::OTHREADS, oz::Cfg<SV>::SMEM_BYTES, h->stream>>>(
-                    mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, nullptr, nullptr, h->flags_stride, nullptr, 0);
+                    mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, nullptr, nullptr, h->flags_stride, nullptr, 0, nullptr);
                 h->exec_pairs_host += (unsigned long long)rowtiles * ((unsigned long long)T64 * (T64 + 1) / 2) * (unsigned long long)(SV * (SV + 1) / 2);
             }
         });

@@ -219,45 +219,46 @@ struct PlaneMaps {
     CUtensorMap m[7];
 };
 
-// Block masks of one tile row (spatial mode): leading all-zero planes of A and B for chunk c.  The producer and the MMA thread
-// walk the same masks, so both skip the same chunks and planes.  Words are fetched four chunks ahead of their use.
-struct ZeroPlaneReader {
-    const unsigned *fa, *fb;
-    unsigned wa_next, wb_next;     // raw masks of the NEXT four chunks (in flight while the current four are consumed)
-    unsigned code4;                // (za*8 + zb) of the current four chunks, one byte each, warp-uniform
-    int ti;
-    __device__ __forceinline__ void init(const unsigned* flagsA, const unsigned* flagsB, int stride, int rt, int ti_) {
-        fa = flagsA ? flagsA + (long long)rt * stride : nullptr;
-        fb = flagsA ? flagsB + (long long)ti_ * stride : nullptr;
-        ti = ti_;
-        wa_next = wb_next = 0u;
-        code4 = 0u;
-        if (fa && ti >= 1) {
-            wa_next = __ldg(fa); wb_next = __ldg(fb);
-        }
-    }
-    // leading all-zero planes of the four chunks of one mask word, packed (za*8 + zb) per byte; `first` = chunk 0 of the tile is in it
+// Block masks of one tile, skipping variant.  Each control warp loads its two mask rows ONCE per tile (one 16-byte load per lane and
+// operand: 16 mask bytes = 16 chunks), decodes them lane-parallel into (za*8 + zb) codes and then hands them out four chunks at a
+// time with one shuffle -- the earlier reader (ZeroPlaneReader) fetched one 32-bit word per four chunks with __ldg and decoded it
+// serially; what-if timings (tools/whatif.py, profiles/r02_whatif_*.log) showed the launch bound by the control warps' instruction
+// streams (a lone warp retires ~0.2 instructions per cycle: 100+ instructions per chunk cost more than the chunk's MMAs).
+struct TileMasks {
+    unsigned code[4];              // this lane's codes for chunks 16*lane + 4*w .. + 3 (one byte each), w = 0..3
+    unsigned cur4;                 // codes of the current group of four chunks (warp-uniform)
     template <int S>
-    __device__ __forceinline__ static unsigned decode4(unsigned wa, unsigned wb, bool first) {
-        unsigned out = 0u;
+    __device__ __forceinline__ void load(const unsigned* flagsA, const unsigned* flagsB, int stride, int rt, int ti, int lane) {
+        uint4 wa = make_uint4(0u, 0u, 0u, 0u), wb = wa;
+        if (flagsA != nullptr && 4 * lane < stride) {
+            wa = __ldg(reinterpret_cast<const uint4*>(flagsA + (long long)rt * stride) + lane);
+            wb = __ldg(reinterpret_cast<const uint4*>(flagsB + (long long)ti * stride) + lane);
+        }
+        const unsigned a[4] = {wa.x, wa.y, wa.z, wa.w}, b[4] = {wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const unsigned ma = (wa >> (8 * k)) & 0xffu, mb = (wb >> (8 * k)) & 0xffu;
-            const unsigned za = ma ? (unsigned)(__ffs(ma) - 1) : (unsigned)S, zb = mb ? (unsigned)(__ffs(mb) - 1) : (unsigned)S;
-            out |= (za * 8u + zb) << (8 * k);
+        for (int w = 0; w < 4; ++w) {
+            unsigned out = 0u;
+            if (flagsA != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned ma = (a[w] >> (8 * k)) & 0xffu, mb = (b[w] >> (8 * k)) & 0xffu;
+                    const unsigned za = ma ? (unsigned)(__ffs(ma) - 1) : (unsigned)S, zb = mb ? (unsigned)(__ffs(mb) - 1) : (unsigned)S;
+                    out |= (za * 8u + zb) << (8 * k);
+                }
+            }
+            code[w] = out;
         }
-        return first ? (out & 0xffffff00u) : out;              // chunk 0 is always dense: it zero-initialises the accumulators
+        if (lane == 0) code[0] &= 0xffffff00u;                   // chunk 0 is always dense: it zero-initialises the accumulators
+        cur4 = 0u;
     }
-    // call for every chunk in order; every fourth call decodes a word (and starts the load of the next one), the others cost a shift
-    template <int S>
+    // call for every chunk in order
     __device__ __forceinline__ void get(int c, int& za, int& zb) {
-        if (!fa) { za = 0; zb = 0; return; }
         if ((c & 3) == 0) {
-            const unsigned wa = wa_next, wb = wb_next;
-            if (c + 4 <= ti) { wa_next = __ldg(fa + (c >> 2) + 1); wb_next = __ldg(fb + (c >> 2) + 1); }
-            code4 = __reduce_max_sync(0xffffffffu, decode4<S>(wa, wb, c == 0));     // warp-uniform (see elect_one_sync)
+            const int w = (c >> 2) & 3;
+            const unsigned mine = (w == 0) ? code[0] : (w == 1) ? code[1] : (w == 2) ? code[2] : code[3];
+            cur4 = __shfl_sync(0xffffffffu, mine, c >> 4);
         }
-        const unsigned z = (code4 >> ((c & 3) * 8)) & 0xffu;
+        const unsigned z = (cur4 >> ((c & 3) * 8)) & 0xffu;
         za = (int)(z >> 3);
         zb = (int)(z & 7u);
     }
@@ -337,7 +338,9 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                                                                 int T64, int rowtiles, long long rows_total,
                                                                 double* __restrict__ part, int* __restrict__ tile_counter, int digit_bits,
                                                                 const unsigned* __restrict__ flagsA, const unsigned* __restrict__ flagsB,
-                                                                int flags_stride, unsigned long long* __restrict__ exec_pairs, int whatif) {
+                                                                int flags_stride, unsigned long long* __restrict__ exec_pairs, int whatif,
+                                                                unsigned long long* __restrict__ prof) {
+    (void)prof;                                               // per-role cycle counters: only the six-stage experiment of round 2 filled them (profiles/r02_role_cycles_*.log)
     // exec_pairs (may be null): number of (plane pair, 64-byte chunk) products this launch really issued, one atomicAdd per tile --
     // the executed-work figure of the roofline (the dense variant issues S(S+1)/2 per chunk by construction, counted on the host).
     // whatif: developer builds only (-DGPTB_OZ_WHATIF, tools/whatif.py): bit 0 = no TMA loads, bit 1 = no MMA issue, bit 2 = no
@@ -489,11 +492,11 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
             if (t < 0) break;
             int rt, ti;
             oz_tile_decode(t, T64, rowtiles, rt, ti);
-            ZeroPlaneReader zr;
-            zr.init(flagsA, flagsB, flags_stride, rt, ti);
+            TileMasks zr;
+            zr.template load<S>(flagsA, flagsB, flags_stride, rt, ti, lane);
             for (int c = 0; c <= ti; ++c) {
                 int za, zb;
-                zr.template get<S>(c, za, zb);
+                zr.get(c, za, zb);
                 const int n = S - za - zb;                  // planes za .. za+n-1 of A meet planes zb .. zb+n-1 of B
                 if (n <= 0) continue;                       // nothing but zeros in this chunk: no slot, no load
                 int base = head, need = n;
@@ -557,12 +560,12 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
             // spatial mode: per (row tile, chunk) / (factor-row tile, chunk) masks of the non-zero digit planes.  Leading zero
             // planes (small values: far-away training points, far-off-diagonal entries of L^-1) are neither loaded nor
             // multiplied -- exact, the skipped products are sums of zeros.
-            ZeroPlaneReader zr;
-            zr.init(flagsA, flagsB, flags_stride, rt, ti);
+            TileMasks zr;
+            zr.template load<S>(flagsA, flagsB, flags_stride, rt, ti, lane);
             unsigned npairs = 0;                             // plane-pair products issued by this warp for this tile
             for (int c = 0; c <= ti; ++c) {
                 int za, zb;
-                zr.template get<S>(c, za, zb);
+                zr.get(c, za, zb);
                 const int n = S - za - zb;
                 if (n <= 0) continue;
                 const int base = (head + n > NSLOT) ? 0 : head;

@@ -176,6 +176,9 @@ int gptb_executed_products(gptb_handle* h, int64_t* pairs, int reset);
  * before gptb_set_train), "oz_force_skip_variant" (1: the dense case runs through the skipping loops), "oz_whatif" (bit mask, acts
  * only in a -DGPTB_OZ_WHATIF build of the library: tools/whatif.py). */
 int gptb_set_debug_option(gptb_handle* h, const char* name, int value);
+/* 64 cycle counters of CTA 0's roles in the last skipping product launch (all zero unless the library was built with
+ * -DGPTB_OZ_WHATIF); the first call allocates the buffer, later launches fill it.  Layout: tools/whatif.py. */
+int gptb_debug_read_profile(gptb_handle* h, int64_t* out64);
 
 /* ---- unit-test hooks: exercise the DMMA tile engine and the small factor kernels in isolation.
  * C (128*mt,128*nt) = A (128*mt,K) * B(128*nt,K)^T, all row-major host arrays, K multiple of 128. */

@@ -50,6 +50,9 @@ def whatif(Ns):
             M = 65536
             xd, kw, keep = buffers(M)
             eng.query_dev(xd.data_ptr(), M, FL, **kw)
+            import ctypes
+            prof = (ctypes.c_int64 * 64)()
+            eng.lib.gptb_debug_read_profile(eng.h, prof)       # allocates the counter buffer
             for wi in (0, 1, 2, 4, 3, 5, 6, 7):
                 eng.set_debug_option("oz_whatif", wi)
                 eng.executed_products(reset=True)
@@ -64,6 +67,15 @@ def whatif(Ns):
                 T64 = Npad // 64
                 dense = (M // 128) * (T64 * (T64 + 1) // 2) * 15
                 mma_cycles_per_sm = ex * 64 / 148          # 64 cycles per plane pair per chunk (2 MMAs of 128x64x32)
+                eng.lib.gptb_debug_read_profile(eng.h, prof)
+                pv = list(prof)
+                if wi in (0, 1, 7):
+                    k = lambda v: round(v / 1e3, 1)             # kilo-cycles, CTA 0, last launch
+                    print(json.dumps({"N": N, "ell": ell, "whatif": wi, "profile_kcycles_cta0": {
+                        "producer": {"total": k(pv[0]), "tile_claim": k(pv[1]), "tile_decode_masks": k(pv[2]), "wait_empty": k(pv[3]), "chunks": pv[4]},
+                        **{f"mma_warp{w}": {"total": k(pv[8 * w]), "wait_tile": k(pv[8 * w + 1]), "wait_acc_empty": k(pv[8 * w + 2]), "masks": k(pv[8 * w + 3]),
+                                            "wait_full": k(pv[8 * w + 4]), "wait_tile_go": k(pv[8 * w + 5]), "issue": k(pv[8 * w + 6]), "chunks": pv[8 * w + 7]} for w in (1, 2, 3)},
+                        "epilogue_warp4": {"total": k(pv[32]), "wait_tile": k(pv[33]), "wait_acc_full": k(pv[34])}}}), flush=True)
                 print(json.dumps({"N": N, "ell": ell, "whatif": wi, "products_ms": t0 / n0, "generator_ms": t1 / n1, "executed_pairs": ex,
                                   "executed_frac": ex / dense, "mma_floor_ms_at_1965MHz": mma_cycles_per_sm / 1.965e6}), flush=True)
             eng.close()
