@@ -26,6 +26,8 @@ SYMBOLS = {
     "gptb_lml": (C.c_int, [C.c_void_p, C.c_double, _dp, C.c_double, C.c_double, C.c_int, _dp, _dp]),
     "gptb_set_variance_mode": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "gptb_prepare_variance": (C.c_int, [C.c_void_p]),
+    "gptb_set_variance_guard": (C.c_int, [C.c_void_p, C.c_double]),
+    "gptb_variance_guard_report": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), _dp, _dp, _dp]),
     "gptb_set_affine": (C.c_int, [C.c_void_p, _dp, C.c_double, _dp, _dp]),
     "gptb_query": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_uint32, _dp] + [_dp] * 9),
     "gptb_query_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p] + [C.c_void_p] * 9),
@@ -181,6 +183,18 @@ class Engine:
         if isinstance(mode, str):
             mode, slices = parse_variance_mode(mode)
         self._check(self.lib.gptb_set_variance_mode(self.h, int(mode), int(slices)), "gptb_set_variance_mode")
+
+    def set_variance_guard(self, threshold):
+        """Probe threshold of the INT8-sliced path's run-time accuracy guard (relative to sqrt(c + s2); default 2e-8, 0 = off)."""
+        self._check(self.lib.gptb_set_variance_guard(self.h, float(threshold)), "gptb_set_variance_guard")
+
+    def variance_guard(self):
+        """What the guard decided for the current model: requested / used digit planes (0 = FP64 path), probe errors, threshold."""
+        rq, us = C.c_int(0), C.c_int(0)
+        e1, e0, th = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0)
+        self._check(self.lib.gptb_variance_guard_report(self.h, C.byref(rq), C.byref(us), C.byref(e1), C.byref(e0), C.byref(th)),
+                    "gptb_variance_guard_report")
+        return {"requested_slices": rq.value, "used_slices": us.value, "probe_err": e1.value, "first_err": e0.value, "threshold": th.value}
 
     def prepare_variance(self):
         self._check(self.lib.gptb_prepare_variance(self.h), "gptb_prepare_variance")

@@ -107,6 +107,12 @@ struct gptb_handle {
     CUtensorMap mapL64;                      // Lbuf with a 64-row box (half-tile trailing update)
     // INT8-sliced variance path (ozaki.cuh): digit planes of the inverse factor + per-row scales
     int var_mode = 0, var_slices = 6, var_bits = 7;   // var_mode 1 = INT8-sliced; var_bits = digit width (7 balanced | 8 full range)
+    // run-time accuracy guard of the INT8-sliced path (gptb_set_variance_guard): what the caller asked for, what the probe decided
+    int var_mode_req = 0, var_slices_req = 6;
+    double guard_thresh = 2.0e-8;             // max |std_int8 - std_fp64| / sqrt(c + s2) on the probe set (a fifth of the 1e-7 tolerance); 0 = off
+    bool guard_done = false, guard_busy = false;
+    double guard_first_err = -1.0, guard_err = -1.0;
+    double* probe = nullptr;                  // probe points + the two std vectors + the reduced error
     int trailing_variant = 1;                // 0: 128x128 tiles, one CTA/SM; 1: 128x64 half tiles, two CTAs/SM
     int8_t* Bplanes = nullptr;
     double* scaleB = nullptr;
@@ -119,9 +125,16 @@ struct gptb_handle {
     double* ws = nullptr;
     size_t ws_bytes = 0;
     long long ws_limit = 16LL << 30;
-    // staging for the host-pointer query
-    double* stage = nullptr;
+    // staging for the host-pointer query: two device buffer sets, slices of HOST_SLICE queries; H2D of slice i+1 (s_h2d) and D2H of
+    // slice i-1 (s_d2h) run under the kernels of slice i (main stream)
+    double* stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    // scratch of the small epilogue entry points (joint covariance, orientation, stiffness): one buffer carved per call, kept
+    // across calls up to SCRATCH_KEEP bytes
+    char* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cd[2] = {nullptr, nullptr}, ev_oc[2] = {nullptr, nullptr};
     long long launches = 0;
     bool timing = false;
     std::vector<EvPair> ev[4];
@@ -181,6 +194,14 @@ static void free_model(gptb_handle* h) {
     h->have_train = h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = h->have_bplanes = false;
 }
 
+// a new model (refit, new hyper-parameters, received state): digit planes are stale, the guard starts again from the requested mode
+static void invalidate_planes(gptb_handle* h) {
+    h->have_bplanes = false;
+    h->guard_done = false;
+    h->var_mode = h->var_mode_req;
+    h->var_slices = h->var_slices_req;
+}
+
 static int set_kernel_attrs(gptb_handle* h) {
     CU(h, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -228,6 +249,10 @@ extern "C" int gptb_create(int device, gptb_handle** out) {
         if (cudaEventCreateWithFlags(&h->ev_gen[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return -2; }
     if (cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming) != cudaSuccess) { delete h; return -2; }
+    if (cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) != cudaSuccess) { delete h; return -2; }
+    for (int i = 0; i < 2; ++i)
+        if (cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_cd[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_oc[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return -2; }
     if (cudaMalloc(&h->info, 4 * sizeof(int)) != cudaSuccess || cudaMalloc(&h->scal, 64 * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->header, 32 * sizeof(double)) != cudaSuccess) {
         delete h;
@@ -250,8 +275,15 @@ extern "C" void gptb_destroy(gptb_handle* h) {
     cudaStreamSynchronize(h->stream);
     free_model(h);
     if (h->ws) cudaFree(h->ws);
-    if (h->stage) cudaFree(h->stage);
+    for (int i = 0; i < 2; ++i) {
+        if (h->stage[i]) cudaFree(h->stage[i]);
+        cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_cd[i]); cudaEventDestroy(h->ev_oc[i]);
+    }
+    cudaStreamSynchronize(h->s_h2d); cudaStreamSynchronize(h->s_d2h);
+    cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_d2h);
     if (h->oz_prof) cudaFree(h->oz_prof);
+    if (h->scratch) cudaFree(h->scratch);
+    if (h->probe) cudaFree(h->probe);
     cudaFree(h->info);
     cudaFree(h->scal);
     cudaFree(h->header);
@@ -375,7 +407,8 @@ static int alloc_model(gptb_handle* h, long long N, int d, int p, bool train) {
         }
     }
     h->N = N;
-    h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = h->have_bplanes = false;
+    h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = false;
+    invalidate_planes(h);
     return 0;
 }
 
@@ -385,16 +418,16 @@ extern "C" int gptb_set_variance_mode(gptb_handle* h, int mode, int slices) {
     if (mode == 1 && (slices < 5 || slices > 7)) GPTB_FAIL(h, -1, "the INT8-sliced variance path supports 5, 6 or 7 seven-bit digit planes (got %d)", slices);
     if (mode == 2 && (slices < 4 || slices > 6)) GPTB_FAIL(h, -1, "the INT8-sliced variance path supports 4, 5 or 6 eight-bit digit planes (got %d)", slices);
     const int bits = (mode == 2) ? 8 : 7;
-    if (mode >= 1 && (slices != h->var_slices || bits != h->var_bits)) h->have_bplanes = false;
-    h->var_mode = mode >= 1 ? 1 : 0;
-    if (mode >= 1) { h->var_slices = slices; h->var_bits = bits; }
+    h->var_mode_req = mode >= 1 ? 1 : 0;
+    if (mode >= 1) { h->var_slices_req = slices; h->var_bits = bits; }
+    if (h->var_mode_req != h->var_mode || (mode >= 1 && (slices != h->var_slices || bits != h->var_bits)) || mode == 0) invalidate_planes(h);
     return 0;
 }
 
 extern "C" int gptb_set_kernel_kind(gptb_handle* h, int kind) {
     if (!h) return -1;
     if (kind < 0 || kind > 3) GPTB_FAIL(h, -1, "unknown kernel kind %d", kind);
-    if (kind != h->kp.kind) h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = false;
+    if (kind != h->kp.kind) { h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = false; invalidate_planes(h); }
     h->kp.kind = kind;
     return 0;
 }
@@ -604,7 +637,8 @@ extern "C" int gptb_factorize(gptb_handle* h, double c, const double* ell, doubl
     CU(h, cudaSetDevice(h->device));
     int rc = set_params(h, c, ell, s2, jitter);
     if (rc) return rc;
-    h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = h->have_bplanes = false;
+    h->have_factor = h->have_alpha = h->have_minv = h->have_kinv = false;
+    invalidate_planes(h);
     if ((rc = factorize_device(h))) return rc;
     if ((rc = solve_alpha(h))) return rc;
     h->have_factor = h->have_alpha = true;
@@ -730,11 +764,125 @@ static int build_kinv(gptb_handle* h) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Run-time accuracy guard of the INT8-sliced variance path.  The digit scales are a-priori bounds (k* <= c, |dk*/dx| <= c/ell,
+// row maxima of L^-1), so how many of the S x 8 bits are significant depends on the data: strongly correlated models (large c/s2,
+// long length-scales, a Z-ordered factor) lose bits exactly where the variance nearly cancels.  Instead of trusting a fixed S, the
+// engine measures: PROBE_N probe queries -- half of them a hair next to training points (where the std is most sensitive), half within
+// a few length-scales of them -- are evaluated on the INT8 path and on the FP64 DMMA path of the same handle.  If the std differs by
+// more than guard_thresh (default 2e-8 = a fifth of the 1e-7 tolerance, relative to sqrt(c + s2)) one more digit plane is
+// added and the probe repeated; when the plane count is exhausted the handle falls back to the FP64 path for this model.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PROBE_N = 2048;
+
+__global__ void probe_points_kernel(const double* __restrict__ X, int N, int Npad, int d, KParams kp, double* __restrict__ xq) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= PROBE_N) return;
+    const int n = (int)(((long long)q * N) / PROBE_N);                  // evenly spread over the (possibly Morton-ordered) training set
+    unsigned long long st = 0x9E3779B97F4A7C15ULL * (unsigned long long)(q + 1);
+    for (int a = 0; a < d; ++a) {
+        st += 0x9E3779B97F4A7C15ULL;
+        unsigned long long z = st;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        z ^= z >> 31;
+        const double u = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;     // [-1, 1)
+        const double reach = (q & 1) ? ((q & 2) ? 1e-2 : 1e-3) : ((q & 2) ? 3.0 : 0.5);    // in length-scales: next to the point (x2) | nearby | around it
+        xq[(long long)q * d + a] = X[(long long)a * Npad + n] + reach * kp.ell[a] * u;
+    }
+}
+
+__global__ void probe_error_kernel(const double* __restrict__ a, const double* __restrict__ b, int n, int stride, double* __restrict__ out) {
+    __shared__ double red[256];
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double e = fabs(a[(long long)i * stride] - b[(long long)i * stride]);
+        m = (e == e) ? fmax(m, e) : 1e300;                                          // a NaN on either path counts as a failure
+    }
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + w]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
+}
+
+static int build_bplanes(gptb_handle* h);
+
+static int run_variance_guard(gptb_handle* h) {
+    if (h->guard_done || h->guard_busy || h->var_mode != 1) return 0;
+    if (!(h->guard_thresh > 0.0)) { h->guard_done = true; h->guard_first_err = h->guard_err = -1.0; return 0; }
+    const int d = h->d, p = h->p;
+    if (!h->probe) CU(h, cudaMalloc(&h->probe, sizeof(double) * ((size_t)PROBE_N * (d + 2 * p) + 8)));
+    double* xq = h->probe;
+    double* s8 = xq + (size_t)PROBE_N * d;
+    double* s64 = s8 + (size_t)PROBE_N * p;
+    double* err_dev = s64 + (size_t)PROBE_N * p;
+    h->guard_busy = true;
+    h->guard_first_err = -1.0;
+    int rc = 0;
+    probe_points_kernel<<<(PROBE_N + 255) / 256, 256, 0, h->stream>>>(h->X, (int)h->N, (int)h->Npad, d, h->kp, xq);
+    h->launches++;
+    bool have64 = false;
+    for (;;) {
+        if ((rc = gptb_query_dev(h, xq, PROBE_N, GPTB_STD, nullptr, nullptr, s8, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr))) break;
+        if (!have64) {
+            h->var_mode = 0;
+            rc = gptb_query_dev(h, xq, PROBE_N, GPTB_STD, nullptr, nullptr, s64, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+            h->var_mode = 1;
+            if (rc) break;
+            have64 = true;
+        }
+        probe_error_kernel<<<1, 256, 0, h->stream>>>(s8, s64, PROBE_N, p, err_dev);
+        h->launches++;
+        double err = 0.0;
+        if (cudaMemcpyAsync(&err, err_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = -2; h->err = "CUDA error in the variance guard"; break; }
+        err /= std::sqrt(h->kp.c + h->kp.s2);
+        if (h->guard_first_err < 0.0) h->guard_first_err = err;
+        h->guard_err = err;
+        if (err <= h->guard_thresh) break;
+        const int smax = (h->var_bits == 8) ? 6 : 7;
+        if (h->var_slices < smax) {
+            h->var_slices += 1;                 // one more digit plane per operand (2S+1 more plane products)
+            h->have_bplanes = false;
+            if ((rc = build_bplanes(h))) break;
+            continue;
+        }
+        h->var_mode = 0;                        // plane count exhausted: this model is served by the FP64 DMMA path
+        h->guard_err = 0.0;
+        break;
+    }
+    h->guard_busy = false;
+    h->guard_done = (rc == 0);
+    return rc;
+}
+
+extern "C" int gptb_set_variance_guard(gptb_handle* h, double threshold) {
+    if (!h || !(threshold >= 0.0)) return -1;
+    h->guard_thresh = threshold;
+    invalidate_planes(h);
+    return 0;
+}
+
+extern "C" int gptb_variance_guard_report(gptb_handle* h, int* requested_slices, int* used_slices, double* probe_err, double* first_err,
+                                          double* threshold) {
+    if (!h) return -1;
+    if (requested_slices) *requested_slices = h->var_mode_req ? h->var_slices_req : 0;
+    if (used_slices) *used_slices = h->var_mode ? h->var_slices : 0;
+    if (probe_err) *probe_err = h->guard_done ? h->guard_err : -1.0;
+    if (first_err) *first_err = h->guard_done ? h->guard_first_err : -1.0;
+    if (threshold) *threshold = h->guard_thresh;
+    return 0;
+}
+
 extern "C" int gptb_prepare_variance(gptb_handle* h) {
     if (!h) return -1;
     CU(h, cudaSetDevice(h->device));
     int rc = (h->var_mode == 1) ? build_bplanes(h) : build_minv(h);
     if (rc) return rc;
+    if ((rc = run_variance_guard(h))) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -954,9 +1102,14 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     if (flags & (GPTB_STD | GPTB_DVAR)) { nrhs = 1; genflags |= 1u; }
     if (flags & (GPTB_JACVAR | GPTB_DVAR)) { nrhs = 1 + d; genflags |= 2u; }
     if (flags & GPTB_DVAR) { nrhs = 1 + 2 * d; genflags |= 4u | 1u; }
+    if (nrhs > 0 && h->var_mode == 1) {
+        int rc = build_bplanes(h);
+        if (rc) return rc;
+        if ((rc = run_variance_guard(h))) return rc;       // may add digit planes or switch this model to the FP64 path
+    }
     const bool ozaki = (nrhs > 0 && h->var_mode == 1);
-    if (nrhs > 0) {
-        int rc = ozaki ? build_bplanes(h) : build_minv(h);
+    if (nrhs > 0 && !ozaki) {
+        int rc = build_minv(h);
         if (rc) return rc;
     }
     // batch size: bounded by the workspace for the right-hand-side rows (nrhs * Bpad * Npad doubles / digit bytes)
@@ -1069,12 +1222,21 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     return 0;
 }
 
-// Host-pointer query: staged through device buffers in slices of at most HOST_CHUNK points so that arbitrarily long
-// query streams (BASELINE configs 4/5: 2^26 .. 2^29 points) never need more than ~1 GB of staging.
-static int query_host_chunk(gptb_handle* h, const double* x, int64_t M, uint32_t flags, const double* vel, double* mean, double* std,
-                            double* jac, double* jacvar, double* xhat, double* vhat, double* vvar, double* jphi, double* dvar,
-                            int64_t dvar_ld) {
+// Host-pointer query: staged through two device buffer sets in slices of HOST_SLICE queries, so that arbitrarily long query streams
+// (BASELINE configs 4/5: 2^26 .. 2^29 points) need ~50 MB of staging, and pipelined: the H2D copy of slice i+1 and the D2H copy of
+// slice i-1 run on their own streams under the kernels of slice i.  (Round 1 copied a 4M-point slice in, ran it, copied it out and
+// synchronised: the copies were 3 % of a step on one GPU and the only thing bending the 8-GPU scaling curve, where eight ranks share
+// the host path.)  A call that fits one slice uses the main stream only (no event hops on the latency path of small queries).
+extern "C" int gptb_query(gptb_handle* h, const double* x, int64_t M, uint32_t flags, const double* vel, double* mean, double* std,
+                          double* jac, double* jacvar, double* xhat, double* vhat, double* vvar, double* jphi, double* dvar) {
+    if (!h || M < 0) return -1;
+    if (M == 0) return 0;
+    if (!x) return -1;
+    CU(h, cudaSetDevice(h->device));
     const int d = h->d, p = h->p;
+    if (d < 1) GPTB_FAIL(h, -1, "gptb_query: model is not fitted");
+    if ((flags & GPTB_VELOCITY) && !vel) GPTB_FAIL(h, -1, "GPTB_VELOCITY without vel");
+    const int64_t HOST_SLICE = 1 << 16;
     struct Seg { const double* hin; double* hout; size_t per; size_t off; };
     Seg segs[11] = {{x, nullptr, (size_t)d, 0},
                     {(flags & GPTB_VELOCITY) ? vel : nullptr, nullptr, (size_t)d, 0},
@@ -1087,54 +1249,94 @@ static int query_host_chunk(gptb_handle* h, const double* x, int64_t M, uint32_t
                     {nullptr, ((flags & GPTB_VELOCITY) && (flags & GPTB_JACVAR)) ? vvar : nullptr, (size_t)p, 0},
                     {nullptr, (flags & GPTB_JPHI) ? jphi : nullptr, (size_t)d * d, 0},
                     {nullptr, (flags & GPTB_DVAR) ? dvar : nullptr, (size_t)d, 0}};
+    const int64_t slice = (M < HOST_SLICE) ? M : HOST_SLICE;
+    const int64_t nslices = (M + slice - 1) / slice;
+    const int nsets = nslices > 1 ? 2 : 1;
     size_t tot = 0;
     for (auto& sg : segs) {
         if (sg.hin || sg.hout) {
             sg.off = tot;
-            tot += (sg.per * (size_t)M * sizeof(double) + 255) / 256 * 256;
+            tot += (sg.per * (size_t)slice * sizeof(double) + 255) / 256 * 256;
         }
     }
-    if (tot > h->stage_bytes) {
+    if (tot > h->stage_bytes || (nsets == 2 && !h->stage[1])) {
         CU(h, cudaStreamSynchronize(h->stream));
-        if (h->stage) cudaFree(h->stage);
-        h->stage = nullptr;
+        const size_t want = tot > h->stage_bytes ? tot : h->stage_bytes;
+        for (int i = 0; i < 2; ++i) {
+            if (h->stage[i]) cudaFree(h->stage[i]);
+            h->stage[i] = nullptr;
+        }
         h->stage_bytes = 0;
-        CU(h, cudaMalloc(&h->stage, tot));
-        h->stage_bytes = tot;
+        for (int i = 0; i < nsets; ++i) CU(h, cudaMalloc(&h->stage[i], want));
+        h->stage_bytes = want;
     }
-    char* sb = reinterpret_cast<char*>(h->stage);
-    auto dp = [&](int i) -> double* { return (segs[i].hin || segs[i].hout) ? reinterpret_cast<double*>(sb + segs[i].off) : nullptr; };
-    for (int i = 0; i < 2; ++i)
-        if (segs[i].hin) CU(h, cudaMemcpyAsync(dp(i), segs[i].hin, segs[i].per * M * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    int rc = gptb_query_dev(h, dp(0), M, flags, dp(1), dp(2), dp(3), dp(4), dp(5), dp(6), dp(7), dp(8), dp(9), dp(10));
-    if (rc) return rc;
-    for (int i = 2; i < 10; ++i)
-        if (segs[i].hout) CU(h, cudaMemcpyAsync(segs[i].hout, dp(i), segs[i].per * M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (segs[10].hout)   // dvar is (d, Mtotal): this slice fills columns [0, M) of each row
-        CU(h, cudaMemcpy2DAsync(dvar, sizeof(double) * dvar_ld, dp(10), sizeof(double) * M, sizeof(double) * M, d, cudaMemcpyDeviceToHost, h->stream));
+    auto dp = [&](int set, int i) -> double* {
+        return (segs[i].hin || segs[i].hout) ? reinterpret_cast<double*>(reinterpret_cast<char*>(h->stage[set]) + segs[i].off) : nullptr;
+    };
+    const bool piped = nslices > 1;
+    cudaStream_t sin = piped ? h->s_h2d : h->stream, sout = piped ? h->s_d2h : h->stream;
+    if (piped) {       // the copy streams start behind whatever is already queued on the main stream
+        CU(h, cudaEventRecord(h->ev_start, h->stream));
+        CU(h, cudaStreamWaitEvent(sin, h->ev_start, 0));
+    }
+    for (int64_t is = 0; is < nslices; ++is) {
+        const int64_t q0 = is * slice;
+        const int64_t m = (M - q0 < slice) ? (M - q0) : slice;
+        const int set = piped ? (int)(is & 1) : 0;
+        if (piped && is >= 2) CU(h, cudaStreamWaitEvent(sin, h->ev_cd[set], 0));          // the kernels of slice is-2 have consumed this set's inputs
+        for (int i = 0; i < 2; ++i)
+            if (segs[i].hin) CU(h, cudaMemcpyAsync(dp(set, i), segs[i].hin + (size_t)q0 * segs[i].per, segs[i].per * m * sizeof(double), cudaMemcpyHostToDevice, sin));
+        if (piped) {
+            CU(h, cudaEventRecord(h->ev_in[set], sin));
+            CU(h, cudaStreamWaitEvent(h->stream, h->ev_in[set], 0));
+            if (is >= 2) CU(h, cudaStreamWaitEvent(h->stream, h->ev_oc[set], 0));         // this set's outputs of slice is-2 have left
+        }
+        int rc = gptb_query_dev(h, dp(set, 0), m, flags, dp(set, 1), dp(set, 2), dp(set, 3), dp(set, 4), dp(set, 5), dp(set, 6), dp(set, 7), dp(set, 8),
+                                dp(set, 9), dp(set, 10));
+        if (rc) {
+            cudaStreamSynchronize(sin); cudaStreamSynchronize(h->stream); cudaStreamSynchronize(sout);
+            return rc;
+        }
+        if (piped) {
+            CU(h, cudaEventRecord(h->ev_cd[set], h->stream));
+            CU(h, cudaStreamWaitEvent(sout, h->ev_cd[set], 0));
+        }
+        for (int i = 2; i < 10; ++i)
+            if (segs[i].hout) CU(h, cudaMemcpyAsync(segs[i].hout + (size_t)q0 * segs[i].per, dp(set, i), segs[i].per * m * sizeof(double), cudaMemcpyDeviceToHost, sout));
+        if (segs[10].hout)   // dvar is (d, M): this slice fills columns [q0, q0 + m) of each row
+            CU(h, cudaMemcpy2DAsync(dvar + q0, sizeof(double) * M, dp(set, 10), sizeof(double) * m, sizeof(double) * m, d, cudaMemcpyDeviceToHost, sout));
+        if (piped) CU(h, cudaEventRecord(h->ev_oc[set], sout));
+    }
+    if (piped) {
+        CU(h, cudaStreamSynchronize(sin));
+        CU(h, cudaStreamSynchronize(sout));
+    }
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 
-extern "C" int gptb_query(gptb_handle* h, const double* x, int64_t M, uint32_t flags, const double* vel, double* mean, double* std,
-                          double* jac, double* jacvar, double* xhat, double* vhat, double* vvar, double* jphi, double* dvar) {
-    if (!h || M < 0) return -1;
-    if (M == 0) return 0;
-    if (!x) return -1;
-    CU(h, cudaSetDevice(h->device));
-    const int d = h->d, p = h->p;
-    if (d < 1) GPTB_FAIL(h, -1, "gptb_query: model is not fitted");
-    if ((flags & GPTB_VELOCITY) && !vel) GPTB_FAIL(h, -1, "GPTB_VELOCITY without vel");
-    const int64_t HOST_CHUNK = 1 << 22;
-    for (int64_t q0 = 0; q0 < M; q0 += HOST_CHUNK) {
-        const int64_t m = (M - q0 < HOST_CHUNK) ? (M - q0) : HOST_CHUNK;
-        auto at = [&](double* ptr, size_t per) -> double* { return ptr ? ptr + (size_t)q0 * per : nullptr; };
-        int rc = query_host_chunk(h, x + q0 * d, m, flags, vel ? vel + q0 * d : nullptr, at(mean, p), at(std, p), at(jac, (size_t)p * d),
-                                  at(jacvar, (size_t)p * d), at(xhat, d), at(vhat, d), at(vvar, p), at(jphi, (size_t)d * d),
-                                  dvar ? dvar + q0 : nullptr, M);
-        if (rc) return rc;
-    }
+// one scratch buffer, carved in 256-byte aligned pieces (sizes in doubles); kept while it stays below SCRATCH_KEEP
+constexpr size_t SCRATCH_KEEP = 256u << 20;
+struct Carver {
+    size_t need = 0;
+    size_t add(size_t doubles) { const size_t off = need; need += (doubles * sizeof(double) + 255) / 256 * 256; return off; }
+};
+static int ensure_scratch(gptb_handle* h, size_t bytes) {
+    if (bytes <= h->scratch_bytes) return 0;
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (h->scratch) cudaFree(h->scratch);
+    h->scratch = nullptr;
+    h->scratch_bytes = 0;
+    CU(h, cudaMalloc(&h->scratch, bytes));
+    h->scratch_bytes = bytes;
     return 0;
+}
+static void release_big_scratch(gptb_handle* h) {
+    if (h->scratch_bytes > SCRATCH_KEEP) {
+        cudaFree(h->scratch);
+        h->scratch = nullptr;
+        h->scratch_bytes = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1175,23 +1377,18 @@ extern "C" int gptb_query_cov(gptb_handle* h, const double* x, int64_t M, double
     const int d = h->d, p = h->p, T = h->T;
     const int Mpad = (int)((M + TS - 1) / TS * TS);
     const long long Npad = h->Npad;
-    double *xd = nullptr, *rhs = nullptr, *W = nullptr, *xr = nullptr, *macc = nullptr, *mean_d = nullptr, *cov_d = nullptr;
-    auto cleanup = [&]() {
-        for (double* q : {xd, rhs, W, xr, macc, mean_d, cov_d})
-            if (q) cudaFree(q);
-    };
+    Carver cv;
+    const size_t o_xd = cv.add((size_t)M * d), o_rhs = cv.add((size_t)Mpad * Npad), o_W = cv.add((size_t)Mpad * Npad), o_xr = cv.add((size_t)Mpad * d),
+                 o_macc = cv.add((size_t)Mpad * (p + p * d)), o_mean = cv.add((size_t)M * p), o_cov = cv.add((size_t)M * M);
+    if ((rc = ensure_scratch(h, cv.need))) return rc;
+    auto at = [&](size_t off) { return reinterpret_cast<double*>(h->scratch + off); };
+    double *xd = at(o_xd), *rhs = at(o_rhs), *W = at(o_W), *xr = at(o_xr), *macc = at(o_macc), *mean_d = at(o_mean), *cov_d = at(o_cov);
+    auto cleanup = [&]() { release_big_scratch(h); };
 #define CUX(call)                                                                                           \
     do {                                                                                                    \
         cudaError_t _e = (call);                                                                            \
         if (_e != cudaSuccess) { cleanup(); GPTB_FAIL(h, -2, "CUDA error %s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); } \
     } while (0)
-    CUX(cudaMalloc(&xd, sizeof(double) * M * d));
-    CUX(cudaMalloc(&rhs, sizeof(double) * Mpad * Npad));
-    CUX(cudaMalloc(&W, sizeof(double) * Mpad * Npad));
-    CUX(cudaMalloc(&xr, sizeof(double) * Mpad * d));
-    CUX(cudaMalloc(&macc, sizeof(double) * Mpad * (p + p * d)));
-    CUX(cudaMalloc(&mean_d, sizeof(double) * M * p));
-    CUX(cudaMalloc(&cov_d, sizeof(double) * M * M));
     CUX(cudaMemcpyAsync(xd, x, sizeof(double) * M * d, cudaMemcpyHostToDevice, h->stream));
     rc = pick_covgen(d, p)(h, xd, (int)M, Mpad, rhs, xr, macc, mean_d);
     if (rc) { cleanup(); return rc; }
@@ -1226,11 +1423,12 @@ extern "C" int gptb_transport_orientation(gptb_handle* h, const double* pos, con
     CU(h, cudaSetDevice(h->device));
     if (!h->have_alpha) GPTB_FAIL(h, -1, "gptb_transport_orientation: model is not fitted");
     if (h->d != 3 || h->p != 3) GPTB_FAIL(h, -1, "orientation transport needs a 3-D map (d = p = 3), got d=%d p=%d", h->d, h->p);
-    double *pd = nullptr, *od = nullptr, *jd = nullptr, *jp = nullptr, *qd = nullptr;
-    auto cleanup = [&]() {
-        for (double* q : {pd, od, jd, jp, qd})
-            if (q) cudaFree(q);
-    };
+    Carver cv;
+    const size_t o_pd = cv.add((size_t)M * 3), o_od = cv.add((size_t)M * 4), o_jd = cv.add((size_t)M * 9), o_jp = cv.add((size_t)M * 9), o_qd = cv.add((size_t)M * 4);
+    if (int rcs = ensure_scratch(h, cv.need)) return rcs;
+    auto at = [&](size_t off) { return reinterpret_cast<double*>(h->scratch + off); };
+    double *pd = at(o_pd), *od = at(o_od), *jd = at(o_jd), *jp = at(o_jp), *qd = at(o_qd);
+    auto cleanup = [&]() { release_big_scratch(h); };
     auto fail = [&](cudaError_t e, int line) {
         cleanup();
         char b[256];
@@ -1239,11 +1437,6 @@ extern "C" int gptb_transport_orientation(gptb_handle* h, const double* pos, con
         return -2;
     };
     cudaError_t e;
-    if ((e = cudaMalloc(&pd, sizeof(double) * M * 3)) != cudaSuccess) return fail(e, __LINE__);
-    if ((e = cudaMalloc(&od, sizeof(double) * M * 4)) != cudaSuccess) return fail(e, __LINE__);
-    if ((e = cudaMalloc(&jd, sizeof(double) * M * 9)) != cudaSuccess) return fail(e, __LINE__);
-    if ((e = cudaMalloc(&jp, sizeof(double) * M * 9)) != cudaSuccess) return fail(e, __LINE__);
-    if ((e = cudaMalloc(&qd, sizeof(double) * M * 4)) != cudaSuccess) return fail(e, __LINE__);
     if ((e = cudaMemcpyAsync(pd, pos, sizeof(double) * M * 3, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return fail(e, __LINE__);
     if ((e = cudaMemcpyAsync(od, ori, sizeof(double) * M * 4, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return fail(e, __LINE__);
     int rc = gptb_query_dev(h, pd, M, GPTB_JAC | GPTB_JPHI, nullptr, nullptr, nullptr, jd, nullptr, nullptr, nullptr, nullptr, jp, nullptr);
@@ -1267,11 +1460,12 @@ extern "C" int gptb_transport_stiffness(gptb_handle* h, const double* pos, const
     const int d = h->d;
     if (d != h->p || d < 2) GPTB_FAIL(h, -1, "stiffness transport needs a square map (d = p >= 2), got d=%d p=%d", h->d, h->p);
     const size_t dd = (size_t)d * d;
-    double *pd = nullptr, *kd = nullptr, *jd = nullptr, *jp = nullptr, *od = nullptr;
-    auto cleanup = [&]() {
-        for (double* q : {pd, kd, jd, jp, od})
-            if (q) cudaFree(q);
-    };
+    Carver cv;
+    const size_t o_pd = cv.add((size_t)M * d), o_kd = cv.add((size_t)M * dd), o_jd = cv.add((size_t)M * dd), o_jp = cv.add((size_t)M * dd), o_od = cv.add((size_t)M * dd);
+    if (int rcs = ensure_scratch(h, cv.need)) return rcs;
+    auto at = [&](size_t off) { return reinterpret_cast<double*>(h->scratch + off); };
+    double *pd = at(o_pd), *kd = at(o_kd), *jd = at(o_jd), *jp = at(o_jp), *od = at(o_od);
+    auto cleanup = [&]() { release_big_scratch(h); };
     auto fail = [&](cudaError_t e, int line) {
         cleanup();
         char b[256];
@@ -1280,11 +1474,6 @@ extern "C" int gptb_transport_stiffness(gptb_handle* h, const double* pos, const
         return -2;
     };
     cudaError_t e;
-    if ((e = cudaMalloc(&pd, sizeof(double) * M * d)) != cudaSuccess) return fail(e, __LINE__);
-    if ((e = cudaMalloc(&kd, sizeof(double) * M * dd)) != cudaSuccess) return fail(e, __LINE__);
-    if ((e = cudaMalloc(&jd, sizeof(double) * M * dd)) != cudaSuccess) return fail(e, __LINE__);
-    if ((e = cudaMalloc(&jp, sizeof(double) * M * dd)) != cudaSuccess) return fail(e, __LINE__);
-    if ((e = cudaMalloc(&od, sizeof(double) * M * dd)) != cudaSuccess) return fail(e, __LINE__);
     if ((e = cudaMemcpyAsync(pd, pos, sizeof(double) * M * d, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return fail(e, __LINE__);
     if ((e = cudaMemcpyAsync(kd, stiff, sizeof(double) * M * dd, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return fail(e, __LINE__);
     // Jphi(x) = (I + Jpsi(gamma(x))) R: the Jacobian of the whole map at x, as for the velocity (policy_transportation.py:37-46)
@@ -1418,7 +1607,7 @@ extern "C" int gptb_state_commit(gptb_handle* h) {
     h->have_alpha = true;                                   // mean / Jacobian queries are served from (X, alpha)
     h->have_minv = (hd[10] != 0.0) && (h->Minv != nullptr);  // variance queries need the inverse factor
     h->have_kinv = false;
-    h->have_bplanes = false;                                 // digit planes of a previous model's inverse factor are stale
+    invalidate_planes(h);                                    // digit planes of a previous model's inverse factor are stale
     return 0;
 }
 

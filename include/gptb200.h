@@ -81,6 +81,17 @@ int gptb_lml(gptb_handle* h, double c, const double* ell, double s2, double jitt
  * bound (128 * largest row sum of |digit| of the inverse factor < 2^31) decides, and the call fails if that does not hold either. */
 int gptb_set_variance_mode(gptb_handle* h, int mode, int slices);
 
+/* ---- run-time accuracy guard of the INT8-sliced path (on by default).  Before the first variance query of a model (and in
+ * gptb_prepare_variance) 2048 probe queries -- half of them next to training points, where the std is most sensitive -- are
+ * evaluated on the INT8 path and on the FP64 path of the same handle.  If max |std_int8 - std_fp64| / sqrt(c + s2) exceeds
+ * `threshold` (default 2e-8, a fifth of the 1e-7 std tolerance of gaussian_process.py:46-49 parity) one digit plane is added and
+ * the probe repeated; with the plane count exhausted the model is served by the FP64 path.  threshold = 0 switches the guard off.
+ * The report returns the requested and the effective plane count (0 = FP64 path), the probe error of the effective mode and the
+ * one measured with the requested plane count. */
+int gptb_set_variance_guard(gptb_handle* h, double threshold);
+int gptb_variance_guard_report(gptb_handle* h, int* requested_slices, int* used_slices, double* probe_err, double* first_err,
+                               double* threshold);
+
 /* ---- spatial mode (call before gptb_set_train; off by default).  The training points are kept in Morton (Z-curve) order
  * inside the handle, every query batch of the INT8-sliced path with 8-bit planes is processed in Morton order too (radix sort
  * of the batch by key, results scattered back to the caller's order), and the generator / the slicer record per
