@@ -9,7 +9,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 S, T = synthetic_pairs(N, 3, seed=0)
 eng = L.Engine(0)
-eng.set_variance_mode("int8w5")
+eng.set_variance_mode(sys.argv[3] if len(sys.argv) > 3 else "int8w5")
 eng.set_spatial(1)
 eng.set_train(S, T - S)
 eng.factorize(0.1, [0.1] * 3, 1e-4, 1e-10)
