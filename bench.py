@@ -574,6 +574,15 @@ def small_n_block(L, local_rank):
             t0 = time.perf_counter(); eng.query(xq, fl); t_q.append(time.perf_counter() - t0)
         out[tag] = {"fit_ms": 1e3 * float(np.median(t_fit)), "lml_grad_ms": 1e3 * float(np.median(t_lml)), "apply_ms": 1e3 * float(np.median(t_q)),
                     "apply_query_points_per_s": Mq / float(np.median(t_q))}
+        if d == 3:
+            # minimum-variance stabilised rollouts (plot_utils.py:298-310: 1000 sequential single-point predict + derivative_of_variance
+            # calls in the reference), device-resident loop; K start points advance together
+            for Kr in (1, 256):
+                st = rng.random((Kr, 3))
+                eng.rollout_min_variance(st, 50)
+                t0 = time.perf_counter(); eng.rollout_min_variance(st, 1000); dt = time.perf_counter() - t0
+                out[tag][f"rollout_K{Kr}_1000_steps_ms"] = 1e3 * dt
+                out[tag][f"rollout_K{Kr}_point_steps_per_s"] = Kr * 1000 / dt
         eng.close()
     return out
 

@@ -31,6 +31,8 @@ SYMBOLS = {
     "gptb_set_affine": (C.c_int, [C.c_void_p, _dp, C.c_double, _dp, _dp]),
     "gptb_query": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_uint32, _dp] + [_dp] * 9),
     "gptb_query_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p] + [C.c_void_p] * 9),
+    "gptb_query_grid": (C.c_int, [C.c_void_p, _dp, _dp, C.POINTER(C.c_int64), C.c_int64, C.c_int64, C.c_uint32, _dp, C.c_int64, _dp]),
+    "gptb_rollout_min_variance": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_int, C.c_double, _dp]),
     "gptb_query_cov": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp, _dp]),
     "gptb_transport_orientation": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, _dp, _dp]),
     "gptb_transport_stiffness": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, _dp, _dp]),
@@ -231,6 +233,33 @@ class Engine:
                                  ptr(g("xhat")), ptr(g("vhat")), ptr(g("vvar")), ptr(g("jphi")), ptr(g("dvar")))
         self._check(rc, "gptb_query")
         return o
+
+    def query_grid(self, origin, step, dims, flags, first=0, count=None, sample_stride=0):
+        """Dense lattice query with on-device point generation and reduction (include/gptb200.h gptb_query_grid).  Returns
+        {"columns": names, "stats": (ncol, 4) [sum, sumsq, min, max], "sample_index": lattice indices, "sample": (n, ncol)}."""
+        origin, step = as_f64(origin), as_f64(step)
+        dims_a = (C.c_int64 * len(dims))(*[int(v) for v in dims])
+        total = int(np.prod([int(v) for v in dims]))
+        count = total - first if count is None else int(count)
+        p, d = self.p, self.d
+        cols = ([f"mean{o}" for o in range(p)] if flags & MEAN else []) + (["std"] if flags & STD else []) + \
+               ([f"jac{o}{a}" for o in range(p) for a in range(d)] if flags & JAC else [])
+        stats = np.zeros((len(cols), 4))
+        j0 = -(-first // sample_stride) if sample_stride > 0 else 0
+        j1 = -(-(first + count) // sample_stride) if sample_stride > 0 else 0
+        sample = np.zeros((max(j1 - j0, 0), len(cols)))
+        self._check(self.lib.gptb_query_grid(self.h, ptr(origin), ptr(step), dims_a, int(first), count, int(flags), ptr(stats), int(sample_stride),
+                                             ptr(sample) if sample.size else None), "gptb_query_grid")
+        return {"columns": cols, "stats": stats, "sample_index": np.arange(j0, j1) * sample_stride if sample_stride > 0 else np.zeros(0, int), "sample": sample}
+
+    def rollout_min_variance(self, start, steps, gain=1.0):
+        """K minimum-variance stabilised rollouts of `steps` steps on the device (include/gptb200.h); returns (steps, K, d)."""
+        start = as_f64(start)
+        if start.ndim != 2 or start.shape[1] != self.d:
+            raise ValueError(f"start points must have shape (K, {self.d}), got {start.shape}")
+        traj = np.empty((int(steps), start.shape[0], self.d))
+        self._check(self.lib.gptb_rollout_min_variance(self.h, ptr(start), start.shape[0], int(steps), float(gain), ptr(traj)), "gptb_rollout_min_variance")
+        return traj
 
     def query_cov(self, x):
         """Posterior mean (M,p) and joint covariance (M,M) on the device (k(x,x) + s2 I - K* K^-1 K*^T)."""

@@ -1340,6 +1340,143 @@ static void release_big_scratch(gptb_handle* h) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// minimum-variance stabilised rollouts, device-resident (one CUDA graph per step shape, replayed `steps` times)
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int gptb_rollout_min_variance(gptb_handle* h, const double* start, int64_t K, int steps, double gain, double* traj) {
+    if (!h || !start || !traj || K < 1 || steps < 1) return -1;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->have_alpha) GPTB_FAIL(h, -1, "gptb_rollout_min_variance: model is not fitted");
+    const int d = h->d, p = h->p;
+    if (d != p || d < 2 || d > 3) GPTB_FAIL(h, -1, "rollouts need a square dynamics model with d = p in {2, 3}, got d=%d p=%d", d, p);
+    Carver cv;
+    const size_t o_pos = cv.add((size_t)K * d), o_mean = cv.add((size_t)K * p), o_std = cv.add((size_t)K * p), o_dv = cv.add((size_t)K * d),
+                 o_slot = cv.add((size_t)K * d), o_traj = cv.add((size_t)steps * K * d);
+    int rc = ensure_scratch(h, cv.need);
+    if (rc) return rc;
+    auto at = [&](size_t off) { return reinterpret_cast<double*>(h->scratch + off); };
+    double *pos = at(o_pos), *md = at(o_mean), *sd = at(o_std), *dv = at(o_dv), *slot = at(o_slot), *tr = at(o_traj);
+    CU(h, cudaMemcpyAsync(pos, start, sizeof(double) * K * d, cudaMemcpyHostToDevice, h->stream));
+    const uint32_t fl = GPTB_MEAN | GPTB_STD | GPTB_DVAR;
+    const unsigned grid = (unsigned)((K + 127) / 128);
+    auto one_step = [&](int t) -> int {
+        int r = gptb_query_dev(h, pos, K, fl, nullptr, md, sd, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dv);
+        if (r) return r;
+        double* dst = tr + (size_t)t * K * d;
+        if (d == 2) rollout_step_kernel<2><<<grid, 128, 0, h->stream>>>(pos, md, sd, dv, K, gain, dst);
+        else rollout_step_kernel<3><<<grid, 128, 0, h->stream>>>(pos, md, sd, dv, K, gain, dst);
+        h->launches++;
+        return 0;
+    };
+    // step 0 eagerly: builds the variance operands, grows the workspace (both synchronise, which a capture does not allow)
+    if ((rc = one_step(0))) { release_big_scratch(h); return rc; }
+    const bool was_timing = h->timing;
+    h->timing = false;
+    int t = 1;
+    // the steps are launch-bound for small K (~20 kernels of a few microseconds each): capture one step as a graph and replay it; the
+    // trajectory slot is the only thing that changes, so the captured step writes into a fixed slot and a D2D copy files it
+    if (steps > 2 && !h->pipeline) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        const long long before = h->launches;
+        bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            int r = gptb_query_dev(h, pos, K, fl, nullptr, md, sd, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dv);
+            if (d == 2) rollout_step_kernel<2><<<grid, 128, 0, h->stream>>>(pos, md, sd, dv, K, gain, slot);
+            else rollout_step_kernel<3><<<grid, 128, 0, h->stream>>>(pos, md, sd, dv, K, gain, slot);
+            h->launches++;
+            ok = (cudaStreamEndCapture(h->stream, &graph) == cudaSuccess) && r == 0 && graph != nullptr;
+        }
+        const long long per_step = h->launches - before;
+        if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+        if (ok) {
+            for (; t < steps; ++t) {
+                if (cudaGraphLaunch(exec, h->stream) != cudaSuccess) { ok = false; break; }
+                CU(h, cudaMemcpyAsync(tr + (size_t)t * K * d, slot, sizeof(double) * K * d, cudaMemcpyDeviceToDevice, h->stream));
+                h->launches += per_step;
+            }
+        } else {
+            cudaGetLastError();               // a failed capture leaves a sticky-free error: fall through to eager steps
+        }
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        if (!ok && t < steps) { h->timing = was_timing; release_big_scratch(h); GPTB_FAIL(h, -3, "graph replay of the rollout step failed"); }
+    }
+    for (; t < steps; ++t)
+        if ((rc = one_step(t))) { h->timing = was_timing; release_big_scratch(h); return rc; }
+    h->timing = was_timing;
+    CU(h, cudaMemcpyAsync(traj, tr, sizeof(double) * (size_t)steps * K * d, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    release_big_scratch(h);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dense lattice queries with on-device generation and reduction (BASELINE config 5)
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int gptb_query_grid(gptb_handle* h, const double* origin, const double* step, const int64_t* dims, int64_t first, int64_t count,
+                               uint32_t flags, double* stats, int64_t sample_stride, double* sample_out) {
+    if (!h || !origin || !step || !dims || !stats || first < 0 || count < 0) return -1;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->have_alpha) GPTB_FAIL(h, -1, "gptb_query_grid: model is not fitted");
+    const int d = h->d, p = h->p;
+    if (flags & ~(GPTB_MEAN | GPTB_STD | GPTB_JAC | GPTB_AFFINE_IN)) GPTB_FAIL(h, -1, "gptb_query_grid supports GPTB_MEAN | GPTB_STD | GPTB_JAC (| GPTB_AFFINE_IN)");
+    GridSpec g{};
+    long long total = 1;
+    for (int a = 0; a < d; ++a) {
+        if (dims[a] < 1) GPTB_FAIL(h, -1, "gptb_query_grid: dims[%d] = %lld", a, (long long)dims[a]);
+        g.origin[a] = origin[a]; g.step[a] = step[a]; g.dims[a] = dims[a];
+        total *= dims[a];
+    }
+    if (first + count > total) GPTB_FAIL(h, -1, "gptb_query_grid: points [%lld, %lld) exceed the lattice of %lld", (long long)first, (long long)(first + count), total);
+    const int ncol = ((flags & GPTB_MEAN) ? p : 0) + ((flags & GPTB_STD) ? 1 : 0) + ((flags & GPTB_JAC) ? p * d : 0);
+    if (ncol == 0) GPTB_FAIL(h, -1, "gptb_query_grid: no output requested");
+    for (int i = 0; i < 4 * ncol; ++i) stats[i] = 0.0;
+    if (count == 0) return 0;
+    const long long B = 65536;
+    // sample j = lattice point j * stride (global numbering, so shards of one lattice produce disjoint pieces of one sample set)
+    const long long j_first = sample_stride > 0 ? (first + sample_stride - 1) / sample_stride : 0;
+    const long long j_end = sample_stride > 0 ? (first + count + sample_stride - 1) / sample_stride : 0;
+    const long long nsample = j_end - j_first;
+    if (nsample > 0 && !sample_out) GPTB_FAIL(h, -1, "gptb_query_grid: sample_stride without sample_out");
+    Carver cv;
+    const size_t o_x = cv.add((size_t)B * d), o_mean = cv.add((size_t)B * p), o_std = cv.add((size_t)B * p), o_jac = cv.add((size_t)B * p * d),
+                 o_pack = cv.add((size_t)B * ncol), o_part = cv.add((size_t)GRID_STAT_BLOCKS * ncol * 4), o_acc = cv.add((size_t)ncol * 4),
+                 o_smp = cv.add((size_t)(nsample > 0 ? nsample : 1) * ncol);
+    int rc = ensure_scratch(h, cv.need);
+    if (rc) return rc;
+    auto at = [&](size_t off) { return reinterpret_cast<double*>(h->scratch + off); };
+    double *xd = at(o_x), *md = at(o_mean), *sd = at(o_std), *jd = at(o_jac), *pack = at(o_pack), *part = at(o_part), *acc = at(o_acc), *smp = at(o_smp);
+    bool firstb = true;
+    for (long long q0 = 0; q0 < count; q0 += B) {
+        const int m = (int)((count - q0 < B) ? (count - q0) : B);
+        grid_points_kernel<<<(m + 255) / 256, 256, 0, h->stream>>>(g, d, first + q0, m, xd);
+        LAUNCH_CHECK(h);
+        rc = gptb_query_dev(h, xd, m, flags, nullptr, (flags & GPTB_MEAN) ? md : nullptr, (flags & GPTB_STD) ? sd : nullptr, (flags & GPTB_JAC) ? jd : nullptr,
+                            nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        if (rc) { release_big_scratch(h); return rc; }
+        grid_pack_kernel<<<(m + 255) / 256, 256, 0, h->stream>>>(md, sd, jd, m, p, d, flags, pack);
+        LAUNCH_CHECK(h);
+        grid_stats_partial_kernel<<<GRID_STAT_BLOCKS, 256, 0, h->stream>>>(pack, m, ncol, part);
+        LAUNCH_CHECK(h);
+        grid_stats_final_kernel<<<(ncol + 31) / 32, 32, 0, h->stream>>>(part, ncol, acc, firstb ? 1 : 0);
+        LAUNCH_CHECK(h);
+        firstb = false;
+        if (nsample > 0) {
+            const long long ja = (first + q0 + sample_stride - 1) / sample_stride, jb = (first + q0 + m + sample_stride - 1) / sample_stride;
+            if (jb > ja) {
+                grid_sample_kernel<<<(unsigned)((jb - ja + 127) / 128), 128, 0, h->stream>>>(pack, ncol, first + q0, m, sample_stride, j_first, smp);
+                LAUNCH_CHECK(h);
+            }
+        }
+    }
+    CU(h, cudaMemcpyAsync(stats, acc, sizeof(double) * 4 * ncol, cudaMemcpyDeviceToHost, h->stream));
+    if (nsample > 0) CU(h, cudaMemcpyAsync(sample_out, smp, sizeof(double) * nsample * ncol, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    release_big_scratch(h);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // joint covariance
 // ---------------------------------------------------------------------------------------------------------------
 template <int D, int P>

@@ -715,4 +715,123 @@ __global__ void __launch_bounds__(128) stiffness_transport_kernel(const double* 
         }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Dense transport grids (BASELINE config 5; the query shape of plot_utils.py:10-15, 353-358): the lattice points are generated on
+// the device from (origin, step, dims) -- point g of the row-major lattice (last dimension fastest) -- and the outputs are reduced to
+// per-column statistics, so a 2^29-point grid needs neither host input nor host output buffers.
+// ------------------------------------------------------------------------------------------------------------
+struct GridSpec {
+    double origin[MAXD], step[MAXD];
+    long long dims[MAXD];
+};
+
+__global__ void __launch_bounds__(256) grid_points_kernel(GridSpec g, int d, long long first, int B, double* __restrict__ xq) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= B) return;
+    long long idx = first + q;
+    double x[MAXD];
+    for (int a = d - 1; a >= 0; --a) {
+        const long long i = idx % g.dims[a];
+        idx /= g.dims[a];
+        x[a] = __dadd_rn(g.origin[a], __dmul_rn(g.step[a], (double)i));      // no FMA contraction: bit-identical to numpy's origin + step * i
+    }
+    for (int a = 0; a < d; ++a) xq[(long long)q * d + a] = x[a];
+}
+
+// packed row of one lattice point: [mean (p) | std (1, the p columns are identical) | jac (p*d)], whichever were requested
+__global__ void __launch_bounds__(256) grid_pack_kernel(const double* __restrict__ mean, const double* __restrict__ std, const double* __restrict__ jac,
+                                                        int B, int p, int d, unsigned flags, double* __restrict__ pack) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= B) return;
+    const int ncol = ((flags & 1u) ? p : 0) + ((flags & 2u) ? 1 : 0) + ((flags & 4u) ? p * d : 0);
+    double* dst = pack + (long long)q * ncol;
+    int c = 0;
+    if (flags & 1u) for (int o = 0; o < p; ++o) dst[c++] = mean[(long long)q * p + o];
+    if (flags & 2u) dst[c++] = std[(long long)q * p];
+    if (flags & 4u) for (int v = 0; v < p * d; ++v) dst[c++] = jac[(long long)q * p * d + v];
+}
+
+// Column statistics of a row-major (B, ncol) block: partial[b][col] = {sum, sum of squares, min, max} over the rows block b owns
+// (fixed assignment, fixed order: the result does not depend on scheduling).  GRID_STAT_BLOCKS blocks of 256 threads.
+constexpr int GRID_STAT_BLOCKS = 128;
+__global__ void __launch_bounds__(256) grid_stats_partial_kernel(const double* __restrict__ v, int B, int ncol, double* __restrict__ partial) {
+    __shared__ double red[4][256];
+    for (int col = 0; col < ncol; ++col) {
+        double s = 0.0, s2 = 0.0, mn = 1e300, mx = -1e300;
+        for (int r = blockIdx.x * 256 + threadIdx.x; r < B; r += GRID_STAT_BLOCKS * 256) {
+            const double x = v[(long long)r * ncol + col];
+            s += x;
+            s2 = fma(x, x, s2);
+            mn = fmin(mn, x);
+            mx = fmax(mx, x);
+        }
+        red[0][threadIdx.x] = s; red[1][threadIdx.x] = s2; red[2][threadIdx.x] = mn; red[3][threadIdx.x] = mx;
+        __syncthreads();
+        for (int w = 128; w > 0; w >>= 1) {
+            if (threadIdx.x < w) {
+                red[0][threadIdx.x] += red[0][threadIdx.x + w];
+                red[1][threadIdx.x] += red[1][threadIdx.x + w];
+                red[2][threadIdx.x] = fmin(red[2][threadIdx.x], red[2][threadIdx.x + w]);
+                red[3][threadIdx.x] = fmax(red[3][threadIdx.x], red[3][threadIdx.x + w]);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            double* dst = partial + ((long long)blockIdx.x * ncol + col) * 4;
+            dst[0] = red[0][0]; dst[1] = red[1][0]; dst[2] = red[2][0]; dst[3] = red[3][0];
+        }
+        __syncthreads();
+    }
+}
+// acc[col] (+)= fixed-order reduction of the block partials; first != 0 initialises the accumulator
+__global__ void grid_stats_final_kernel(const double* __restrict__ partial, int ncol, double* __restrict__ acc, int first) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol) return;
+    double s = 0.0, s2 = 0.0, mn = 1e300, mx = -1e300;
+    for (int b = 0; b < GRID_STAT_BLOCKS; ++b) {
+        const double* src = partial + ((long long)b * ncol + col) * 4;
+        s += src[0]; s2 += src[1]; mn = fmin(mn, src[2]); mx = fmax(mx, src[3]);
+    }
+    double* dst = acc + (long long)col * 4;
+    if (first) { dst[0] = s; dst[1] = s2; dst[2] = mn; dst[3] = mx; }
+    else { dst[0] += s; dst[1] += s2; dst[2] = fmin(dst[2], mn); dst[3] = fmax(dst[3], mx); }
+}
+// every `stride`-th lattice point of the block [first, first + B) -> packed sample rows (ncol each)
+__global__ void grid_sample_kernel(const double* __restrict__ v, int ncol, long long first, int B, long long stride, long long first_sample,
+                                   double* __restrict__ out) {
+    // sample j is lattice point j * stride; this block holds samples j with first <= j*stride < first + B
+    const long long j0 = (first + stride - 1) / stride;
+    const long long j = j0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const long long g = j * stride;
+    if (g >= first + B) return;
+    for (int c = 0; c < ncol; ++c) out[(j - first_sample) * ncol + c] = v[(g - first) * ncol + c];
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Minimum-variance stabilised rollout (plot_utils.py:298-310): pos <- pos + mean(pos) - gain * std(pos) * g / |g| with
+// g = derivative_of_variance(pos) (gaussian_process.py:104-126); one thread per start point, the step is recorded in traj.
+// ------------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) rollout_step_kernel(double* __restrict__ pos, const double* __restrict__ mean, const double* __restrict__ std,
+                                                           const double* __restrict__ dvar, long long K, double gain, double* __restrict__ traj_t) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    double g[D], nrm = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        g[a] = dvar[(long long)a * K + k];
+        nrm = fma(g[a], g[a], nrm);
+    }
+    nrm = sqrt(nrm);
+    const double sd = std[k * D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        const double x = pos[k * D + a] + mean[k * D + a] - gain * sd * (g[a] / nrm);
+        pos[k * D + a] = x;
+        traj_t[k * D + a] = x;
+    }
+}
+
 }  // namespace gptb

@@ -281,3 +281,17 @@ class GaussianProcess:
 
     def derivative_of_variance(self, x):
         return self._query(x, _lib.DVAR)["dvar"]
+
+    # -- minimum-variance stabilisation (plot_utils.py:283-317): the two query shapes of the reference's plotting helpers -------------
+    def minimum_variance_field(self, x, gain=2.0):
+        """vel - gain * std * g / |g| with g = derivative_of_variance (plot_utils.plot_vector_field_minvar:286-289, gain 2): one fused
+        query (mean, std and the variance gradient share the regenerated k(x*, X)); returns (M, n_outputs)."""
+        o = self._query(x, _lib.MEAN | _lib.STD | _lib.DVAR)
+        grad = o["dvar"].T
+        return o["mean"] - gain * o["std"] * grad / np.linalg.norm(grad, axis=1).reshape(-1, 1)
+
+    def rollout_min_variance(self, start, steps=1000, gain=1.0):
+        """Rollouts pos <- pos + mean(pos) - gain * std(pos) * g / |g| from every row of `start` (plot_utils.plot_traj_evolution:298-310 is
+        the one-start-point, gain = 1 case); the loop runs on the device.  Returns the positions after each step, (steps, K, d)."""
+        self._ensure_fitted_factor()
+        return self._engine.rollout_min_variance(np.atleast_2d(np.asarray(start, dtype=np.float64)), steps, gain)

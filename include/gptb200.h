@@ -124,6 +124,26 @@ int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, uint32_t flag
                    double* mean_dev, double* std_dev, double* jac_dev, double* jacvar_dev,
                    double* xhat_dev, double* vhat_dev, double* vvar_dev, double* jphi_dev, double* dvar_dev);
 
+/* ---- minimum-variance stabilised rollouts (plot_utils.py:298-310, and :283-296 for the one-step grid form): K start points are
+ * advanced `steps` times by  pos <- pos + mean(pos) - gain * std(pos) * g / |g|,  g = derivative_of_variance(pos)
+ * (gaussian_process.py:46-49, 104-126), all K points per step in ONE batched query; the loop is device-resident (one step is
+ * captured as a CUDA graph and replayed -- for small K a step is ~20 launch-bound kernels), only the finished trajectories travel.
+ * start (K,d) in; traj (steps, K, d) out: the positions AFTER each step.  Needs d == p in {2, 3} (a dynamics model).  The
+ * reference's loop is the K = 1, gain = 1 case. */
+int gptb_rollout_min_variance(gptb_handle* h, const double* start, int64_t K, int steps, double gain, double* traj);
+
+/* ---- dense transport grid (BASELINE config 5; the query shape of plot_utils.py:10-15, 353-358: a regular lattice over the workspace).
+ * The lattice points are GENERATED ON THE DEVICE: point g of the row-major lattice `dims` (last dimension fastest) is
+ * x_a = origin[a] + step[a] * i_a; this call evaluates points [first, first + count) -- a rank's shard of the lattice -- with
+ * flags from {GPTB_MEAN, GPTB_STD, GPTB_JAC, GPTB_AFFINE_IN} and reduces the outputs on the device, so a 2^29-point grid needs no host
+ * buffers.  Packed columns per point: [mean (p) | std (1) | jac (p*d)] (those requested, ncol in total).
+ *   stats (ncol, 4) out: per column {sum, sum of squares, min, max} over the evaluated points (fixed-order reductions: deterministic;
+ *          shard sums add up to the whole-lattice sums -- the size-independent parity property at full size);
+ *   sample_stride > 0: lattice points j * sample_stride that fall into [first, first + count) are also returned, packed rows in
+ *          sample_out (ceil-counted: (ceil((first+count)/stride) - ceil(first/stride), ncol)), for checks against the CPU oracle. */
+int gptb_query_grid(gptb_handle* h, const double* origin, const double* step, const int64_t* dims, int64_t first, int64_t count,
+                    uint32_t flags, double* stats, int64_t sample_stride, double* sample_out);
+
 /* ---- joint posterior on M points: mean (M,p) and covariance (M,M) = k(x,x) + s2 I - K* K^-1 K*^T, the quantity behind
  * GaussianProcess.predict(return_cov=True) and samples() (gaussian_process.py:50-60; sklearn:_gpr.py:470-475, 502-539).
  * The covariance is output-independent (the host replicates it over p as sklearn does). */

@@ -220,3 +220,46 @@ def test_n32768_spot_check_against_refined_cpu_solve():
         print(f"N=32768 {mode} spatial={int(spatial)} std err vs refined CPU solve {err:.2e}", eng.variance_guard() if mode != "fp64" else "")
         assert err < (TOL_STD / STD_MARGIN if mode != "fp64" else 1e-8)
         eng.close()
+
+
+def test_dense_grid_query_matches_explicit_queries_and_shards_add_up():
+    """gptb_query_grid (BASELINE config 5 shape: lattice generated on the device, outputs reduced on the device) against the same
+    lattice passed as explicit query points; shard statistics add up to the whole-lattice statistics; sampled rows are the rows."""
+    from gaussian_process_transportation_b200 import _lib as L
+    from oracle.gp_oracle import synthetic_pairs, ChoGP
+    N = 700
+    S, T = synthetic_pairs(N, 3, seed=2)
+    eng = L.Engine(0)
+    eng.set_variance_mode("int8w5")
+    eng.set_spatial(True)
+    eng.set_train(S, T - S)
+    eng.factorize(0.1, [0.1, 0.15, 0.2], 1e-4, 1e-10)
+    dims = (37, 41, 53)                       # 80401 points: two batches, a ragged tail
+    origin, step = np.array([-0.1, -0.1, -0.1]), np.array([1.2 / 36, 1.2 / 40, 1.2 / 52])
+    fl = L.MEAN | L.STD | L.JAC
+    whole = eng.query_grid(origin, step, dims, fl, sample_stride=997)
+    ii = np.stack(np.meshgrid(*[np.arange(n) for n in dims], indexing="ij"), axis=-1).reshape(-1, 3)
+    x = origin + step * ii
+    o = eng.query(x, fl)
+    pack = np.hstack([o["mean"], o["std"][:, :1], o["jac"].reshape(len(x), -1)])
+    assert whole["columns"][3] == "std" and whole["stats"].shape == (13, 4)
+    assert np.allclose(whole["stats"][:, 0], pack.sum(axis=0), rtol=1e-12, atol=1e-12 * len(x))
+    assert np.allclose(whole["stats"][:, 1], (pack ** 2).sum(axis=0), rtol=1e-12)
+    assert np.array_equal(whole["stats"][:, 2], pack.min(axis=0)) and np.array_equal(whole["stats"][:, 3], pack.max(axis=0))
+    assert np.array_equal(whole["sample"], pack[whole["sample_index"]])
+    # two ranks' shards of the same lattice
+    total = len(x)
+    a = eng.query_grid(origin, step, dims, fl, first=0, count=total // 2 + 13, sample_stride=997)
+    b = eng.query_grid(origin, step, dims, fl, first=total // 2 + 13, count=total - (total // 2 + 13), sample_stride=997)
+    assert np.allclose(a["stats"][:, 0] + b["stats"][:, 0], whole["stats"][:, 0], rtol=1e-12, atol=1e-9)
+    assert np.array_equal(np.minimum(a["stats"][:, 2], b["stats"][:, 2]), whole["stats"][:, 2])
+    assert np.array_equal(np.concatenate([a["sample_index"], b["sample_index"]]), whole["sample_index"])
+    assert np.array_equal(np.vstack([a["sample"], b["sample"]]), whole["sample"])
+    # and the sampled lattice points against the CPU oracle
+    ora = ChoGP(0.1, [0.1, 0.15, 0.2], 1e-4).fit(S, T - S)
+    xs = x[whole["sample_index"]]
+    m, s = ora.predict(xs, return_std=True)
+    assert rel(whole["sample"][:, :3], m) < 1e-9
+    assert np.max(np.abs(whole["sample"][:, 3] - s[:, 0])) / np.sqrt(0.1 + 1e-4) < TOL_STD / STD_MARGIN
+    assert rel(whole["sample"][:, 4:].reshape(-1, 3, 3), ora.derivative(xs)) < 1e-9
+    eng.close()

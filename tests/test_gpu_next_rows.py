@@ -158,3 +158,36 @@ def test_stiffness_transport_congruence(d):
     with contextlib.redirect_stdout(io.StringIO()):
         g.apply_transportation()
     assert np.array_equal(g.training_stiff, out)
+
+
+def test_min_variance_rollouts_and_field_vs_oracle_loop():
+    """f2: the stabilised rollout of plot_utils.plot_traj_evolution:298-310 (sequential predict + derivative_of_variance calls in the
+    reference) as one device-resident batched loop, and the one-step grid form of plot_vector_field_minvar:283-289."""
+    import gaussian_process_transportation_b200 as pkg
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+    from oracle.gp_oracle import SkGaussianProcess
+    rng = np.random.default_rng(4)
+    X = rng.random((300, 3))
+    Y = 0.02 * np.stack([np.sin(3 * X[:, 1]), np.cos(2 * X[:, 0]), X[:, 2] - 0.5], axis=1)       # a small, smooth velocity field
+    k = C(0.05) * RBF([0.3, 0.3, 0.3]) + WhiteKernel(1e-4)
+    mine = pkg.GaussianProcess(kernel=k, optimizer=None)
+    ora = SkGaussianProcess(kernel=k, optimizer=None)
+    mine.fit(X, Y); ora.fit(X, Y)
+    start = rng.random((5, 3))
+    steps = 40
+    traj = mine.rollout_min_variance(start, steps=steps, gain=1.0)
+    assert traj.shape == (steps, 5, 3)
+    for kk in range(5):
+        pos = start[kk:kk + 1].copy()
+        for t in range(steps):
+            vel, std = ora.predict(pos, return_std=True)
+            grad = ora.derivative_of_variance(pos)
+            f = grad[:, 0] / np.sqrt(np.sum(grad[:, 0] ** 2))
+            pos = pos + vel.reshape(1, -1) - std[0] * f
+            assert np.linalg.norm(traj[t, kk] - pos[0]) < 1e-8 * (1 + t), (kk, t)
+    # eager (2 steps: no graph) and replayed steps agree bit for bit
+    assert np.array_equal(mine.rollout_min_variance(start, steps=2)[:2], traj[:2])
+    grid = rng.random((257, 3))
+    vel, std = ora.predict(grid, return_std=True)
+    g = ora.derivative_of_variance(grid).transpose()
+    assert np.allclose(mine.minimum_variance_field(grid), vel - 2 * std * g / np.linalg.norm(g, axis=1).reshape(-1, 1), rtol=1e-7, atol=1e-9)
