@@ -603,9 +603,17 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
         // ---------------- epilogue warps 4..7: TMEM lane quarter = warp % 4 ----------------
         const int quarter = warp & 3;
         const int q = quarter * 32 + lane;                      // query row within the tile = TMEM lane
-        double wgt[S];                                          // digits are 1-based: diagonal d = a+b-2 carries 2^-bits(d+2)
+        // digits are 1-based: diagonal d = a+b-2 carries 2^-bits(d+2).  The diagonals are recombined three at a time in 64-bit INTEGER
+        // arithmetic (|acc| < 2^31, so acc_d 2^2b + acc_d+1 2^b + acc_d+2 < 2^48: exact), each group is converted once through the
+        // mantissa trick (exact below 2^51) and only the NG = ceil(S / 3) group values meet in FP64: 2 NG + 1 FP64 instructions per
+        // output instead of 2 S -- the epilogue's FP64 work is what the next tile's first MMAs wait for (acc_empty).
+        constexpr int NG = (S + 2) / 3;
+        double gw[NG];                                          // weight of the LAST diagonal of each group
 #pragma unroll
-        for (int d = 0; d < S; ++d) wgt[d] = ldexp(1.0, -digit_bits * (d + 2));
+        for (int g = 0; g < NG; ++g) {
+            const int dlast = (3 * g + 2 < S) ? 3 * g + 2 : S - 1;
+            gw[g] = ldexp(1.0, -digit_bits * (dlast + 2));
+        }
         for (int lt = 0;; ++lt) {
             mbar_wait(&slot_full[lt & 1], (lt >> 1) & 1);
             const int t = tile_slot[lt & 1];
@@ -639,13 +647,16 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-                for (int d = 0; d < S; ++d) {
+                for (int g = 0; g < NG; ++g) {
+                    const int d0 = 3 * g, cnt = (d0 + 3 <= S) ? 3 : S - d0;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        // int32 -> double without the conversion pipe (I2F.F64 issues at a quarter of the DFMA rate and there are
-                        // S of them per output): 2^52 + 2^31 + r sits exactly in the mantissa, one DADD removes the offset
-                        const double dr = __hiloint2double(0x43300000, (int)(r[d][j] ^ 0x80000000u)) - 4503601774854144.0;
-                        v[j] = fma(dr, wgt[d], v[j]);
+                        long long acc = (long long)(int)r[d0][j];
+#pragma unroll
+                        for (int e = 1; e < cnt; ++e) acc = acc * (1LL << digit_bits) + (long long)(int)r[d0 + e][j];
+                        // int64 -> double without the conversion pipe: 1.5 * 2^52 + acc sits exactly in the mantissa (|acc| < 2^51)
+                        const double da = __longlong_as_double(acc + 0x4338000000000000LL) - 6755399441055744.0;
+                        v[j] = fma(da, gw[g], v[j]);
                     }
                 }
                 if (cb == ON / 16 - 1) {
