@@ -23,6 +23,7 @@ SYMBOLS = {
     "gptb_set_train": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_int, C.c_int]),
     "gptb_set_kernel_kind": (C.c_int, [C.c_void_p, C.c_int]),
     "gptb_factorize": (C.c_int, [C.c_void_p, C.c_double, _dp, C.c_double, C.c_double, _dp]),
+    "gptb_append_point": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
     "gptb_lml": (C.c_int, [C.c_void_p, C.c_double, _dp, C.c_double, C.c_double, C.c_int, _dp, _dp]),
     "gptb_set_variance_mode": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "gptb_prepare_variance": (C.c_int, [C.c_void_p]),
@@ -168,6 +169,18 @@ class Engine:
         out = C.c_double(float("nan"))
         rc = self.lib.gptb_factorize(self.h, float(c), ptr(e), float(s2), float(jitter), C.byref(out) if want_lml else None)
         self._check(rc, "gptb_factorize")
+        return rc, out.value
+
+    def append_point(self, x, y, want_lml=False):
+        """Rank-1 append of one training point at the current hyper-parameters; returns (info, lml)."""
+        x, y = as_f64(x).ravel(), as_f64(y).ravel()
+        if x.size != self.d or y.size != self.p:
+            raise ValueError(f"append_point needs x ({self.d},) and y ({self.p},)")
+        out = C.c_double(float("nan"))
+        rc = self.lib.gptb_append_point(self.h, ptr(x), ptr(y), C.byref(out) if want_lml else None)
+        self._check(rc, "gptb_append_point")
+        if rc == 0:
+            self.N += 1
         return rc, out.value
 
     def lml(self, c, ell, s2, jitter, want_grad=True):

@@ -206,9 +206,13 @@ __device__ __forceinline__ int warp_potrf_trtri32(double (&a)[DB], double (&x)[D
 // running right-hand side, already updated by the panels of the previous steps) into sol.
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ Lbuf, long long ld, int kt, double* __restrict__ dinv,
                                                             int* info, const double* __restrict__ rhs, double* __restrict__ sol,
-                                                            int Npad, int p) {
+                                                            int Npad, int p, long long* __restrict__ prof = nullptr) {
     extern __shared__ __align__(16) double sm[];
     __shared__ double ys[MAXP][TS];
+    // prof (developer hook, gptb_test_potrf_tile): clock64 at the phase boundaries, written by thread 0
+    int pslot = 0;
+    auto stamp = [&]() { if (prof != nullptr && threadIdx.x == 0) prof[pslot] = clock64(); ++pslot; };
+    stamp();
     if (rhs != nullptr)
         for (int e = threadIdx.x; e < p * TS; e += 256) ys[e / TS][e % TS] = rhs[(long long)(e / TS) * Npad + kt * TS + (e % TS)];
     double* S = sm;                         // [128][DLD]
@@ -223,6 +227,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
         S[r * DLD + c2 + 1] = v.y;
     }
     __syncthreads();
+    stamp();                                 // 1: tile loaded
     // ---- blocked Cholesky, 32-wide block columns -----------------------------------------------------------------
     for (int b = 0; b < TS / DB; ++b) {
         const int j0 = b * DB;
@@ -239,6 +244,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
             }
         }
         __syncthreads();
+        stamp();                             // 2, 4, 6, 8: 32 x 32 block factorised + inverted by warp 0
         const int rem = TS - j0 - DB;
         if (rem > 0) {
             // panel: rows below the block times the block inverse (in place)
@@ -250,6 +256,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
                                     rem, rem, DB, -1.0, 1.0, true);
             __syncthreads();
         }
+        stamp();                             // 3, 5, 7, 9: panel + trailing update inside the tile
     }
     // ---- write L (lower) and its mirror (upper) back ---------------------------------------------------------------
     for (int e = tid; e < TS * TS; e += 256) {
@@ -257,6 +264,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
         tile[(long long)r * ld + c] = (c <= r) ? S[r * DLD + c] : S[c * DLD + r];
     }
     __syncthreads();
+    stamp();                                 // 10: L written back
     // ---- inverse: off-diagonal 32-blocks, block row by block row.  (Linv_ij)^T is kept in S's upper block (j,i). ----
     for (int i = 1; i < TS / DB; ++i) {
         // Tm[:, 32j..32j+31] = L_ij Linv_jj + sum_{k=j+1}^{i-1} L_ik Linv_kj        for every j < i
@@ -273,6 +281,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
         smem_gemm<true, false>(S + i * DB, DLD, Tm, DLD, Zd + i * DB * ZLD, ZLD, i * DB, DB, DB, -1.0, 0.0, false);
         __syncthreads();
     }
+    stamp();                                 // 11: off-diagonal blocks of the inverse
     double* dk = dinv + (long long)kt * TS * TS;
     for (int e = tid; e < TS * TS; e += 256) {
         int r = e >> 7, c = e & 127;
@@ -295,6 +304,8 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
         }
         for (int q = 0; q < p; ++q) sol[(long long)q * Npad + kt * TS + r] = z[q];
     }
+    __syncthreads();
+    stamp();                                 // 12: inverse written, forward substitution done
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -840,6 +851,117 @@ __global__ void __launch_bounds__(256) lml_grad_reduce_kernel(const double* __re
             else grad[1 + (v - 2)] = 0.5 * tot;
         }
         __syncthreads();
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Rank-1 append of one training point at fixed hyper-parameters (the greedy loop of gaussian_process_al.py:26-55 adds one point per
+// iteration; with fixed hyper-parameters its re-fit is exactly this update).  With M = L^-1 (lower + mirror) and the new point's
+// kernel vector k:   l = M k,  dd = sqrt(k** - l.l),  new row of L = [l, dd],  new row of M = [r, 1/dd] with r = -(l^T M)/dd,
+// alpha <- [alpha + r^T z_n ; z_n/dd] with z_n = r.Y + y_n/dd.   O(N^2) memory-bound work instead of the O(N^3) re-factorisation.
+// ------------------------------------------------------------------------------------------------------------
+struct NewPoint {
+    double x[MAXD], xs[MAXD], y[MAXP];
+};
+
+__global__ void __launch_bounds__(256) append_kvec_kernel(const double* __restrict__ Xs, int N, int Npad, int d, NewPoint np, KParams kp,
+                                                          double* __restrict__ kv) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Npad) return;
+    double v = 0.0;
+    if (j < N) {
+        double sq = 0.0;
+        for (int a = 0; a < d; ++a) {
+            const double df = np.xs[a] - Xs[(long long)a * Npad + j];
+            sq = fma(df, df, sq);
+        }
+        v = kp.c * kernel_profile(sq, kp.kind, [](double z) { return exp(z); });
+    }
+    kv[j] = v;
+}
+
+// out[i] = sum_{j <= i} M[i][j] v[j], i < N (one warp per row of the lower triangle)
+__global__ void __launch_bounds__(256) gemv_lower_rows_kernel(const double* __restrict__ M, long long ld, int N, const double* __restrict__ v,
+                                                              double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= N) return;
+    const double* row = M + (long long)i * ld;
+    double s = 0.0;
+    for (int j = lane; j <= i; j += 32) s = fma(row[j], v[j], s);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) out[i] = s;
+}
+
+// scal[0] = dd = sqrt(kss - l.l) (0 when not positive), fixed-order reduction
+__global__ void __launch_bounds__(1024) append_pivot_kernel(const double* __restrict__ l, int N, double kss, double* __restrict__ scal) {
+    __shared__ double red[1024];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < N; i += 1024) s = fma(l[i], l[i], s);
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 512; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double d2 = kss - red[0];
+        scal[0] = d2 > 0.0 ? sqrt(d2) : 0.0;
+    }
+}
+
+// r[j] = -(1/dd) (l[j] M[j][j] + sum_{j < i < N} l[i] M[i][j]); M[i][j] for i > j is read from the mirror (row j, column i): contiguous
+__global__ void __launch_bounds__(256) gemv_mirror_rows_kernel(const double* __restrict__ M, long long ld, int N, const double* __restrict__ l,
+                                                               const double* __restrict__ scal, double* __restrict__ r) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (j >= N) return;
+    const double* row = M + (long long)j * ld;
+    double s = 0.0;
+    for (int i = j + lane; i < N; i += 32) s = fma(row[i], l[i], s);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) r[j] = -s / scal[0];
+}
+
+// write the new row / mirror column of L and M, the last diagonal tile's explicit inverse, the new training point and alpha
+__global__ void __launch_bounds__(1024) append_write_kernel(double* __restrict__ Lbuf, double* __restrict__ Minv, double* __restrict__ dinv, long long ld,
+                                                            int N, int Npad, int d, int p, const double* __restrict__ l, const double* __restrict__ r,
+                                                            const double* __restrict__ scal, NewPoint np, double* __restrict__ X, double* __restrict__ Xs,
+                                                            double* __restrict__ Y, double* __restrict__ alpha) {
+    __shared__ double red[MAXP][1024];
+    const int n = N;                                            // index of the new point
+    const double dd = scal[0], idd = 1.0 / dd;
+    double zacc[MAXP] = {0.0, 0.0, 0.0, 0.0};
+    for (int j = threadIdx.x; j < N; j += 1024) {
+        const double lj = l[j], rj = r[j];
+        Lbuf[(long long)n * ld + j] = lj;
+        Lbuf[(long long)j * ld + n] = lj;
+        Minv[(long long)n * ld + j] = rj;
+        Minv[(long long)j * ld + n] = rj;
+        for (int q = 0; q < p; ++q) zacc[q] = fma(rj, Y[(long long)q * Npad + j], zacc[q]);
+    }
+    for (int q = 0; q < MAXP; ++q) red[q][threadIdx.x] = zacc[q];
+    __syncthreads();
+    for (int w = 512; w > 0; w >>= 1) {
+        if (threadIdx.x < w)
+            for (int q = 0; q < MAXP; ++q) red[q][threadIdx.x] += red[q][threadIdx.x + w];
+        __syncthreads();
+    }
+    double zn[MAXP];
+    for (int q = 0; q < MAXP; ++q) zn[q] = (q < p) ? red[q][0] + np.y[q] * idd : 0.0;
+    for (int j = threadIdx.x; j < N; j += 1024)
+        for (int q = 0; q < p; ++q) alpha[(long long)q * Npad + j] += r[j] * zn[q];
+    const int tile0 = (n / TS) * TS, nl = n - tile0;
+    double* dk = dinv + (long long)(n / TS) * TS * TS;
+    for (int c = threadIdx.x; c < TS; c += 1024) dk[nl * TS + c] = (c < nl) ? r[tile0 + c] : (c == nl ? idd : 0.0);
+    if (threadIdx.x == 0) {
+        Lbuf[(long long)n * ld + n] = dd;
+        Minv[(long long)n * ld + n] = idd;
+        for (int a = 0; a < d; ++a) { X[(long long)a * Npad + n] = np.x[a]; Xs[(long long)a * Npad + n] = np.xs[a]; }
+        for (int q = 0; q < p; ++q) { Y[(long long)q * Npad + n] = np.y[q]; alpha[(long long)q * Npad + n] = zn[q] * idd; }
     }
 }
 

@@ -1340,6 +1340,67 @@ static void release_big_scratch(gptb_handle* h) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// rank-1 append of a training point at the current hyper-parameters
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int gptb_append_point(gptb_handle* h, const double* x, const double* y, double* lml) {
+    if (!h || !x || !y) return -1;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->have_train || !h->have_factor || !h->have_alpha) GPTB_FAIL(h, -1, "gptb_append_point: no fitted model (gptb_set_train + gptb_factorize first)");
+    const int d = h->d, p = h->p;
+    const long long N = h->N, Npad = h->Npad;
+    int rc = 0;
+    if (N == Npad) {
+        // no room in the last 128-row tile: the N x N buffers have to grow -- re-factorise once with the point included (every 128th append)
+        std::vector<double> xs((size_t)d * Npad), ys((size_t)p * Npad), X2((size_t)(N + 1) * d), Y2((size_t)(N + 1) * p);
+        CU(h, cudaMemcpyAsync(xs.data(), h->X, sizeof(double) * d * Npad, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaMemcpyAsync(ys.data(), h->Y, sizeof(double) * p * Npad, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        const std::vector<int> perm = h->perm;
+        for (long long n = 0; n < N; ++n) {
+            const long long dst = perm.empty() ? n : perm[(size_t)n];           // back to the caller's order
+            for (int a = 0; a < d; ++a) X2[(size_t)dst * d + a] = xs[(size_t)a * Npad + n];
+            for (int o = 0; o < p; ++o) Y2[(size_t)dst * p + o] = ys[(size_t)o * Npad + n];
+        }
+        for (int a = 0; a < d; ++a) X2[(size_t)N * d + a] = x[a];
+        for (int o = 0; o < p; ++o) Y2[(size_t)N * p + o] = y[o];
+        const KParams kp = h->kp;
+        if ((rc = gptb_set_train(h, X2.data(), Y2.data(), N + 1, d, p))) return rc;
+        if ((rc = gptb_factorize(h, kp.c, kp.ell, kp.s2, kp.jitter, lml))) return rc;
+        return build_minv(h);
+    }
+    if ((rc = build_minv(h))) return rc;
+    NewPoint np{};
+    for (int a = 0; a < d; ++a) { np.x[a] = x[a]; np.xs[a] = x[a] / h->kp.ell[a]; }
+    for (int o = 0; o < p; ++o) np.y[o] = y[o];
+    Carver cv;
+    const size_t o_kv = cv.add((size_t)Npad), o_l = cv.add((size_t)Npad), o_r = cv.add((size_t)Npad);
+    if ((rc = ensure_scratch(h, cv.need))) return rc;
+    double *kv = reinterpret_cast<double*>(h->scratch + o_kv), *l = reinterpret_cast<double*>(h->scratch + o_l), *r = reinterpret_cast<double*>(h->scratch + o_r);
+    double* scal = h->scal + 48;
+    append_kvec_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, h->stream>>>(h->Xs, (int)N, (int)Npad, d, np, h->kp, kv);
+    LAUNCH_CHECK(h);
+    gemv_lower_rows_kernel<<<(unsigned)((N + 7) / 8), 256, 0, h->stream>>>(h->Minv, Npad, (int)N, kv, l);
+    LAUNCH_CHECK(h);
+    append_pivot_kernel<<<1, 1024, 0, h->stream>>>(l, (int)N, h->kp.c + h->kp.s2 + h->kp.jitter, scal);
+    LAUNCH_CHECK(h);
+    double dd = 0.0;
+    CU(h, cudaMemcpyAsync(&dd, scal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (!(dd > 0.0)) GPTB_FAIL(h, (int)(N + 1), "the kernel matrix is not positive definite: leading minor of order %lld (appended point)", N + 1);
+    gemv_mirror_rows_kernel<<<(unsigned)((N + 7) / 8), 256, 0, h->stream>>>(h->Minv, Npad, (int)N, l, scal, r);
+    LAUNCH_CHECK(h);
+    append_write_kernel<<<1, 1024, 0, h->stream>>>(h->Lbuf, h->Minv, h->Dinv, Npad, (int)N, (int)Npad, d, p, l, r, scal, np, h->X, h->Xs, h->Y, h->alpha);
+    LAUNCH_CHECK(h);
+    h->N = N + 1;
+    if (!h->perm.empty()) h->perm.push_back((int)N);           // spatial mode: appended points follow the Morton-ordered ones
+    h->have_kinv = false;
+    invalidate_planes(h);
+    if (lml) return lml_value(h, lml);
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // minimum-variance stabilised rollouts, device-resident (one CUDA graph per step shape, replayed `steps` times)
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int gptb_rollout_min_variance(gptb_handle* h, const double* start, int64_t K, int steps, double gain, double* traj) {
@@ -1801,7 +1862,9 @@ extern "C" int gptb_test_potrf_tile(gptb_handle* h, const double* A128, double* 
     CU(h, cudaMalloc(&dI, sizeof(double) * TS * TS));
     CU(h, cudaMemcpyAsync(dA, A128, sizeof(double) * TS * TS, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
-    potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->stream>>>(dA, TS, 0, dI, h->info, nullptr, nullptr, TS, 0);
+    long long* prof = nullptr;                   // phase clocks of the diagonal-tile kernel (developer record: gptb_debug_read_profile)
+    if (h->oz_prof) prof = reinterpret_cast<long long*>(h->oz_prof);
+    potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->stream>>>(dA, TS, 0, dI, h->info, nullptr, nullptr, TS, 0, prof);
     LAUNCH_CHECK(h);
     CU(h, cudaMemcpyAsync(L128, dA, sizeof(double) * TS * TS, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(Linv128, dI, sizeof(double) * TS * TS, cudaMemcpyDeviceToHost, h->stream));

@@ -282,6 +282,24 @@ class GaussianProcess:
     def derivative_of_variance(self, x):
         return self._query(x, _lib.DVAR)["dvar"]
 
+    # -- rank-1 growth of the training set at the fitted hyper-parameters ---------------------------------------------------------
+    def append(self, x, y):
+        """Add ONE training pair (x (d,), y (p,)) to the fitted model without re-optimising the hyper-parameters: what a re-`fit` with
+        `optimizer=None` (or an all-fixed kernel) on the extended set computes, as an O(N^2) update of L, L^-1 and alpha on the device
+        (include/gptb200.h gptb_append_point) instead of an O(N^3) re-factorisation.  The greedy active-learning loop of
+        models/gaussian_process_al.py:41-55 is the caller."""
+        self._ensure_fitted_factor()
+        x = np.asarray(x, dtype=np.float64).reshape(1, -1)
+        y = np.asarray(y, dtype=np.float64).reshape(1, -1)
+        info, lml = self._engine.append_point(x, y, want_lml=True)
+        if info > 0:
+            raise np.linalg.LinAlgError(f"The kernel, {self.kernel}, is not returning a positive definite matrix ({info}-th leading minor).")
+        self.X = np.vstack([self.X, x])
+        self.Y = np.vstack([self.Y, y])
+        self.n_samples = self.X.shape[0]
+        self.gp.log_marginal_likelihood_value_ = lml
+        self._K_inv = None
+
     # -- minimum-variance stabilisation (plot_utils.py:283-317): the two query shapes of the reference's plotting helpers -------------
     def minimum_variance_field(self, x, gain=2.0):
         """vel - gain * std * g / |g| with g = derivative_of_variance (plot_utils.plot_vector_field_minvar:286-289, gain 2): one fused

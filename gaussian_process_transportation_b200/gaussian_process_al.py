@@ -50,8 +50,12 @@ class GaussianProcess():
                 Y_sample = np.vstack([Y_sample, Y_tmp[query_idx]])
                 X_tmp = np.delete(X_tmp, query_idx, axis=0)
                 Y_tmp = np.delete(Y_tmp, query_idx, axis=0)
-                with contextlib.redirect_stdout(quiet):
-                    gp_active.fit(X_sample, Y_sample)
+                if gp_active.gp.optimizer is None or gp_active.gp.kernel_.n_dims == 0:
+                    # nothing to optimise (all hyper-parameters fixed): the re-fit is a rank-1 update of the factor on the device
+                    gp_active.append(X_sample[-1], Y_sample[-1])
+                else:
+                    with contextlib.redirect_stdout(quiet):
+                        gp_active.fit(X_sample, Y_sample)
             mean = gp_active.predict(self.X)
             error = np.mean(np.sum(np.abs(mean - self.X), axis=1))        # sic: compared against the INPUTS (file:57)
             print("error:", error)

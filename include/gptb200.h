@@ -63,6 +63,13 @@ int gptb_set_kernel_kind(gptb_handle* h, int kind);
  * (sklearn:_gpr.py:613-617).  Non-PD => returns the failing order (>0). */
 int gptb_factorize(gptb_handle* h, double c, const double* ell, double s2, double jitter, double* lml);
 
+/* ---- append ONE training point (x (d), y (p)) to a fitted model at its current hyper-parameters: the re-fit of the greedy
+ * active-learning loop (gaussian_process_al.py:41-55 adds the pool point of largest predictive std and calls fit again) when the
+ * hyper-parameters are fixed.  Rank-1 update of L, L^-1, alpha in O(N^2) instead of the O(N^3) re-factorisation; every 128th point
+ * (a new row tile) re-factorises.  *lml (may be NULL) receives the log marginal likelihood of the extended model.  Returns the
+ * order of the non-positive leading minor (> 0) when the extended kernel matrix is not positive definite. */
+int gptb_append_point(gptb_handle* h, const double* x, const double* y, double* lml);
+
 /* ---- one log-marginal-likelihood evaluation with gradient w.r.t. log-hyper-parameters, the objective that
  * scipy's L-BFGS-B drives in sklearn:_gpr.py:302-309,541-656.  grad has 2+d entries:
  * [d/dlog c, d/dlog ell_0 .. ell_{d-1}, d/dlog s2]; an isotropic kernel's gradient is the sum of the ell entries.

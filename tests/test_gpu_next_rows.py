@@ -191,3 +191,62 @@ def test_min_variance_rollouts_and_field_vs_oracle_loop():
     vel, std = ora.predict(grid, return_std=True)
     g = ora.derivative_of_variance(grid).transpose()
     assert np.allclose(mine.minimum_variance_field(grid), vel - 2 * std * g / np.linalg.norm(g, axis=1).reshape(-1, 1), rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("spatial", [False, True])
+def test_rank1_append_matches_full_refit(spatial):
+    """f4: gptb_append_point -- growing a fitted model one point at a time (across a 128-row tile boundary) gives the factor, alpha,
+    LML and posterior of a fit on the whole set."""
+    from gaussian_process_transportation_b200 import _lib as L
+    rng = np.random.default_rng(8)
+    X = rng.random((300, 3)); Y = 0.05 * np.sin(4 * X) + 0.01 * rng.standard_normal((300, 3))
+    xq = rng.random((200, 3))
+    theta = (0.1, [0.1, 0.15, 0.2], 1e-4, 1e-10)
+    inc, full = L.Engine(0), L.Engine(0)
+    inc.set_spatial(spatial)
+    n0 = 120                                           # 120 -> 300 crosses the 128- and 256-row boundaries
+    inc.set_train(X[:n0], Y[:n0])
+    inc.factorize(*theta)
+    for i in range(n0, 300):
+        info, lml_inc = inc.append_point(X[i], Y[i], want_lml=True)
+        assert info == 0
+    full.set_train(X, Y)
+    info, lml_full = full.factorize(*theta)
+    assert inc.N == 300 and abs(lml_inc - lml_full) < 1e-9 * abs(lml_full)
+    assert rel(inc.export_alpha(), full.export_alpha()) < 1e-9
+    if not spatial:
+        assert rel(inc.export_L(), full.export_L()) < 1e-12
+    fl = L.MEAN | L.STD | L.JAC | L.JACVAR
+    a, b = inc.query(xq, fl), full.query(xq, fl)
+    assert rel(a["mean"], b["mean"]) < 1e-10 and rel(a["jac"], b["jac"]) < 1e-10
+    assert np.max(np.abs(a["std"] - b["std"])) < 1e-10 and rel(a["jacvar"], b["jacvar"]) < 1e-8
+    # a duplicate of a training point with zero noise is not positive definite: reported like a failed factorisation
+    sing = L.Engine(0)
+    sing.set_train(X[:50], Y[:50])
+    sing.factorize(0.1, [0.1] * 3, 0.0, 0.0)
+    info, _ = sing.append_point(X[7], Y[7])
+    assert info == 51
+
+
+def test_active_learning_fixed_kernel_uses_appends_and_matches_oracle(monkeypatch):
+    """GP-AL with an all-fixed kernel: every greedy step is a rank-1 append; the selected subset and the final model match the oracle's
+    loop (which re-fits sklearn's regressor from scratch at every step)."""
+    import gaussian_process_transportation_b200 as pkg
+    from gaussian_process_transportation_b200.gaussian_process_al import GaussianProcess as GPAL
+    from oracle.gp_oracle import OracleGPAL
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+    rng = np.random.default_rng(11)
+    X = rng.random((90, 2)); Y = np.stack([np.sin(3 * X[:, 0]), np.cos(2 * X[:, 1])], axis=1)
+    k = C(0.5, constant_value_bounds="fixed") * RBF([0.3, 0.3], length_scale_bounds="fixed") + WhiteKernel(1e-3, noise_level_bounds="fixed")
+    calls = {"append": 0}
+    orig = pkg.GaussianProcess.append
+    monkeypatch.setattr(pkg.GaussianProcess, "append", lambda self, x, y: (calls.__setitem__("append", calls["append"] + 1), orig(self, x, y))[1])
+    mine, ora = GPAL(k, n_samples_max=40), OracleGPAL(k, n_samples_max=40)
+    with contextlib.redirect_stdout(io.StringIO()):
+        np.random.seed(5); mine.fit(X, Y)
+        np.random.seed(5); ora.fit(X, Y)
+    assert calls["append"] == 36                       # 40 - int(0.1 * 40) greedy additions, none of them a re-fit
+    assert np.array_equal(mine.X, ora.X)
+    xq = rng.random((50, 2))
+    (m1, s1), (m2, s2) = mine.predict(xq), ora.predict(xq)
+    assert rel(m1, m2) < 1e-9 and np.max(np.abs(s1 - s2)) < 1e-8
