@@ -90,7 +90,7 @@ class _Regressor:
 
 class GaussianProcess:
     def __init__(self, kernel, alpha=1e-10, optimizer='fmin_l_bfgs_b', n_restarts_optimizer=5, n_targets=None, device=None,
-                 variance_mode=None, spatial=None):
+                 variance_mode=None, spatial=None, parallel_restarts=None):
         check_supported(kernel)
         if optimizer is None:
             n_restarts_optimizer = 0                     # gaussian_process.py:18-21 (sklearn default)
@@ -105,6 +105,12 @@ class GaussianProcess:
         self._variance_mode = variance_mode or _os.environ.get("GPTB_VARIANCE_MODE", "fp64")
         # spatial mode (include/gptb200.h: Morton-ordered training points, sorted query batches, zero-plane skipping); GPTB_SPATIAL=1
         self._spatial = bool(int(_os.environ.get("GPTB_SPATIAL", "0"))) if spatial is None else bool(spatial)
+        # small-N fits are launch-latency bound (tens of microsecond kernels, a host round trip per objective evaluation): the optimiser
+        # restarts are independent L-BFGS-B runs, so they can run concurrently, one engine handle (= one stream set) per run, the
+        # GPU interleaving their kernels.  Same start points (drawn up front from the global RNG in the same order), same runs, same
+        # arg-min as the sequential loop of sklearn:_gpr.py:312-337.  Opt-in (GPTB_PARALLEL_RESTARTS=1 sets the default).
+        self._parallel_restarts = bool(int(_os.environ.get("GPTB_PARALLEL_RESTARTS", "0"))) if parallel_restarts is None else bool(parallel_restarts)
+        self._restart_engines = []
         self._engine_obj = None
         self._factor_theta = None
         self._K_inv = None
@@ -160,10 +166,12 @@ class GaussianProcess:
                     return -lml, -grad
                 return -gp.log_marginal_likelihood(theta, clone_kernel=False)
 
-            optima = [self._constrained_optimization(obj_func, kernel_.theta, kernel_.bounds)]
-            if gp.n_restarts_optimizer > 0:
-                if not np.isfinite(kernel_.bounds).all():
-                    raise ValueError("Multiple optimizer restarts (n_restarts_optimizer>0) requires that all bounds are finite.")
+            if gp.n_restarts_optimizer > 0 and not np.isfinite(kernel_.bounds).all():
+                raise ValueError("Multiple optimizer restarts (n_restarts_optimizer>0) requires that all bounds are finite.")
+            if self._parallel_restarts and gp.n_restarts_optimizer > 0:
+                optima = self._optimise_concurrently(kernel_, rng)
+            else:
+                optima = [self._constrained_optimization(obj_func, kernel_.theta, kernel_.bounds)]
                 bounds = kernel_.bounds
                 for _ in range(gp.n_restarts_optimizer):
                     theta_initial = rng.uniform(bounds[:, 0], bounds[:, 1])
@@ -195,6 +203,37 @@ class GaussianProcess:
         self.noise_var_ = gp.alpha + prm['k2__noise_level']
         self.prior_var = prm['k1__k1__constant_value']
         print('lenghtscales', prm['k1__k2__length_scale'])
+
+    def _optimise_concurrently(self, kernel_, rng):
+        """Run 0 (from the kernel's theta) and the restarts as concurrent L-BFGS-B runs, one scratch engine each."""
+        from concurrent.futures import ThreadPoolExecutor
+        gp, eng = self.gp, self._engine
+        bounds = kernel_.bounds
+        starts = [np.array(kernel_.theta, copy=True)] + [rng.uniform(bounds[:, 0], bounds[:, 1]) for _ in range(gp.n_restarts_optimizer)]
+        while len(self._restart_engines) < len(starts) - 1:
+            self._restart_engines.append(_lib.Engine(eng.device))
+        engines = [eng] + self._restart_engines[:len(starts) - 1]
+        for e in engines[1:]:
+            e.set_kernel_kind(kernel_kind(kernel_))
+            e.set_train(self.X, self.Y)
+
+        def run(i):
+            e = engines[i]
+
+            def obj(theta, eval_gradient=True):
+                k = kernel_.clone_with_theta(theta)              # per-evaluation clone: the runs share no mutable kernel object
+                c, ell, s2 = read_params(k, e.d)
+                info, lml, g = e.lml(c, ell, s2, gp.alpha, want_grad=eval_gradient)
+                if info > 0:
+                    return (np.inf, np.zeros_like(theta)) if eval_gradient else np.inf
+                return (-lml, -map_gradient(k, g, e.d)) if eval_gradient else -lml
+
+            return self._constrained_optimization(obj, starts[i], bounds)
+
+        with ThreadPoolExecutor(max_workers=len(starts)) as pool:
+            optima = list(pool.map(run, range(len(starts))))
+        self._factor_theta = None
+        return optima
 
     def _constrained_optimization(self, obj_func, initial_theta, bounds):
         gp = self.gp

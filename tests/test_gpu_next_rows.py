@@ -250,3 +250,22 @@ def test_active_learning_fixed_kernel_uses_appends_and_matches_oracle(monkeypatc
     xq = rng.random((50, 2))
     (m1, s1), (m2, s2) = mine.predict(xq), ora.predict(xq)
     assert rel(m1, m2) < 1e-9 and np.max(np.abs(s1 - s2)) < 1e-8
+
+
+def test_concurrent_restarts_reproduce_the_sequential_fit():
+    """Batched small-N fits: the optimiser restarts as concurrent L-BFGS-B runs on separate engine handles give the sequential result."""
+    import gaussian_process_transportation_b200 as pkg
+    rng = np.random.default_rng(2)
+    X = rng.random((150, 2)); Y = np.stack([np.sin(4 * X[:, 0]) * X[:, 1], np.cos(3 * X[:, 1])], axis=1) + 0.01 * rng.standard_normal((150, 2))
+    k = kern(1.0, [0.5, 0.5], 1e-2)
+    fits = []
+    for par in (False, True):
+        gp = pkg.GaussianProcess(kernel=k, n_restarts_optimizer=4, parallel_restarts=par)
+        np.random.seed(3)
+        with contextlib.redirect_stdout(io.StringIO()):
+            gp.fit(X, Y)
+        fits.append(gp)
+    assert np.allclose(fits[0].kernel.theta, fits[1].kernel.theta, rtol=1e-9, atol=1e-9)
+    assert abs(fits[0].gp.log_marginal_likelihood_value_ - fits[1].gp.log_marginal_likelihood_value_) < 1e-9
+    xq = rng.random((40, 2))
+    assert rel(fits[1].predict(xq), fits[0].predict(xq)) < 1e-9
