@@ -443,7 +443,7 @@ def measure_queries(hs, L, eng, M, K, W, xq, variance, spatial, int8_peaks, dgem
     q_per_launch = M * K / max(trmm_n, 1)
     if int8:
         S_ = guard["used_slices"]
-        pairs = S_ * (S_ + 1) // 2
+        pairs = S_ * (S_ + 1) // 2 + (S_ - 1) * guard.get("used_extra_diagonal", 0)
         bits = 8 if variance[4] == "w" else 7
         T64 = Npad // 64
         ops_per_product = 2.0 * 128 * 64 * 64                      # one digit-plane pair on one 128 x 64 tile and one 64-byte k-chunk
@@ -460,7 +460,7 @@ def measure_queries(hs, L, eng, M, K, W, xq, variance, spatial, int8_peaks, dgem
         except Exception:
             pass
         out["roofline"] = {
-            "bound": "tensor", "kernel": f"ozaki_trmm_kernel<{S_}, {'true' if spatial else 'false'}> (tcgen05.mma kind::i8, TMEM accumulators, {pairs} products of {bits}-bit digit planes)",
+            "bound": "tensor", "kernel": f"ozaki_trmm_kernel<{S_}, {'true' if (spatial or guard.get('used_extra_diagonal')) else 'false'}{', 1' if guard.get('used_extra_diagonal') else ''}> (tcgen05.mma kind::i8, TMEM accumulators, {pairs} products of {bits}-bit digit planes)",
             "achieved": achieved, "peak": burst, "unit": "TOP/s (int8)", "frac": achieved / burst, "traffic": traffic,
             "traffic_unit": "bytes/launch (ncu dram read+write)", "peak_source": src, "peak_sustained": sustained,
             "frac_of_sustained": achieved / sustained if sustained else None,
@@ -621,7 +621,7 @@ def main():
     ap.add_argument("--no-c4", action="store_true", help="skip the config-4 block (N = 16384 fit / LML / broadcast / queries in the same run)")
     ap.add_argument("--no-small-n", action="store_true", help="skip the small-N latency block")
     ap.add_argument("--queries", type=int, default=0, help="override queries per step per GPU")
-    ap.add_argument("--variance", default="int8w5", choices=["fp64", "int8x5", "int8x6", "int8x7", "int8w4", "int8w5", "int8w6"],
+    ap.add_argument("--variance", default="int8w5", choices=["fp64", "int8x5", "int8x6", "int8x7", "int8w4", "int8w5", "int8w5p", "int8w6"],
                     help="evaluation of the predictive-variance products: FP64 DMMA tile engine, or the INT8-sliced tcgen05 path "
                          "(exact int32 digit-plane GEMMs, FP64 recombination): int8xS = S 7-bit digit planes, int8wS = S 8-bit digit planes; the "
                          "library's run-time guard may add planes (reported as variance_guard)")

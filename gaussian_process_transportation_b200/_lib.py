@@ -28,7 +28,7 @@ SYMBOLS = {
     "gptb_set_variance_mode": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "gptb_prepare_variance": (C.c_int, [C.c_void_p]),
     "gptb_set_variance_guard": (C.c_int, [C.c_void_p, C.c_double]),
-    "gptb_variance_guard_report": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), _dp, _dp, _dp]),
+    "gptb_variance_guard_report": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _dp, _dp, _dp]),
     "gptb_set_affine": (C.c_int, [C.c_void_p, _dp, C.c_double, _dp, _dp]),
     "gptb_query": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_uint32, _dp] + [_dp] * 9),
     "gptb_query_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p] + [C.c_void_p] * 9),
@@ -97,13 +97,16 @@ class GptbError(RuntimeError):
 
 
 def parse_variance_mode(name):
-    """'fp64' -> (0, 6); 'int8xS' -> (1, S) (7-bit digit planes); 'int8wS' -> (2, S) (8-bit digit planes)."""
+    """'fp64' -> (0, 6); 'int8xS' -> (1, S) (7-bit digit planes); 'int8wS' -> (2, S) (8-bit digit planes); 'int8w5p' -> (3, 5)
+    (five 8-bit planes plus the first dropped diagonal of plane products)."""
     vm = str(name).lower()
     if vm == "fp64":
         return 0, 6
+    if vm == "int8w5p":
+        return 3, 5
     if len(vm) == 6 and vm[:4] == "int8" and vm[4] in "xw" and vm[5].isdigit():
         return (1 if vm[4] == "x" else 2), int(vm[5])
-    raise ValueError(f"unknown variance_mode {name!r} (use 'fp64', 'int8x5'..'int8x7' or 'int8w4'..'int8w6')")
+    raise ValueError(f"unknown variance_mode {name!r} (use 'fp64', 'int8x5'..'int8x7', 'int8w4'..'int8w6' or 'int8w5p')")
 
 
 class Engine:
@@ -205,11 +208,12 @@ class Engine:
 
     def variance_guard(self):
         """What the guard decided for the current model: requested / used digit planes (0 = FP64 path), probe errors, threshold."""
-        rq, us = C.c_int(0), C.c_int(0)
+        rq, us, ex = C.c_int(0), C.c_int(0), C.c_int(0)
         e1, e0, th = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0)
-        self._check(self.lib.gptb_variance_guard_report(self.h, C.byref(rq), C.byref(us), C.byref(e1), C.byref(e0), C.byref(th)),
+        self._check(self.lib.gptb_variance_guard_report(self.h, C.byref(rq), C.byref(us), C.byref(ex), C.byref(e1), C.byref(e0), C.byref(th)),
                     "gptb_variance_guard_report")
-        return {"requested_slices": rq.value, "used_slices": us.value, "probe_err": e1.value, "first_err": e0.value, "threshold": th.value}
+        return {"requested_slices": rq.value, "used_slices": us.value, "used_extra_diagonal": ex.value, "probe_err": e1.value, "first_err": e0.value,
+                "threshold": th.value}
 
     def prepare_variance(self):
         self._check(self.lib.gptb_prepare_variance(self.h), "gptb_prepare_variance")

@@ -109,6 +109,7 @@ struct gptb_handle {
     int var_mode = 0, var_slices = 6, var_bits = 7;   // var_mode 1 = INT8-sliced; var_bits = digit width (7 balanced | 8 full range)
     // run-time accuracy guard of the INT8-sliced path (gptb_set_variance_guard): what the caller asked for, what the probe decided
     int var_mode_req = 0, var_slices_req = 6;
+    int var_extra = 0, var_extra_req = 0;     // 8-bit planes, S = 5: also form the first dropped diagonal a + b = S (19 products; ozaki.cuh)
     double guard_thresh = 2.0e-8;             // max |std_int8 - std_fp64| / sqrt(c + s2) on the probe set (a fifth of the 1e-7 tolerance); 0 = off
     bool guard_done = false, guard_busy = false;
     double guard_first_err = -1.0, guard_err = -1.0;
@@ -200,6 +201,7 @@ static void invalidate_planes(gptb_handle* h) {
     h->guard_done = false;
     h->var_mode = h->var_mode_req;
     h->var_slices = h->var_slices_req;
+    h->var_extra = h->var_extra_req;
 }
 
 static int set_kernel_attrs(gptb_handle* h) {
@@ -215,6 +217,7 @@ static int set_kernel_attrs(gptb_handle* h) {
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<4>::SMEM_SKIP_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<5>::SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<5>::SMEM_SKIP_BYTES));
+    CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<5, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<5>::SMEM_SKIP_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<6>::SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<6>::SMEM_SKIP_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<7>::SMEM_BYTES));
@@ -414,13 +417,18 @@ static int alloc_model(gptb_handle* h, long long N, int d, int p, bool train) {
 
 extern "C" int gptb_set_variance_mode(gptb_handle* h, int mode, int slices) {
     if (!h) return -1;
-    if (mode < 0 || mode > 2) GPTB_FAIL(h, -1, "unknown variance mode %d", mode);
+    if (mode < 0 || mode > 3) GPTB_FAIL(h, -1, "unknown variance mode %d", mode);
+    if (mode == 3 && slices != 5) GPTB_FAIL(h, -1, "the extra-diagonal variant exists for five 8-bit digit planes only (got %d)", slices);
+    const int extra = (mode == 3) ? 1 : 0;
+    if (mode == 3) mode = 2;
     if (mode == 1 && (slices < 5 || slices > 7)) GPTB_FAIL(h, -1, "the INT8-sliced variance path supports 5, 6 or 7 seven-bit digit planes (got %d)", slices);
     if (mode == 2 && (slices < 4 || slices > 6)) GPTB_FAIL(h, -1, "the INT8-sliced variance path supports 4, 5 or 6 eight-bit digit planes (got %d)", slices);
     const int bits = (mode == 2) ? 8 : 7;
+    const bool same = (mode >= 1) == (h->var_mode == 1) && (mode == 0 || (slices == h->var_slices && bits == h->var_bits && extra == h->var_extra));
     h->var_mode_req = mode >= 1 ? 1 : 0;
+    h->var_extra_req = extra;
     if (mode >= 1) { h->var_slices_req = slices; h->var_bits = bits; }
-    if (h->var_mode_req != h->var_mode || (mode >= 1 && (slices != h->var_slices || bits != h->var_bits)) || mode == 0) invalidate_planes(h);
+    if (!same || mode == 0) invalidate_planes(h);
     return 0;
 }
 
@@ -844,8 +852,13 @@ static int run_variance_guard(gptb_handle* h) {
         h->guard_err = err;
         if (err <= h->guard_thresh) break;
         const int smax = (h->var_bits == 8) ? 6 : 7;
+        if (h->var_bits == 8 && h->var_slices == 5 && !h->var_extra) {
+            h->var_extra = 1;                   // first the dropped diagonal a + b = S: 4 more products on the SAME planes (no rebuild)
+            continue;
+        }
         if (h->var_slices < smax) {
-            h->var_slices += 1;                 // one more digit plane per operand (2S+1 more plane products)
+            h->var_slices += 1;                 // one more digit plane per operand
+            h->var_extra = 0;
             h->have_bplanes = false;
             if ((rc = build_bplanes(h))) break;
             continue;
@@ -866,11 +879,12 @@ extern "C" int gptb_set_variance_guard(gptb_handle* h, double threshold) {
     return 0;
 }
 
-extern "C" int gptb_variance_guard_report(gptb_handle* h, int* requested_slices, int* used_slices, double* probe_err, double* first_err,
-                                          double* threshold) {
+extern "C" int gptb_variance_guard_report(gptb_handle* h, int* requested_slices, int* used_slices, int* used_extra_diagonal, double* probe_err,
+                                          double* first_err, double* threshold) {
     if (!h) return -1;
     if (requested_slices) *requested_slices = h->var_mode_req ? h->var_slices_req : 0;
     if (used_slices) *used_slices = h->var_mode ? h->var_slices : 0;
+    if (used_extra_diagonal) *used_extra_diagonal = (h->var_mode && h->var_slices == 5 && h->var_bits == 8) ? h->var_extra : 0;
     if (probe_err) *probe_err = h->guard_done ? h->guard_err : -1.0;
     if (first_err) *first_err = h->guard_done ? h->guard_first_err : -1.0;
     if (threshold) *threshold = h->guard_thresh;
@@ -1022,7 +1036,8 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
         const int T64 = (int)(h->Npad / oz::ON);
         oz::PlaneMaps mapsAq;
         const bool use_masks = spatial && h->spatial == 1;
-        const bool skipping = use_masks || h->oz_force_skip;
+        const bool extra = h->var_extra && S == 5 && h->var_bits == 8;        // S = 5 + the first dropped diagonal (skipping kernel only)
+        const bool skipping = use_masks || h->oz_force_skip || extra;
         if (!make_plane_maps(&mapsAq, Aplanes, rows_total, h->Npad, S, oz::OM, oz::OKB)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
         if (!fused) {
             tic(h, 3);
@@ -1040,7 +1055,12 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
             cudaMemsetAsync(h->info + 1, 0, sizeof(int), h->stream);      // dynamic tile counter
             const unsigned grid_oz = (unsigned)(ntiles < nsm ? ntiles : nsm);
-            if (skipping) {
+            if (skipping && extra) {
+                if constexpr (SV == 5)
+                    oz::ozaki_trmm_kernel<5, true, 1><<<grid_oz, oz::OTHREADS, oz::Cfg<5>::SMEM_SKIP_BYTES, h->stream>>>(
+                        mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, use_masks ? flagsA_slot : nullptr, use_masks ? h->flagsB : nullptr, h->flags_stride,
+                        exec_counter(h), h->oz_whatif, h->oz_prof);
+            } else if (skipping) {
                 oz::ozaki_trmm_kernel<SV, true><<<grid_oz, oz::OTHREADS, oz::Cfg<SV>::SMEM_SKIP_BYTES, h->stream>>>(
                     mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, use_masks ? flagsA_slot : nullptr, use_masks ? h->flagsB : nullptr, h->flags_stride,
                     exec_counter(h), h->oz_whatif, h->oz_prof);

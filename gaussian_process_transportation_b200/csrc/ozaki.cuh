@@ -276,33 +276,48 @@ struct TileMasks {
 // (6 KB per 32-cycle MMA = 192 B/clk) exceeded the 128 B/clk shared-memory port and capped the kernel at 2/3 of the
 // tensor rate (ncu: sm__throughput 88 %, tensor pipe 42 %).
 // ------------------------------------------------------------------------------------------------------------
-template <int S, int ZA, int ZB>
+// X = 1 adds the first DROPPED diagonal a + b = S (0-based planes) to the scheme: S + X diagonals, S(S+1)/2 + (S-1) products.  The CPU
+// study (tools/plane_error_study.py, profiles/r02_plane_error_study.log) shows that with 8-bit planes the std error of the S = 5
+// scheme is NOT the 40-bit operand truncation (5.5e-10 at N = 4096) but the dropped diagonal (9.0e-9); its four products recover
+// the truncation level for 27 % more MMA work and no extra operand traffic, where a sixth plane costs 40 % and 20 %.
+template <int S, int ZA, int ZB, int X = 0>
 __device__ __forceinline__ void oz_issue_chunk(uint64_t adesc0, uint64_t bdesc0, uint32_t tmem_base, uint32_t idesc_base, uint32_t first) {
-#pragma unroll
-    for (int a = ZA; a < S; ++a) {
-        const int nbp = S - a - ZB;                                     // B planes ZB .. S-1-a
-        if (nbp <= 0) continue;
-        const int ncols = ON * nbp;
+    constexpr int DMAX = S - 1 + X;                                     // last diagonal kept
+    // B planes blo .. bhi (0-based plane numbers, >= ZB) against A plane a; init: the first MMA overwrites instead of accumulating
+    auto issue = [&](int a, int blo, int bhi, bool init) {
+        const int ncols = ON * (bhi - blo + 1);
         const int nhalf = (ncols > 256) ? 2 : 1;
         const int nw = ncols / nhalf;                                   // multiple of 32
         const uint64_t ad = adesc0 + (uint64_t)(((a - ZA) * OM * OKB) >> 4);      // the stage holds A planes ZA.. and B planes ZB.. from slot 0
 #pragma unroll
         for (int hf = 0; hf < nhalf; ++hf) {
-            const uint64_t bd = bdesc0 + (uint64_t)(((hf * nw) * OKB) >> 4);
-            const uint32_t dcol = tmem_base + (uint32_t)((a + ZB) * ON + hf * nw);
+            const uint64_t bd = bdesc0 + (uint64_t)((((blo - ZB) * ON + hf * nw) * OKB) >> 4);
+            const uint32_t dcol = tmem_base + (uint32_t)((a + blo) * ON + hf * nw);
             const uint32_t idn = idesc_base | ((uint32_t)(nw >> 3) << 17);
 #pragma unroll
             for (int kk = 0; kk < OKB / 32; ++kk)
-                umma_i8(dcol, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idn, (a == 0 && kk == 0) ? (first ? 0u : 1u) : 1u);
+                umma_i8(dcol, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idn, (init && kk == 0) ? 0u : 1u);
+        }
+    };
+#pragma unroll
+    for (int a = ZA; a < S; ++a) {
+        const int bhi = (DMAX - a < S - 1) ? DMAX - a : S - 1;          // partner planes ZB .. bhi
+        if (bhi < ZB) continue;
+        if (first && X == 1 && a == 1) {
+            // chunk 0 zero-initialises the accumulators: plane 0 covers diagonals 0 .. S-1, the extra diagonal S is first touched here
+            issue(a, ZB, bhi - 1, false);
+            issue(a, bhi, bhi, true);
+        } else {
+            issue(a, ZB, bhi, first && a == 0);
         }
     }
 }
 // (za, zb) -> specialised issue code through one indexed branch
-template <int S>
+template <int S, int X = 0>
 __device__ __forceinline__ void oz_dispatch(int za, int zb, uint64_t adesc0, uint64_t bdesc0, uint32_t tmem_base, uint32_t idesc_base) {
 #define OZ_CASE(ZA, ZB)                                                                                     \
     case (ZA) * 8 + (ZB):                                                                                   \
-        if constexpr ((ZA) + (ZB) < S) oz_issue_chunk<S, (ZA), (ZB)>(adesc0, bdesc0, tmem_base, idesc_base, 0u); \
+        if constexpr ((ZA) + (ZB) <= S - 1 + X && (ZA) < S && (ZB) < S) oz_issue_chunk<S, (ZA), (ZB), X>(adesc0, bdesc0, tmem_base, idesc_base, 0u); \
         break;
 #define OZ_ROW(ZA) OZ_CASE(ZA, 0) OZ_CASE(ZA, 1) OZ_CASE(ZA, 2) OZ_CASE(ZA, 3) OZ_CASE(ZA, 4) OZ_CASE(ZA, 5) OZ_CASE(ZA, 6)
     switch (za * 8 + zb) {
@@ -311,6 +326,17 @@ __device__ __forceinline__ void oz_dispatch(int za, int zb, uint64_t adesc0, uin
     }
 #undef OZ_ROW
 #undef OZ_CASE
+}
+// planes of A / of B a chunk with za / zb leading zero planes needs, and the number of plane-pair products it carries (0: skip it)
+template <int S, int X>
+__device__ __forceinline__ void oz_chunk_planes(int za, int zb, int& nA, int& nB, int& npairs) {
+    constexpr int DMAX = S - 1 + X;
+    const int ahi = min(S - 1, DMAX - zb), bhi = min(S - 1, DMAX - za);
+    nA = ahi - za + 1;
+    nB = bhi - zb + 1;
+    npairs = 0;
+    if (nA <= 0 || nB <= 0) { nA = nB = 0; return; }
+    for (int a = za; a <= ahi; ++a) npairs += min(S - 1, DMAX - a) - zb + 1;
 }
 
 __device__ __forceinline__ void oz_tile_decode(long long idx, int T64, int rowtiles, int& rt, int& ti) {
@@ -331,7 +357,7 @@ __device__ __forceinline__ void oz_tile_decode(long long idx, int T64, int rowti
 // issue the same TMA loads and the same MMAs -- and neither the templated issue code, nor the run-time tensor-map index,
 // nor the converged-warp issue (which does remove the ELECT / R2UR waterfall around every UTCIMMA / UTMALDG) accounts for it.
 // Unexplained at the end of round 1; the dense path therefore stays on the loops it was tuned with.
-template <int S, bool SKIP>
+template <int S, bool SKIP, int X = 0>
 __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_constant__ PlaneMaps mapsA,
                                                                 const __grid_constant__ PlaneMaps mapsB,
                                                                 const double* __restrict__ scaleA, const double* __restrict__ scaleB,
@@ -497,8 +523,10 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
             for (int c = 0; c <= ti; ++c) {
                 int za, zb;
                 zr.get(c, za, zb);
-                const int n = S - za - zb;                  // planes za .. za+n-1 of A meet planes zb .. zb+n-1 of B
-                if (n <= 0) continue;                       // nothing but zeros in this chunk: no slot, no load
+                int nA, nB, npr;
+                oz_chunk_planes<S, X>(za, zb, nA, nB, npr);  // planes za .. za+nA-1 of A meet planes zb .. zb+nB-1 of B
+                if (npr == 0) continue;                     // nothing but zeros in this chunk: no slot, no load
+                const int n = max(nA, nB);                  // slots: one A plane + one B plane each
                 int base = head, need = n;
                 if (head + n > NSLOT) { need += NSLOT - head; base = 0; }      // no wrap inside a chunk: the tail slots ride along as padding
                 while (free_slots < need || inflight == NE) {                  // retire the oldest chunk(s)
@@ -515,9 +543,9 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                     if (wi & 1) {
                         mbar_expect_tx_a(fbar, 0);
                     } else {
-                        mbar_expect_tx_a(fbar, n * (OM + ON) * OKB);
-                        tma_load_3d_u8_a(smemA + base * C::SLOT_A, &mapsA.m[n - 1], c * OKB, rt * OM, za, fbar);
-                        tma_load_3d_u8_a(smemB + base * C::SLOT_B, &mapsB.m[n - 1], c * OKB, ti * ON, zb, fbar);
+                        mbar_expect_tx_a(fbar, (nA * OM + nB * ON) * OKB);
+                        tma_load_3d_u8_a(smemA + base * C::SLOT_A, &mapsA.m[nA - 1], c * OKB, rt * OM, za, fbar);
+                        tma_load_3d_u8_a(smemB + base * C::SLOT_B, &mapsB.m[nB - 1], c * OKB, ti * ON, zb, fbar);
                     }
                 }
                 ++inflight;
@@ -566,8 +594,10 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
             for (int c = 0; c <= ti; ++c) {
                 int za, zb;
                 zr.get(c, za, zb);
-                const int n = S - za - zb;
-                if (n <= 0) continue;
+                int nA, nB, npr;
+                oz_chunk_planes<S, X>(za, zb, nA, nB, npr);
+                if (npr == 0) continue;
+                const int n = max(nA, nB);
                 const int base = (head + n > NSLOT) ? 0 : head;
                 head = base + n;
                 const bool mine = (e3 == my);
@@ -576,7 +606,7 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                 if (++e3 == 3) e3 = 0;
                 if (++ej == NE) { ej = 0; epar ^= 1u; }
                 if (!mine) continue;
-                npairs += (unsigned)(n * (n + 1) / 2);
+                npairs += (unsigned)npr;
                 const uint64_t adesc0 = adescA + (uint64_t)((base * C::SLOT_A) >> 4), bdesc0 = bdescB + (uint64_t)((base * C::SLOT_B) >> 4);
                 mbar_wait_a(fbar, par);
                 if (!go_seen) {
@@ -586,8 +616,8 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 if (elect_one_sync()) {
                     if (!(wi & 2)) {
-                        if (c == 0) oz_issue_chunk<S, 0, 0>(adesc0, bdesc0, tmem_base, idesc_base, 1u);   // zero-initialises every column
-                        else oz_dispatch<S>(za, zb, adesc0, bdesc0, tmem_base, idesc_base);
+                        if (c == 0) oz_issue_chunk<S, 0, 0, X>(adesc0, bdesc0, tmem_base, idesc_base, 1u);   // zero-initialises every column
+                        else oz_dispatch<S, X>(za, zb, adesc0, bdesc0, tmem_base, idesc_base);
                     }
                     umma_commit_a(ebar);                    // the slots are free once these MMAs have read them
                     if (c == 0) mbar_arrive_a(tgo);         // the zero-initialising products are in the pipe: the other warps may issue
@@ -607,11 +637,12 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
         // arithmetic (|acc| < 2^31, so acc_d 2^2b + acc_d+1 2^b + acc_d+2 < 2^48: exact), each group is converted once through the
         // mantissa trick (exact below 2^51) and only the NG = ceil(S / 3) group values meet in FP64: 2 NG + 1 FP64 instructions per
         // output instead of 2 S -- the epilogue's FP64 work is what the next tile's first MMAs wait for (acc_empty).
-        constexpr int NG = (S + 2) / 3;
+        constexpr int ND = S + (SKIP ? X : 0);                  // diagonals held in TMEM
+        constexpr int NG = (ND + 2) / 3;
         double gw[NG];                                          // weight of the LAST diagonal of each group
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
-            const int dlast = (3 * g + 2 < S) ? 3 * g + 2 : S - 1;
+            const int dlast = (3 * g + 2 < ND) ? 3 * g + 2 : ND - 1;
             gw[g] = ldexp(1.0, -digit_bits * (dlast + 2));
         }
         for (int lt = 0;; ++lt) {
@@ -635,9 +666,9 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                 double v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = 0.0;
-                uint32_t r[S][16];
+                uint32_t r[ND][16];
 #pragma unroll
-                for (int d = 0; d < S; ++d) {          // all S diagonals of this column block in flight, one wait
+                for (int d = 0; d < ND; ++d) {         // all diagonals of this column block in flight, one wait
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(d * ON + cb * 16);
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
@@ -648,7 +679,7 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                 asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    const int d0 = 3 * g, cnt = (d0 + 3 <= S) ? 3 : S - d0;
+                    const int d0 = 3 * g, cnt = (d0 + 3 <= ND) ? 3 : ND - d0;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         long long acc = (long long)(int)r[d0][j];

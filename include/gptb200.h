@@ -85,19 +85,24 @@ int gptb_lml(gptb_handle* h, double c, const double* ell, double s2, double jitt
  * (tolerance 1e-7), 7 to ~1e-11; the posterior mean and Jacobian are unaffected.  mode 2 = the same evaluation with
  * `slices` in {4,5,6} 8-bit digit planes (the full int8 range): 5 planes (15 plane products instead of 21) give ~5e-9,
  * 6 give ~2e-11; limited to N <= 26112 by the worst-case exactness bound of the int32 accumulators (S * N * 2^14 < 2^31); beyond it the slicer's data-dependent
- * bound (128 * largest row sum of |digit| of the inverse factor < 2^31) decides, and the call fails if that does not hold either. */
+ * bound (128 * largest row sum of |digit| of the inverse factor < 2^31) decides, and the call fails if that does not hold either.
+ * mode 3 = mode 2 with slices = 5 plus the first DROPPED diagonal of plane products (a + b = S: 19 products instead of 15).  With
+ * 8-bit planes the error of the 15-product scheme is that dropped diagonal, not the 40-bit operands (tools/plane_error_study.py: std
+ * error 9.0e-9 -> 5.5e-10 at N = 4096), so this buys the accuracy of a sixth plane for 27 % instead of 40 % more tensor work and no
+ * extra operand traffic. */
 int gptb_set_variance_mode(gptb_handle* h, int mode, int slices);
 
 /* ---- run-time accuracy guard of the INT8-sliced path (on by default).  Before the first variance query of a model (and in
  * gptb_prepare_variance) 2048 probe queries -- half of them next to training points, where the std is most sensitive -- are
  * evaluated on the INT8 path and on the FP64 path of the same handle.  If max |std_int8 - std_fp64| / sqrt(c + s2) exceeds
  * `threshold` (default 2e-8, a fifth of the 1e-7 std tolerance of gaussian_process.py:46-49 parity) one digit plane is added and
- * the probe repeated; with the plane count exhausted the model is served by the FP64 path.  threshold = 0 switches the guard off.
+ * the probe repeated (five 8-bit planes first gain the extra diagonal of mode 3, which needs no new planes); with the plane count
+ * exhausted the model is served by the FP64 path.  threshold = 0 switches the guard off.
  * The report returns the requested and the effective plane count (0 = FP64 path), the probe error of the effective mode and the
  * one measured with the requested plane count. */
 int gptb_set_variance_guard(gptb_handle* h, double threshold);
-int gptb_variance_guard_report(gptb_handle* h, int* requested_slices, int* used_slices, double* probe_err, double* first_err,
-                               double* threshold);
+int gptb_variance_guard_report(gptb_handle* h, int* requested_slices, int* used_slices, int* used_extra_diagonal, double* probe_err,
+                               double* first_err, double* threshold);
 
 /* ---- spatial mode (call before gptb_set_train; off by default).  The training points are kept in Morton (Z-curve) order
  * inside the handle, every query batch of the INT8-sliced path with 8-bit planes is processed in Morton order too (radix sort

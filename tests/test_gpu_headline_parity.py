@@ -22,7 +22,7 @@ warnings.filterwarnings("ignore")
 TOL_STD = 1e-7
 STD_MARGIN = 4.0
 CASES = ["c3", "fitted", "snr1e4", "snr1e5", "long", "ard10"]
-MODES = [("fp64", False), ("int8w5", False), ("int8w5", True)]
+MODES = [("fp64", False), ("int8w5", False), ("int8w5", True), ("int8w5p", True), ("int8w5p", False)]
 
 
 def rel(a, b):
@@ -85,6 +85,16 @@ def test_variance_guard_promotes_or_falls_back(train):
     rep = eng.variance_guard()
     assert rep["requested_slices"] == 4 and (rep["used_slices"] > 4 or rep["used_slices"] == 0), rep
     assert rep["probe_err"] <= 2.5e-8, rep
+    # five planes asked for at a setting where 15 products are not enough: the guard adds the dropped diagonal before a sixth plane
+    mid = L.Engine(0)
+    mid.set_variance_mode("int8w5")
+    mid.set_spatial(True)
+    mid.set_train(train["X"], train["Y"])
+    mid.factorize(1.0, [0.3] * 3, 1e-4, 1e-10)           # the "snr1e4" setting: first probe error 1.4e-7
+    mid.prepare_variance()
+    rm = mid.variance_guard()
+    assert rm["first_err"] > rm["threshold"] and rm["used_slices"] == 5 and rm["used_extra_diagonal"] == 1 and rm["probe_err"] <= rm["threshold"], rm
+    mid.close()
     ref = L.Engine(0)
     ref.set_train(train["X"], train["Y"])
     ref.factorize(0.1, [0.1] * 3, 1e-4, 1e-10)

@@ -545,3 +545,51 @@ def test_spatial_mode_edge_shapes(pkg):
         assert np.max(np.abs(std - s0)) / np.sqrt(0.5 + 1e-3) < TOL_STD, (n, d, p, m)
         J = gp.derivative(xq)
         assert rel(J, np.reshape(ora.derivative(xq), np.shape(J))) < TOL_MEAN, (n, d, p, m)
+
+
+def test_integration_md_reference_side_stub_runs(golden_dir):
+    """INTEGRATION.md section 2 shows the ctypes stub a maintainer of the reference would add; this test executes that very code block
+    (only the library path is substituted) and checks it against a golden from the unmodified reference."""
+    import re
+    from gaussian_process_transportation_b200 import _lib as L
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = [b for b in blocks if "class GaussianProcessB200" in b]
+    assert len(stub) == 1
+    code = stub[0].replace('C.CDLL("libgptb200.so")', f'C.CDLL({L.LIB_PATH!r})')
+    ns = {}
+    exec(compile(code, "INTEGRATION.md#stub", "exec"), ns)
+    g = load(golden_dir, "syn_ard300.npz")
+    gp = ns["GaussianProcessB200"](float(g["c"]), g["ell"], float(g["s2"]))
+    gp.fit(g["X"], g["Y"])
+    mean, std = gp.predict(g["xq"], return_std=True)
+    J, V = gp.derivative(g["xq"], return_var=True)
+    assert rel(mean, g["mean"]) < TOL_MEAN and rel(J, g["J"]) < TOL_MEAN
+    assert np.max(np.abs(std - g["std"])) / np.sqrt(float(g["c"]) + float(g["s2"])) < TOL_STD
+    assert rel(V, g["Jvar"]) < 1e-6
+    assert rel(gp.predict(g["xq"]), g["mean"]) < TOL_MEAN
+
+
+def test_orientation_quaternion_against_scipy_rotation():
+    """Independent check of the orientation epilogue (numpy-quaternion is absent, so parity with the reference's dependency itself
+    stays unpinned): for a RIGID map (no residual: Jphi = R exactly orthogonal) the transported orientation must be
+    quat(R) * q with quat(R) from scipy's Rotation, which shares no code with the repo's Bar-Itzhack restatement."""
+    from scipy.spatial.transform import Rotation
+    import gaussian_process_transportation_b200 as pkg
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+    rng = np.random.default_rng(6)
+    S = rng.random((120, 3))
+    Rot = Rotation.from_euler("zyx", [35.0, -20.0, 50.0], degrees=True)
+    T = Rot.apply(S) + np.array([0.2, -0.1, 0.3])                   # exactly rigid: the residual GP learns zero
+    pt = pkg.PolicyTransportation(pkg.GaussianProcess(kernel=C(1e-6) * RBF([0.5] * 3) + WhiteKernel(1e-8), optimizer=None))
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        pt.fit(S, T)
+        q_in = Rotation.random(25, random_state=1)
+        pos = rng.random((25, 3))
+        wxyz = np.roll(q_in.as_quat(), 1, axis=1)                   # scipy is (x, y, z, w)
+        out = pt.transport_orientation(pos, wxyz)
+    expect = np.roll((Rot * q_in).as_quat(), 1, axis=1)
+    sign = np.sign(np.sum(out * expect, axis=1))[:, None]
+    assert np.max(np.abs(out * sign - expect)) < 1e-9
