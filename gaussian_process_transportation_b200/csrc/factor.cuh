@@ -163,42 +163,51 @@ __device__ __forceinline__ void smem_gemm(double* C, int ldc, const double* A, i
     }
 }
 
-// One warp: in-register Cholesky of a 32x32 block (lane i holds row i in a[0..31], lower part meaningful) followed by
-// the inverse of the factor.  On return a[] holds row i of L (entries above the diagonal are unspecified), x[] holds
-// COLUMN `lane` of L^-1 (x[r] = Linv[r][lane], zero for r < lane).  Returns the 1-based index of the first
-// non-positive pivot in the block, 0 if none.
-__device__ __forceinline__ int warp_potrf_trtri32(double (&a)[DB], double (&x)[DB], int lane) {
+// One warp: Cholesky of a 32x32 block (lane i holds row i in a[0..31], lower part meaningful) followed by the inverse of the
+// factor.  On return a[] holds row i of L (entries above the diagonal are unspecified), x[] holds COLUMN `lane` of L^-1
+// (x[r] = Linv[r][lane], zero for r < lane).  Returns the 1-based index of the first non-positive pivot in the block, 0 if none.
+// Broadcasts go through shared memory (`scratch`: 32*34 + 96 doubles, warp-private): the first version broadcast every L[k][j] with
+// a 64-bit shuffle (two SHFL each: 62 per column step, ~1000 for the inverse) and spent 63 % of the diagonal-tile kernel here
+// (tools/diag_prof.py: 19.7 k cycles per block); a column written once and read back with broadcast loads costs a fraction of that.
+constexpr int WB_LD = 34;                                        // row stride of the block copy (16-byte aligned rows)
+constexpr int WARP_BLOCK_SCRATCH = DB * WB_LD + 3 * DB;          // doubles
+__device__ __forceinline__ int warp_potrf_trtri32(double (&a)[DB], double (&x)[DB], int lane, double* scratch) {
     const unsigned full = 0xffffffffu;
+    double* Lb = scratch;                                        // [32][WB_LD]: the factor, row-major
+    double* col = scratch + DB * WB_LD;                          // [2][32]: current column of L, double-buffered
+    double* rinvs = col + 2 * DB;                                // [32]: 1 / L_jj
     int bad = 0;
-    double rinv_mine = 1.0;
 #pragma unroll
     for (int j = 0; j < DB; ++j) {
         const double d = __shfl_sync(full, a[j], j);
         if (!(d > 0.0) && bad == 0) bad = j + 1;
         const double piv = (d > 0.0) ? sqrt(d) : 1.0;
         const double rinv = (d > 0.0) ? rsqrt(d) : 1.0;        // independent of the sqrt: halves the pivot latency
-        if (lane == j) rinv_mine = rinv;
         const double l = (lane == j) ? piv : a[j] * rinv;     // column j of L (lanes > j); LAPACK dpotf2 scales by 1/ajj too
         a[j] = l;
+        double* cj = col + (j & 1) * DB;
+        cj[lane] = l;
+        if (lane == j) rinvs[j] = rinv;
+        __syncwarp();
 #pragma unroll
-        for (int k = j + 1; k < DB; ++k) {
-            const double lk = __shfl_sync(full, l, k);
-            a[k] = fma(-l, lk, a[k]);                          // rank-1 update (only i >= k is used later)
-        }
+        for (int k = j + 1; k < DB; ++k) a[k] = fma(-l, cj[k], a[k]);      // rank-1 update (only i >= k is used later)
     }
-    // inverse: lane c solves L x = e_c by forward substitution; L[r][k] is broadcast from lane r
+#pragma unroll
+    for (int c = 0; c < DB; ++c) Lb[lane * WB_LD + c] = a[c];
+    __syncwarp();
+    // inverse: lane c solves L x = e_c by forward substitution; L[r][k] is a broadcast load
 #pragma unroll
     for (int r = 0; r < DB; ++r) {
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int k = 0; k < r; ++k) {
-            const double lrk = __shfl_sync(full, a[k], r);
+            const double lrk = Lb[r * WB_LD + k];
             if (k & 1) s1 = fma(lrk, x[k], s1); else s0 = fma(lrk, x[k], s0);
         }
-        const double ri = __shfl_sync(full, rinv_mine, r);
         const double rhs = (r == lane) ? 1.0 : 0.0;
-        x[r] = (r < lane) ? 0.0 : (rhs - (s0 + s1)) * ri;
+        x[r] = (r < lane) ? 0.0 : (rhs - (s0 + s1)) * rinvs[r];
     }
+    __syncwarp();
     return bad;
 }
 
@@ -235,7 +244,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
             double a[DB], x[DB];
 #pragma unroll
             for (int c = 0; c < DB; ++c) a[c] = S[(j0 + lane) * DLD + j0 + c];
-            const int bad = warp_potrf_trtri32(a, x, lane);
+            const int bad = warp_potrf_trtri32(a, x, lane, Tm);        // Tm is free until the off-diagonal inverse phase
             if (bad && lane == 0) atomicCAS(info, 0, kt * TS + j0 + bad);
 #pragma unroll
             for (int c = 0; c < DB; ++c) {

@@ -92,6 +92,11 @@ if rank == 0:
                 "all_finite": bool(torch.isfinite(sums).all().item()), "guard_rank0_after_queries": eng.variance_guard()})
     idx = np.concatenate([s[0] for s in samples]); smp = np.vstack([s[1] for s in samples])
     rec["sample_points"] = int(len(idx))
+    try:        # kept for the CPU oracle check off the GPU box (tools/check_config5_samples.py)
+        os.makedirs("gpurun_out", exist_ok=True)
+        np.savez_compressed(f"gpurun_out/config5_samples_log2p{log2p}_N{N}.npz", idx=idx, sample=smp, dims=np.array(dims), origin=origin, step=step, aff=aff)
+    except Exception:
+        pass
     # the sampled lattice points through the ordinary host-pointer query of the same engine (explicit coordinates): the grid path adds nothing
     ii = np.stack(np.unravel_index(idx, dims), axis=1)
     xs = origin + step * ii
