@@ -219,6 +219,9 @@ struct PlaneMaps {
     CUtensorMap m[7];
 };
 
+// (Tried and backed out in round 2: the producer publishing the decoded codes in shared memory so that the issuing warps need not load
+// and decode the masks themselves -- the slot then stays busy until the issuing warps finish the tile, which throttles the producer's
+// run-ahead: c3 step 78.8 -> 79.7 ms, N = 16384 208.7 -> 220.0 ms; profiles/r02_pipeline_ab_v_published_codes_rejected.log.)
 // Block masks of one tile, skipping variant.  Each control warp loads its two mask rows ONCE per tile (one 16-byte load per lane and
 // operand: 16 mask bytes = 16 chunks), decodes them lane-parallel into (za*8 + zb) codes and then hands them out four chunks at a
 // time with one shuffle -- the earlier reader (ZeroPlaneReader) fetched one 32-bit word per four chunks with __ldg and decoded it
