@@ -126,6 +126,7 @@ struct gptb_handle {
     double* ws = nullptr;
     size_t ws_bytes = 0;
     long long ws_limit = 16LL << 30;
+    long long batch_cap = 131072;             // queries per batch (debug option "batch_cap"): 65536 -> 131072 measured 3-5 % faster (fewer sort / finalize / launch gaps per query)
     // staging for the host-pointer query: two device buffer sets, slices of HOST_SLICE queries; H2D of slice i+1 (s_h2d) and D2H of
     // slice i-1 (s_d2h) run under the kernels of slice i (main stream)
     double* stage[2] = {nullptr, nullptr};
@@ -324,6 +325,7 @@ extern "C" int gptb_set_debug_option(gptb_handle* h, const char* name, int value
     if (!strcmp(name, "spatial_shuffle")) h->spatial_shuffle = value != 0;
     else if (!strcmp(name, "oz_force_skip_variant")) h->oz_force_skip = value != 0;
     else if (!strcmp(name, "oz_whatif")) h->oz_whatif = value;
+    else if (!strcmp(name, "batch_cap")) { if (value < 128 || value % 128) GPTB_FAIL(h, -1, "batch_cap must be a multiple of 128"); h->batch_cap = value; }
     else GPTB_FAIL(h, -1, "gptb_set_debug_option: unknown option '%s'", name);
     return 0;
 }
@@ -1139,7 +1141,7 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
         long long bm = h->ws_limit / (nbuf * per_elem * nrhs * h->Npad);
         bm = bm / TS * TS;
         if (bm < TS) bm = TS;
-        if (bm > 65536) bm = 65536;
+        if (bm > h->batch_cap) bm = h->batch_cap;
         return bm;
     };
     long long Bmax = (nrhs > 0) ? batch_cap(1) : (1LL << 20);
@@ -1256,7 +1258,7 @@ extern "C" int gptb_query(gptb_handle* h, const double* x, int64_t M, uint32_t f
     const int d = h->d, p = h->p;
     if (d < 1) GPTB_FAIL(h, -1, "gptb_query: model is not fitted");
     if ((flags & GPTB_VELOCITY) && !vel) GPTB_FAIL(h, -1, "GPTB_VELOCITY without vel");
-    const int64_t HOST_SLICE = 1 << 16;
+    const int64_t HOST_SLICE = 1 << 17;
     struct Seg { const double* hin; double* hout; size_t per; size_t off; };
     Seg segs[11] = {{x, nullptr, (size_t)d, 0},
                     {(flags & GPTB_VELOCITY) ? vel : nullptr, nullptr, (size_t)d, 0},

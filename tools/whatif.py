@@ -84,6 +84,8 @@ def whatif(Ns):
 def pipeline():
     for N, M, ell in ((4096, 1 << 20, 0.1), (16384, 1 << 18, 0.1), (16384, 1 << 18, 0.68), (4096, 1 << 20, 0.68)):
         eng = engine(N, 1, ell)
+        if os.environ.get("BATCH_CAP"):
+            eng.set_debug_option("batch_cap", int(os.environ["BATCH_CAP"]))
         xd, kw, keep = buffers(M)
         st = torch.cuda.ExternalStream(eng.stream())
         res = {}
