@@ -686,6 +686,27 @@ def main():
         other_out = {"value": qo["value"], "unit": "query-points/s", "ms_per_step": qo["ms_per_step"], "roofline": qo.get("roofline")}
         eng.set_variance_mode(args.variance)
 
+    # ---- mode A0 (mean + Jacobian, no variance: SURVEY section 8d asks for it beside mode A) ----------------------
+    a0 = None
+    try:
+        fl0 = L.MEAN | L.JAC | L.AFFINE_IN
+        st0 = torch.cuda.ExternalStream(eng.stream(), device=dev)
+        x0 = torch.from_numpy(xq).to(dev)
+        m0 = torch.empty(M, p, dtype=torch.float64, device=dev)
+        j0 = torch.empty(M, p, d, dtype=torch.float64, device=dev)
+        step0 = lambda: eng.query_dev(x0.data_ptr(), M, fl0, 0, m0.data_ptr(), 0, j0.data_ptr())
+        step0()
+        ms0 = hs.timed(st0, step0, max(1, min(K, 3)))
+        if rank == 0:
+            qps0 = world * M * max(1, min(K, 3)) / (ms0 * 1e-3)
+            # FP64 instructions per (query, training point) pair from the ncu source view (profiles/r02_kstar_v5_*): ~43, of which the
+            # exp is ~15; against the measured DFMA-pipe rate 37 TFLOP/s = 1.85e13 FP64 instructions/s (profiles/r01_fp64_peaks.json)
+            a0 = {"value": qps0, "unit": "query-points/s", "ms_per_step": ms0 / max(1, min(K, 3)),
+                  "fp64_pipe_frac_at_43_instr_per_pair": qps0 / world * ((N + 127) // 128 * 128) * 43.0 / 1.85e13}
+        del x0, m0, j0
+    except Exception as exc:  # pragma: no cover
+        a0 = {"error": str(exc)[:120]}
+
     # ---- end to end through the host-pointer C ABI with pinned buffers ------------------------------------------
     flags = L.MEAN | L.STD | L.JAC | L.AFFINE_IN
     stream = torch.cuda.ExternalStream(eng.stream(), device=dev)
@@ -754,7 +775,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "query-points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / Ke, "steps": Ke, "e2e_over_device": e2e_value / value},
                 "gpu_launches": q["gpu_launches"], "roofline": q.get("roofline"), "variance_guard": guard,
-                "fp64_dmma_variance": other_out, "parity_vs_fp64_path": parity64, "cpu_baseline": cpu, "c4": c4, "small_n": small,
+                "mode_A0_mean_jacobian": a0, "fp64_dmma_variance": other_out, "parity_vs_fp64_path": parity64, "cpu_baseline": cpu, "c4": c4, "small_n": small,
                 "clocks": dict(sampler.summary(windows), scope="samples inside the two timed regions (device-resident and e2e), 100 ms period",
                                whole_run=sampler.summary()) if sampler else None}
         if problems:
