@@ -36,6 +36,7 @@ SYMBOLS = {
     "gptb_rollout_min_variance": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_int, C.c_double, _dp]),
     "gptb_query_cov": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp, _dp]),
     "gptb_transport_orientation": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, _dp, _dp]),
+    "gptb_transport_orientation_diffeo": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, _dp]),
     "gptb_transport_stiffness": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, _dp, _dp]),
     "gptb_export_L": (C.c_int, [C.c_void_p, _dp]),
     "gptb_export_alpha": (C.c_int, [C.c_void_p, _dp]),
@@ -299,6 +300,17 @@ class Engine:
         if M:
             self._check(self.lib.gptb_transport_orientation(self.h, ptr(pos), ptr(ori), M, ptr(out), ptr(jphi)), "gptb_transport_orientation")
         return out, jphi
+
+    def transport_orientation_diffeo(self, pos, ori):
+        """q_hat = quat(I + Jpsi(gamma(pos))) (x) (quat(R) (x) ori) on the device (the diffeomorphic variant's composition)."""
+        pos, ori = as_f64(pos), as_f64(ori)
+        M = pos.shape[0]
+        if pos.shape != (M, 3) or ori.shape != (M, 4):
+            raise ValueError(f"orientation transport needs pos (M,3) and ori (M,4), got {pos.shape} and {ori.shape}")
+        out = np.empty((M, 4))
+        if M:
+            self._check(self.lib.gptb_transport_orientation_diffeo(self.h, ptr(pos), ptr(ori), M, ptr(out)), "gptb_transport_orientation_diffeo")
+        return out
 
     def transport_stiffness(self, pos, stiff):
         """K_hat = Jphi(pos) K Jphi(pos)^T on the device; returns (stiff_out (M,d,d), jphi (M,d,d))."""

@@ -1636,7 +1636,7 @@ extern "C" int gptb_query_cov(gptb_handle* h, const double* x, int64_t M, double
 // ---------------------------------------------------------------------------------------------------------------
 // orientation transport
 // ---------------------------------------------------------------------------------------------------------------
-extern "C" int gptb_transport_orientation(gptb_handle* h, const double* pos, const double* ori, int64_t M, double* ori_out, double* jphi) {
+static int transport_orientation_impl(gptb_handle* h, const double* pos, const double* ori, int64_t M, double* ori_out, double* jphi, int mode) {
     if (!h || M < 0) return -1;
     if (M == 0) return 0;
     if (!pos || !ori || !ori_out) return -1;
@@ -1659,9 +1659,11 @@ extern "C" int gptb_transport_orientation(gptb_handle* h, const double* pos, con
     cudaError_t e;
     if ((e = cudaMemcpyAsync(pd, pos, sizeof(double) * M * 3, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return fail(e, __LINE__);
     if ((e = cudaMemcpyAsync(od, ori, sizeof(double) * M * 4, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return fail(e, __LINE__);
-    int rc = gptb_query_dev(h, pd, M, GPTB_JAC | GPTB_JPHI, nullptr, nullptr, nullptr, jd, nullptr, nullptr, nullptr, nullptr, jp, nullptr);
+    // mode 0: Jphi = R + Jpsi(pos) R at the UN-rotated positions (quirk Q7); mode 1 (diffeomorphic variant): Jpsi at gamma(pos)
+    int rc = gptb_query_dev(h, pd, M, mode == 1 ? (GPTB_JAC | GPTB_JPHI | GPTB_AFFINE_IN) : (GPTB_JAC | GPTB_JPHI), nullptr, nullptr, nullptr, jd, nullptr, nullptr,
+                            nullptr, nullptr, jp, nullptr);
     if (rc) { cleanup(); return rc; }
-    quat_transport_kernel<<<(unsigned)((M + 127) / 128), 128, 0, h->stream>>>(jp, od, M, qd);
+    quat_transport_kernel<<<(unsigned)((M + 127) / 128), 128, 0, h->stream>>>(mode == 1 ? jd : jp, od, M, qd, mode, h->af);
     h->launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, __LINE__);
     if ((e = cudaMemcpyAsync(ori_out, qd, sizeof(double) * M * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) return fail(e, __LINE__);
@@ -1669,6 +1671,13 @@ extern "C" int gptb_transport_orientation(gptb_handle* h, const double* pos, con
     if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return fail(e, __LINE__);
     cleanup();
     return 0;
+}
+
+extern "C" int gptb_transport_orientation(gptb_handle* h, const double* pos, const double* ori, int64_t M, double* ori_out, double* jphi) {
+    return transport_orientation_impl(h, pos, ori, M, ori_out, jphi, 0);
+}
+extern "C" int gptb_transport_orientation_diffeo(gptb_handle* h, const double* pos, const double* ori, int64_t M, double* ori_out) {
+    return transport_orientation_impl(h, pos, ori, M, ori_out, nullptr, 1);
 }
 
 extern "C" int gptb_transport_stiffness(gptb_handle* h, const double* pos, const double* stiff, int64_t M, double* stiff_out, double* jphi) {

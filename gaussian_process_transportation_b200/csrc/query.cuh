@@ -585,15 +585,9 @@ __global__ void __launch_bounds__(128) finalize_kernel(const double* __restrict_
 // dominant eigenvector of the symmetric 4x4 matrix K3, found here with cyclic Jacobi rotations (one thread per point,
 // everything in registers).  Quaternions are (w, x, y, z); the eigenvector sign is normalised to w >= 0.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) quat_transport_kernel(const double* __restrict__ jphi, const double* __restrict__ ori, long long M,
-                                                             double* __restrict__ out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M) return;
-    double R[3][3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) R[r][c] = jphi[i * 9 + r * 3 + c];
+// Bar-Itzhack quaternion (w, x, y, z; sign normalised to w >= 0) of a possibly non-orthogonal 3x3 matrix: dominant eigenvector of the
+// symmetric 4x4 matrix K3 by cyclic Jacobi rotations, everything in registers.
+__device__ __forceinline__ void quat_of_matrix(const double (&R)[3][3], double (&qa)[4]) {
     double A[4][4];
     A[0][0] = (R[0][0] - R[1][1] - R[2][2]) / 3.0;
     A[0][1] = (R[1][0] + R[0][1]) / 3.0;
@@ -668,12 +662,42 @@ __global__ void __launch_bounds__(128) quat_transport_kernel(const double* __res
     }
     double nrm = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3]);
     double sgn = (e[3] < 0.0) ? -1.0 / nrm : 1.0 / nrm;
-    const double aw = e[3] * sgn, ax = -e[0] * sgn, ay = -e[1] * sgn, az = -e[2] * sgn;
-    const double bw = ori[i * 4 + 0], bx = ori[i * 4 + 1], by = ori[i * 4 + 2], bz = ori[i * 4 + 3];
-    out[i * 4 + 0] = aw * bw - ax * bx - ay * by - az * bz;
-    out[i * 4 + 1] = aw * bx + ax * bw + ay * bz - az * by;
-    out[i * 4 + 2] = aw * by - ax * bz + ay * bw + az * bx;
-    out[i * 4 + 3] = aw * bz + ax * by - ay * bx + az * bw;
+    qa[0] = e[3] * sgn; qa[1] = -e[0] * sgn; qa[2] = -e[1] * sgn; qa[3] = -e[2] * sgn;
+}
+__device__ __forceinline__ void quat_mul(const double (&a)[4], const double (&b)[4], double (&o)[4]) {
+    o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    o[2] = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+    o[3] = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+}
+
+// mode 0 (policy_transportation.py:61-77): mat = Jphi (M,3,3), out = quat(Jphi) (x) q.
+// mode 1 (gaussian_process_transportation_diffeomorphic.py:94-101): mat = Jpsi at the ROTATED positions, out = quat(I + Jpsi) (x) (quat(Raff) (x) q).
+__global__ void __launch_bounds__(128) quat_transport_kernel(const double* __restrict__ mat, const double* __restrict__ ori, long long M,
+                                                             double* __restrict__ out, int mode, Affine af) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    double R[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) R[r][c] = mat[i * 9 + r * 3 + c] + ((mode == 1 && r == c) ? 1.0 : 0.0);
+    double qa[4], qb[4] = {ori[i * 4 + 0], ori[i * 4 + 1], ori[i * 4 + 2], ori[i * 4 + 3]}, qo[4];
+    quat_of_matrix(R, qa);
+    if (mode == 1) {
+        double Ra[3][3], qr[4], qt[4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Ra[r][c] = af.R[r][c];
+        quat_of_matrix(Ra, qr);
+        quat_mul(qr, qb, qt);
+        quat_mul(qa, qt, qo);
+    } else {
+        quat_mul(qa, qb, qo);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[i * 4 + k] = qo[k];
 }
 
 // ------------------------------------------------------------------------------------------------------------

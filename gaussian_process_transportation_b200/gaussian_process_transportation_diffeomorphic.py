@@ -5,7 +5,7 @@ plus the inverse-map consistency check used to tune the length-scale bound.
 Every posterior quantity comes from the B200 engine: `apply_transportation` is ONE fused query (affine prologue,
 mean, std, Jacobian, Jacobian variance, x_hat, v_hat, Var v_hat), the inverse-map check is a second engine fit + mean
 query.  What stays on the host is what the reference keeps on the host: the d x d Kabsch SVD, the optuna study driver
-(`optimize_diffeomorphism`, only if optuna is importable) and the O(M) quaternion algebra of the orientation branch.
+(`optimize_diffeomorphism`, only if optuna is importable).
 Differences to `GaussianProcessTransportation` that are reproduced on purpose (they are the reference's behaviour):
 the Jacobian of the orientation branch is evaluated at the ROTATED positions and composed as
 quat(I + J) * (quat(R) * q) (file:97-101) instead of quat(R + J R) * q at the un-rotated ones.
@@ -16,7 +16,6 @@ from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as
 from . import _lib
 from .affine_transform import AffineTransform
 from .gaussian_process import GaussianProcess
-from .quaternion import from_rotation_matrix_nonorthogonal, multiply as quat_multiply
 
 
 class GaussianProcessTransportationDiffeo():
@@ -41,18 +40,16 @@ class GaussianProcessTransportationDiffeo():
         self.gp_delta_map._engine.set_affine(a.rotation_matrix, float(a.scale), a.S_centroid, a.T_centroid)
 
     # -- apply (file:69-101) -------------------------------------------------------------------------------------
-    def _forward(self, traj, vel=None, want_jac=False):
+    def _forward(self, traj, vel=None):
         flags = _lib.MEAN | _lib.STD | _lib.AFFINE_IN | _lib.TRANSPORT
         if vel is not None:
             flags |= _lib.JAC | _lib.JACVAR | _lib.VELOCITY
-        elif want_jac:
-            flags |= _lib.JAC
         return self.gp_delta_map._query(traj, flags, vel=vel)
 
     def apply_transportation(self):
         self.training_traj_old = self.training_traj
         has_delta, has_ori = hasattr(self, 'training_delta'), hasattr(self, 'training_ori')
-        o = self._forward(self.training_traj, self.training_delta if has_delta else None, want_jac=has_ori)
+        o = self._forward(self.training_traj, self.training_delta if has_delta else None)
         self.traj_rotated = self.affine_transform.predict(self.training_traj)
         self.delta_map_mean, self.std = o["mean"], o["std"]
         self.training_traj = o["xhat"]                      # traj_rotated + delta_map_mean
@@ -61,10 +58,9 @@ class GaussianProcessTransportationDiffeo():
             self.training_delta = o["vhat"]
             self.var_vel_transported = o["vvar"]
         if has_ori:
-            rot_gp = np.eye(o["jac"].shape[1]) + o["jac"]
-            quat_affine = from_rotation_matrix_nonorthogonal(self.affine_transform.rotation_matrix)
-            quat_gp = from_rotation_matrix_nonorthogonal(rot_gp)
-            self.training_ori = quat_multiply(quat_gp, quat_multiply(quat_affine, np.asarray(self.training_ori, dtype=np.float64)))
+            # quat(I + J(gamma(x))) * (quat(R) * q)   (file:94-101): Jacobian, both 4x4 eigen-problems and the products on the GPU
+            self.gp_delta_map._ensure_fitted_factor()
+            self.training_ori = self.gp_delta_map._engine.transport_orientation_diffeo(self.training_traj_old, self.training_ori)
 
     def sample_transportation(self):
         delta_map_samples = self.gp_delta_map.samples(self.traj_rotated)

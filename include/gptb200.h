@@ -165,6 +165,9 @@ int gptb_query_cov(gptb_handle* h, const double* x, int64_t M, double* mean, dou
  * (the reference's behaviour), q_hat = quat(Jphi) (x) q with the Bar-Itzhack quaternion of the non-orthogonal 3x3 Jphi.
  * pos (M,3), ori (M,4) as (w,x,y,z) in; ori_out (M,4); jphi (M,3,3) optional (may be NULL).  Needs d == p == 3. */
 int gptb_transport_orientation(gptb_handle* h, const double* pos, const double* ori, int64_t M, double* ori_out, double* jphi);
+/* the composition of the older diffeomorphic variant (gaussian_process_transportation_diffeomorphic.py:94-101): the Jacobian of the
+ * residual map at the ROTATED positions, q_hat = quat(I + Jpsi(gamma(pos))) (x) (quat(R) (x) q). */
+int gptb_transport_orientation_diffeo(gptb_handle* h, const double* pos, const double* ori, int64_t M, double* ori_out);
 
 /* ---- stiffness transport: K_hat = Jphi K Jphi^T per point, Jphi(x) = (I + Jpsi(gamma(x))) R the Jacobian of the whole map
  * at x (the linearisation the velocity transport uses, policy_transportation.py:37-46).  NOT in the reference code: its

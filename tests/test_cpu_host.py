@@ -75,16 +75,21 @@ def test_affine_transform_matches_oracle():
         assert abs(np.linalg.det(a.rotation_matrix) - 1.0) < 1e-12
 
 
-def test_quaternion_helpers_match_oracle():
-    from gaussian_process_transportation_b200.quaternion import from_rotation_matrix_nonorthogonal, multiply
+def test_oracle_quaternion_restatement_is_self_consistent():
+    """The Bar-Itzhack restatement in the oracle (numpy-quaternion itself is absent): on orthogonal matrices it returns the generating
+    quaternion, against scipy's Rotation, up to sign."""
+    from scipy.spatial.transform import Rotation
     from oracle.gp_oracle import quat_from_matrix_nonorthogonal, quat_mul
-    rng = np.random.default_rng(0)
-    M = np.eye(3) + 0.2 * rng.standard_normal((30, 3, 3))
-    a, b = from_rotation_matrix_nonorthogonal(M), quat_from_matrix_nonorthogonal(M)
+    rot = Rotation.random(30, random_state=0)
+    a = quat_from_matrix_nonorthogonal(rot.as_matrix())
+    b = np.roll(rot.as_quat(), 1, axis=1)                       # scipy is (x, y, z, w)
     s = np.sign(np.sum(a * b, axis=1))[:, None]
     assert np.max(np.abs(a * s - b)) < 1e-12
-    q = rng.standard_normal((30, 4))
-    assert np.allclose(multiply(a, q), quat_mul(a, q))
+    q = np.roll(Rotation.random(30, random_state=1).as_quat(), 1, axis=1)
+    prod = np.roll((rot * Rotation.from_quat(np.roll(q, -1, axis=1))).as_quat(), 1, axis=1)
+    mine = quat_mul(b, q)
+    s = np.sign(np.sum(mine * prod, axis=1))[:, None]
+    assert np.max(np.abs(mine * s - prod)) < 1e-12
 
 
 def test_bench_reference_arm_contract():

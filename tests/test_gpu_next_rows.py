@@ -269,3 +269,25 @@ def test_concurrent_restarts_reproduce_the_sequential_fit():
     assert abs(fits[0].gp.log_marginal_likelihood_value_ - fits[1].gp.log_marginal_likelihood_value_) < 1e-9
     xq = rng.random((40, 2))
     assert rel(fits[1].predict(xq), fits[0].predict(xq)) < 1e-9
+
+
+def test_diffeo_orientation_branch_on_gpu_vs_oracle(golden_dir):
+    """The diffeomorphic variant's orientation composition quat(I + J(gamma(x))) * (quat(R) * q) (file:94-101) runs on the GPU; compared
+    with the oracle's restatement (the reference itself cannot run it: numpy-quaternion is absent)."""
+    import gaussian_process_transportation_b200 as pkg
+    from oracle.gp_oracle import OracleDiffeo
+    g = np.load(os.path.join(golden_dir, "f4_diffeo3d.npz"))
+    k = kern(g["c"], g["ell"], g["s2"])
+    rng = np.random.default_rng(12)
+    ori = rng.standard_normal((len(g["traj_in"]), 4)); ori /= np.linalg.norm(ori, axis=1, keepdims=True)
+    outs = []
+    for cls in (pkg.GaussianProcessTransportationDiffeo, OracleDiffeo):
+        t = cls(kernel_transport=k)
+        t.source_distribution, t.target_distribution = g["S"], g["T"]
+        t.training_traj, t.training_ori = g["traj_in"].copy(), ori.copy()
+        with contextlib.redirect_stdout(io.StringIO()):
+            t.fit_transportation(optimize=False)
+            t.apply_transportation()
+        outs.append(np.asarray(t.training_ori))
+    s = np.sign(np.sum(outs[0] * outs[1], axis=1))[:, None]
+    assert np.max(np.abs(outs[0] * s - outs[1])) < 1e-9

@@ -173,7 +173,7 @@ def test_orientation_vs_oracle_restatement(pkg, golden_dir):
     s = np.sign(np.sum(mine.training_ori * ora.training_ori, axis=1))[:, None]
     assert np.max(np.abs(mine.training_ori * s - ora.training_ori)) < 1e-8
     # the device eigen-solver against numpy's on random non-orthogonal matrices (sign-normalised, unit norm)
-    from gaussian_process_transportation_b200.quaternion import from_rotation_matrix_nonorthogonal, multiply
+    from oracle.gp_oracle import quat_from_matrix_nonorthogonal as from_rotation_matrix_nonorthogonal, quat_mul as multiply
     eng = mine.method.delta_map._engine
     out, jphi = eng.transport_orientation(g["traj_in"], g["ori_in"])
     ref = multiply(from_rotation_matrix_nonorthogonal(jphi), g["ori_in"])
