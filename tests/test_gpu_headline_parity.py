@@ -273,3 +273,59 @@ def test_dense_grid_query_matches_explicit_queries_and_shards_add_up():
     assert np.max(np.abs(whole["sample"][:, 3] - s[:, 0])) / np.sqrt(0.1 + 1e-4) < TOL_STD / STD_MARGIN
     assert rel(whole["sample"][:, 4:].reshape(-1, 3, 3), ora.derivative(xs)) < 1e-9
     eng.close()
+
+
+@pytest.mark.parametrize("n,d,m", [(20, 2, 257), (129, 2, 300), (834, 3, 1031), (1500, 3, 77), (257, 3, 1)])
+def test_int8_spatial_path_on_ragged_shapes_vs_oracle(n, d, m):
+    """The benchmark's variance mode (8-bit planes, spatial skipping, run-time guard) on small / ragged shapes: queries far outside the
+    data (every digit plane zero), exactly ON training points, and in between; d = 2 and d = 3."""
+    from gaussian_process_transportation_b200 import _lib as L
+    from oracle.gp_oracle import ChoGP, synthetic_pairs
+    S, T = synthetic_pairs(n, d, seed=n)
+    Y = T - S
+    ell = np.linspace(0.15, 0.25, d)
+    ora = ChoGP(0.2, ell, 1e-3).fit(S, Y)
+    eng = L.Engine(0)
+    eng.set_variance_mode("int8w5")
+    eng.set_spatial(True)
+    eng.set_train(S, Y)
+    info, _ = eng.factorize(0.2, ell, 1e-3, 1e-10)
+    assert info == 0
+    rng = np.random.default_rng(m)
+    xq = np.vstack([rng.random((m, d)), 50.0 + rng.random((3, d)), S[: min(n, 5)]])[: max(m, 1) + 8]
+    o = eng.query(xq, L.MEAN | L.STD | L.JAC | L.JACVAR)
+    mean, std = ora.predict(xq, return_std=True)
+    J, V = ora.derivative(xq, return_var=True)
+    assert rel(o["mean"], mean) < 1e-9 and rel(o["jac"], J) < 1e-9
+    assert np.max(np.abs(o["std"] - std)) / np.sqrt(0.2 + 1e-3) < TOL_STD / STD_MARGIN
+    assert np.max(np.abs(o["jacvar"] - V) / (0.2 / ell ** 2)) < 1e-6
+    assert eng.query(np.zeros((0, d)), L.MEAN)["mean"].shape == (0, Y.shape[1])
+    eng.close()
+
+
+def test_pipelined_host_query_equals_device_slices():
+    """gptb_query (host pointers) pipelines 131072-query slices over two copy streams; the result must be the device-resident result
+    slice by slice (bit for bit), including the (d, M) layout of derivative_of_variance across slices."""
+    import torch
+    from gaussian_process_transportation_b200 import _lib as L
+    from oracle.gp_oracle import synthetic_pairs
+    S, T = synthetic_pairs(300, 3, seed=4)
+    eng = L.Engine(0)
+    eng.set_train(S, T - S)
+    eng.factorize(0.1, [0.1, 0.15, 0.2], 1e-4, 1e-10)
+    M = 2 * 131072 + 4321
+    x = np.random.default_rng(0).random((M, 3))
+    vel = np.random.default_rng(1).standard_normal((M, 3))
+    fl = L.MEAN | L.STD | L.JAC | L.JACVAR | L.DVAR | L.VELOCITY | L.JPHI | L.TRANSPORT
+    o = eng.query(x, fl, vel=vel)
+    xd = torch.from_numpy(x).cuda(); vd = torch.from_numpy(vel).cuda()
+    for lo in (0, 131072, 262144):
+        m = min(131072, M - lo)
+        bufs = {k: torch.empty(s, dtype=torch.float64, device="cuda") for k, s in
+                dict(mean=(m, 3), std=(m, 3), jac=(m, 3, 3), jacvar=(m, 3, 3), xhat=(m, 3), vhat=(m, 3), vvar=(m, 3), jphi=(m, 3, 3), dvar=(3, m)).items()}
+        eng.query_dev(xd[lo:lo + m].contiguous().data_ptr(), m, fl, vd[lo:lo + m].contiguous().data_ptr(), **{k: v.data_ptr() for k, v in bufs.items()})
+        torch.cuda.synchronize()
+        for k, v in bufs.items():
+            ref = o[k][:, lo:lo + m] if k == "dvar" else o[k][lo:lo + m]
+            assert np.array_equal(v.cpu().numpy(), ref), (k, lo)
+    eng.close()
