@@ -29,21 +29,25 @@ def broadcast_tensors(tensors, src=0, group=None):
 
 def broadcast_model(gp_or_engine, shape=None, src=0, group=None, with_variance=True):
     """Broadcast a fitted model from `src` to every rank.  On `src` pass the fitted GaussianProcess / Engine; on the
-    other ranks pass an un-fitted one (its engine receives the state).  Returns the engine."""
+    other ranks pass an un-fitted one: its ENGINE receives the state (X, alpha, inverse factor, hyper-parameters, ordering) and serves
+    `Engine.query / query_dev / query_grid` for that rank's shard.  The host-side object of a receiving rank stays un-fitted (no kernel
+    object, no training arrays travel): receivers query through the returned engine, not through `predict` / `derivative`.
+    Returns the engine."""
     import torch
     import torch.distributed as dist
     eng = getattr(gp_or_engine, "_engine", gp_or_engine)
     rank = dist.get_rank(group)
     dev = torch.device("cuda", eng.device)
-    meta = torch.zeros(4, dtype=torch.int64, device=dev)
+    meta = torch.zeros(5, dtype=torch.int64, device=dev)
     if rank == src:
         if with_variance:
             eng.prepare_variance()
-        meta[:] = torch.tensor([eng.N, eng.d, eng.p, int(with_variance)], dtype=torch.int64)
+        meta[:] = torch.tensor([eng.N, eng.d, eng.p, int(with_variance), int(eng.spatial)], dtype=torch.int64)
     dist.broadcast(meta, src=src, group=group)
-    N, d, p, wv = (int(v) for v in meta.tolist())
+    N, d, p, wv, sp = (int(v) for v in meta.tolist())
     if rank != src:
         eng.state_alloc(N, d, p, bool(wv))
+        eng.spatial = bool(sp)                    # the handle itself learns the ordering from the state header (gptb_state_commit)
     bufs = []
     for which in (0, 1, 2) + ((3,) if wv else ()):
         ptr, nbytes = eng.state_buffer(which)

@@ -38,6 +38,8 @@ class _Regressor:
     @property
     def L_(self):
         o = self._o
+        if getattr(o, "_L_cache", None) is not None:
+            return o._L_cache
         if o._engine.spatial:
             # the handle holds the factor of the Morton-ordered system; sklearn's L_ is the factor in the caller's order:
             # factorise once more on a scratch handle in natural order (attribute access only, not on any hot path)
@@ -49,7 +51,8 @@ class _Regressor:
                 info, _ = scratch.factorize(c, ell, s2, self.alpha, want_lml=False)
                 if info > 0:
                     raise np.linalg.LinAlgError("kernel matrix is not positive definite")
-                return scratch.export_L()
+                o._L_cache = scratch.export_L()      # kept until the next fit / append: repeated attribute reads cost nothing
+                return o._L_cache
             finally:
                 scratch.close()
         o._ensure_fitted_factor()
@@ -196,6 +199,7 @@ class GaussianProcess:
             gp.log_marginal_likelihood_value_ = lml
         self._factor_theta = np.array(kernel_.theta, copy=True)
         self._K_inv = None
+        self._L_cache = None
 
         self.kernel = kernel_
         prm = self.kernel.get_params()
@@ -338,6 +342,7 @@ class GaussianProcess:
         self.n_samples = self.X.shape[0]
         self.gp.log_marginal_likelihood_value_ = lml
         self._K_inv = None
+        self._L_cache = None
 
     # -- minimum-variance stabilisation (plot_utils.py:283-317): the two query shapes of the reference's plotting helpers -------------
     def minimum_variance_field(self, x, gain=2.0):
