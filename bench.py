@@ -707,6 +707,27 @@ def main():
     except Exception as exc:  # pragma: no cover
         a0 = {"error": str(exc)[:120]}
 
+    # ---- mode B (mode A + Jacobian variance: what apply_transportation computes when training_delta is set, policy_transportation.py:41;
+    #      1 + d triangular products per query instead of 1) on a quarter of the step's queries ------------------------------------------
+    modeb = None
+    try:
+        Mb = max(1 << 16, M // 4)
+        flb = L.MEAN | L.STD | L.JAC | L.JACVAR | L.AFFINE_IN
+        stb = torch.cuda.ExternalStream(eng.stream(), device=dev)
+        xb = torch.from_numpy(xq[:Mb]).to(dev)
+        mb = torch.empty(Mb, p, dtype=torch.float64, device=dev); sb = torch.empty(Mb, p, dtype=torch.float64, device=dev)
+        jb = torch.empty(Mb, p, d, dtype=torch.float64, device=dev); vb = torch.empty(Mb, p, d, dtype=torch.float64, device=dev)
+        stepb = lambda: eng.query_dev(xb.data_ptr(), Mb, flb, 0, mb.data_ptr(), sb.data_ptr(), jb.data_ptr(), vb.data_ptr())
+        stepb()
+        Kb = max(1, min(K, 3))
+        msb = hs.timed(stb, stepb, Kb)
+        if rank == 0:
+            modeb = {"value": world * Mb * Kb / (msb * 1e-3), "unit": "query-points/s", "ms_per_step": msb / Kb, "queries_per_step_per_gpu": Mb,
+                     "triangular_products_per_query": 1 + d}
+        del xb, mb, sb, jb, vb
+    except Exception as exc:  # pragma: no cover
+        modeb = {"error": str(exc)[:120]}
+
     # ---- end to end through the host-pointer C ABI with pinned buffers ------------------------------------------
     flags = L.MEAN | L.STD | L.JAC | L.AFFINE_IN
     stream = torch.cuda.ExternalStream(eng.stream(), device=dev)
@@ -775,7 +796,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "query-points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / Ke, "steps": Ke, "e2e_over_device": e2e_value / value},
                 "gpu_launches": q["gpu_launches"], "roofline": q.get("roofline"), "variance_guard": guard,
-                "mode_A0_mean_jacobian": a0, "fp64_dmma_variance": other_out, "parity_vs_fp64_path": parity64, "cpu_baseline": cpu, "c4": c4, "small_n": small,
+                "mode_A0_mean_jacobian": a0, "mode_B_with_jacobian_variance": modeb, "fp64_dmma_variance": other_out, "parity_vs_fp64_path": parity64, "cpu_baseline": cpu, "c4": c4, "small_n": small,
                 "clocks": dict(sampler.summary(windows), scope="samples inside the two timed regions (device-resident and e2e), 100 ms period",
                                whole_run=sampler.summary()) if sampler else None}
         if problems:
