@@ -1039,7 +1039,9 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
         oz::PlaneMaps mapsAq;
         const bool use_masks = spatial && h->spatial == 1;
         const bool extra = h->var_extra && S == 5 && h->var_bits == 8;        // S = 5 + the first dropped diagonal (skipping kernel only)
-        const bool skipping = use_masks || h->oz_force_skip || extra;
+        // spatial mode 2 (every plane product issued: the A/B of the skipping itself) runs the same kernel with null masks, so that the two
+        // differ in nothing but the skipped all-zero products
+        const bool skipping = use_masks || h->oz_force_skip || extra || spatial;
         if (!make_plane_maps(&mapsAq, Aplanes, rows_total, h->Npad, S, oz::OM, oz::OKB)) GPTB_FAIL(h, -5, "cuTensorMapEncodeTiled failed for the digit planes");
         if (!fused) {
             tic(h, 3);
@@ -1059,11 +1061,11 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
             const unsigned grid_oz = (unsigned)(ntiles < nsm ? ntiles : nsm);
             if (skipping && extra) {
                 if constexpr (SV == 5)
-                    oz::ozaki_trmm_kernel<5, true, 1><<<grid_oz, oz::OTHREADS, oz::Cfg<5>::SMEM_SKIP_BYTES, h->stream>>>(
+                    oz::ozaki_trmm_kernel<5, true, 1><<<grid_oz, oz::OTHREADS_SKIP, oz::Cfg<5>::SMEM_SKIP_BYTES, h->stream>>>(
                         mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, use_masks ? flagsA_slot : nullptr, use_masks ? h->flagsB : nullptr, h->flags_stride,
                         exec_counter(h), h->oz_whatif, h->oz_prof);
             } else if (skipping) {
-                oz::ozaki_trmm_kernel<SV, true><<<grid_oz, oz::OTHREADS, oz::Cfg<SV>::SMEM_SKIP_BYTES, h->stream>>>(
+                oz::ozaki_trmm_kernel<SV, true><<<grid_oz, oz::OTHREADS_SKIP, oz::Cfg<SV>::SMEM_SKIP_BYTES, h->stream>>>(
                     mapsAq, h->mapsBq, oz_scale, h->scaleB, T64, rowtiles, rows_total, part, h->info + 1, h->var_bits, use_masks ? flagsA_slot : nullptr, use_masks ? h->flagsB : nullptr, h->flags_stride,
                     exec_counter(h), h->oz_whatif, h->oz_prof);
             } else {
@@ -1074,7 +1076,7 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
         });
         toc(h, 0);
         LAUNCH_CHECK(h);
-        Tpart = T64;
+        Tpart = skipping ? 2 * T64 : T64;           // the skipping kernel writes two partial sums per (tile, row): one per epilogue warp group
     } else if (nrhs > 0) {
         const int rowtiles = (int)(rows_total / TS);
         tic(h, 0);
@@ -1173,7 +1175,7 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     size_t o_rhs = carve(fused_planes ? 0 : (size_t)nrhs * Bfirst * h->Npad);
     size_t o_part[2], o_ozp[2], o_ozs[2], o_macc[2], o_xr[2];
     for (int b = 0; b < nbuf; ++b) {
-        o_part[b] = carve((size_t)(nrhs > 0 ? (ozaki ? 2 * T : T) : 0) * nrhs * Bfirst);
+        o_part[b] = carve((size_t)(nrhs > 0 ? (ozaki ? 4 * T : T) : 0) * nrhs * Bfirst);
         o_ozp[b] = carve(ozaki ? ((size_t)h->var_slices * nrhs * Bfirst * h->Npad + 7) / 8 : 0);
         o_ozs[b] = carve(ozaki ? (size_t)nrhs * Bfirst : 0);
         o_macc[b] = carve((size_t)nsplit * Bfirst * NACC);

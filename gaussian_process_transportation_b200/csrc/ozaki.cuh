@@ -25,7 +25,10 @@ namespace oz {
 constexpr int OM = 128;      // queries per tile (UMMA M)
 constexpr int ON = 64;       // inverse-factor rows per tile (UMMA N)
 constexpr int OKB = 64;      // k bytes (= k elements) per pipeline chunk, one 64-byte swizzle row
-constexpr int OTHREADS = 256;   // warp group 0: warp 0 = TMA producer, warps 1..NST = MMA issuers (warp 1 owns TMEM); warp group 1: epilogue
+constexpr int OTHREADS = 256;   // dense variant -- warp group 0: warp 0 = TMA producer, warp 1 = MMA issuer (owns TMEM); warp group 1: epilogue
+// skipping variant: 384 threads -- warp 0 producer, warps 1..3 MMA issuers, warps 4..7 and 8..11 epilogue (two warps per TMEM lane quarter,
+// 32 of the 64 accumulator columns each: the issuing warps wait for the epilogue of the previous tile 8-10 % of a launch at N = 4096)
+constexpr int OTHREADS_SKIP = 384;
 // Register budget (setmaxnreg): __launch_bounds__(256, 2) launches the CTA with 128 registers per thread; warp group 0
 // gives back down to 80 and the epilogue warp group grows to 176 (128*80 + 128*176 = 256*128; ptxas compiles each
 // branch against its own budget, no spills).  What matters is the LAUNCH footprint: 2 warps x 128 x 32 = 8 K of the 16 K
@@ -361,7 +364,7 @@ __device__ __forceinline__ void oz_tile_decode(long long idx, int T64, int rowti
 // nor the converged-warp issue (which does remove the ELECT / R2UR waterfall around every UTCIMMA / UTMALDG) accounts for it.
 // Unexplained at the end of round 1; the dense path therefore stays on the loops it was tuned with.
 template <int S, bool SKIP, int X = 0>
-__global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_constant__ PlaneMaps mapsA,
+__global__ void __launch_bounds__(SKIP ? OTHREADS_SKIP : OTHREADS, SKIP ? 1 : 2) ozaki_trmm_kernel(const __grid_constant__ PlaneMaps mapsA,
                                                                 const __grid_constant__ PlaneMaps mapsB,
                                                                 const double* __restrict__ scaleA, const double* __restrict__ scaleB,
                                                                 int T64, int rowtiles, long long rows_total,
@@ -395,9 +398,9 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
     if (tid == 0) {
         for (int i = 0; i < NBAR; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(&acc_full, NMMA);        // one tcgen05.commit per issuing warp
-        mbar_init(&acc_empty, 4);          // one arrival per epilogue warp
+        mbar_init(&acc_empty, SKIP ? 8 : 4);   // one arrival per epilogue warp
         mbar_init(&tile_go, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], NMMA + 4); }   // issuing warps + 4 epilogue warps
+        for (int i = 0; i < 2; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], NMMA + (SKIP ? 8 : 4)); }   // issuing warps + epilogue warps
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {
@@ -664,8 +667,10 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty);
             }
+            // skipping variant: warps 4..7 take columns 0..31, warps 8..11 columns 32..63 of the tile (two partial sums per row and tile)
+            const int cb0 = (SKIP && warp >= 8) ? ON / 32 : 0, cb1 = SKIP ? cb0 + ON / 32 : ON / 16;
 #pragma unroll 1
-            for (int cb = (wi & 4) ? ON / 16 : 0; cb < ON / 16; ++cb) {
+            for (int cb = (wi & 4) ? cb1 : cb0; cb < cb1; ++cb) {
                 double v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = 0.0;
@@ -693,7 +698,7 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
                         v[j] = fma(da, gw[g], v[j]);
                     }
                 }
-                if (cb == ON / 16 - 1) {
+                if (cb == cb1 - 1) {
                     // every accumulator column of this tile has been read: let the MMA thread start the next tile
                     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
                     __syncwarp();
@@ -707,7 +712,7 @@ __global__ void __launch_bounds__(OTHREADS, 2) ozaki_trmm_kernel(const __grid_co
             }
             const long long grow = (long long)rt * OM + q;
             const double sa = scaleA[grow];
-            part[(long long)ti * rows_total + grow] = ssum * sa * sa;
+            part[(long long)(ti + ((SKIP && warp >= 8) ? T64 : 0)) * rows_total + grow] = ssum * sa * sa;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
