@@ -120,3 +120,50 @@ def test_variance_mode_names():
     for bad in ("int8", "int8y5", "fp32", "int8x"):
         with pytest.raises(ValueError):
             _lib.parse_variance_mode(bad)
+
+
+def test_bench_alignment_matches_the_package_and_the_oracle():
+    """bench.py aligns the synthetic clouds with its own few lines of Kabsch (so that the GPU arm imports nothing from oracle/);
+    they must be the reference's AffineTransform."""
+    import contextlib, io, sys
+    sys.path.insert(0, ROOT)
+    import bench
+    from gaussian_process_transportation_b200 import AffineTransform
+    from oracle.gp_oracle import OracleAffine
+    S, T = bench.synthetic_pairs(200, 3, seed=0)
+    R, Sc, Tc = bench.kabsch(S, T)
+    with contextlib.redirect_stdout(io.StringIO()):
+        a = AffineTransform(); a.fit(S, T)
+        b = OracleAffine(); b.fit(S, T)
+    assert np.allclose(R, a.rotation_matrix, atol=1e-14) and np.allclose(R, b.rotation_matrix, atol=1e-14)
+    _, _, _, _, _, Sr, D = bench.aligned_training_set(200)
+    assert np.allclose(Sr, a.predict(S), atol=1e-14) and np.allclose(D, T - a.predict(S), atol=1e-14)
+    from gaussian_process_transportation_b200 import _lib
+    assert _lib.parse_variance_mode("int8w5p") == (3, 5)
+
+
+def test_unmodified_reference_and_oracle_port_agree():
+    """baseline/_ref (the unmodified reference, when installed by build()) against the oracle port on a small problem: the CPU arm of
+    bench.py times the former, the tests on the GPU box use the latter."""
+    import contextlib, io, sys, warnings
+    sys.path.insert(0, ROOT)
+    from baseline.reference_shim import available, import_reference
+    if not available():
+        pytest.skip("baseline/_ref is not installed on this checkout")
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+    from oracle.gp_oracle import SkGaussianProcess, synthetic_pairs
+    warnings.filterwarnings("ignore")
+    pt = import_reference()
+    S, T = synthetic_pairs(150, 3, seed=2)
+    k = C(0.1) * RBF([0.1, 0.15, 0.2]) + WhiteKernel(1e-4)
+    xq = np.random.default_rng(0).random((40, 3))
+    outs = []
+    for cls in (pt.GaussianProcess, SkGaussianProcess):
+        gp = cls(kernel=k, optimizer=None)
+        with contextlib.redirect_stdout(io.StringIO()):
+            gp.fit(S, T - S)
+        m, s = gp.predict(xq, return_std=True)
+        J, V = gp.derivative(xq, return_var=True)
+        outs.append((m, s, J, V, gp.derivative_of_variance(xq)))
+    for a, b in zip(*outs):
+        assert np.max(np.abs(np.asarray(a) - np.asarray(b))) < 1e-12
