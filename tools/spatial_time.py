@@ -11,6 +11,8 @@ S, T = synthetic_pairs(N, 3, seed=0)
 eng = L.Engine(0)
 eng.set_variance_mode(sys.argv[3] if len(sys.argv) > 3 else "int8w5")
 eng.set_spatial(1)
+if len(sys.argv) > 4:
+    eng.set_variance_guard(float(sys.argv[4]))        # 0 = guard off (ncu captures: the first product launch is then the warm-up query)
 eng.set_train(S, T - S)
 eng.factorize(0.1, [0.1] * 3, 1e-4, 1e-10)
 xq = -0.1 + 1.2 * np.random.default_rng(0).random((M, 3))
