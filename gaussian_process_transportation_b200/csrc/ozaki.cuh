@@ -29,12 +29,11 @@ constexpr int OTHREADS = 256;   // dense variant -- warp group 0: warp 0 = TMA p
 // skipping variant: 384 threads -- warp 0 producer, warps 1..3 MMA issuers, warps 4..7 and 8..11 epilogue (two warps per TMEM lane quarter,
 // 32 of the 64 accumulator columns each: the issuing warps wait for the epilogue of the previous tile 8-10 % of a launch at N = 4096)
 constexpr int OTHREADS_SKIP = 384;
-// Register budget (setmaxnreg): __launch_bounds__(256, 2) launches the CTA with 128 registers per thread; warp group 0
-// gives back down to 80 and the epilogue warp group grows to 176 (128*80 + 128*176 = 256*128; ptxas compiles each
-// branch against its own budget, no spills).  What matters is the LAUNCH footprint: 2 warps x 128 x 32 = 8 K of the 16 K
-// registers of each SM sub-partition, which leaves room for one 256-thread generator CTA (2 warps x 120 x 32 per
-// sub-partition) next to the persistent product CTA -- the generator of the next batch runs on the FP64 pipe while this
-// kernel keeps the tensor pipe busy (gptb_set_query_pipeline).  With 6 warps x 168 registers the generator never fitted.
+// Register budget (setmaxnreg): the control warp group gives registers back (down to 80 per thread), the epilogue warp groups grow to
+// 176 (ptxas compiles each branch against its own budget, no spills).  Dense variant: __launch_bounds__(256, 2) = 128 registers at
+// launch, a footprint that leaves room for one 256-thread generator CTA on the SM (the generator/product overlap of round 1,
+// gptb_set_query_pipeline: kernels overlap, no net gain).  Skipping variant: __launch_bounds__(384, 1) = 168 registers at launch, 55 K of
+// the SM's 64 K after the exchange; it owns the SM (216 KB of shared memory), so the overlap option only double-buffers there.
 constexpr int OREG_LIGHT = 80, OREG_EPI = 176;
 // digit width: 7 (balanced digits, "int8xS") or 8 (full int8 range, "int8wS"; digits.cuh) -- a template parameter of the
 // slicers and a run-time argument of the product kernel (it only changes the recombination weights)

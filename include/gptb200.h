@@ -211,7 +211,8 @@ int gptb_set_workspace_limit(gptb_handle* h, int64_t bytes);
 /* INT8-sliced path only: overlap the k* generator of batch i+1 (FP64 pipe, low-priority stream) with the digit-plane
  * products of batch i (tensor pipe) through double-buffered batches.  Off by default: on this pool's B200 the product
  * kernel runs at the 1 kW power cap (SM clock ~1.72 GHz), the two kernels then share one energy budget and the overlapped
- * step is no faster than the serialised one (profiles/r01_pipeline_ab.log).  Results are bit-identical either way. */
+ * step is no faster than the serialised one (profiles/r01_pipeline_ab.log; re-measured in spatial mode after every kernel change of round 2:
+ * profiles/r02_pipeline_ab_spatial_*.log).  Results are bit-identical either way. */
 int gptb_set_query_pipeline(gptb_handle* h, int on);
 
 /* number of (digit-plane pair, 64-byte k-chunk, 128 x 64 tile) products the INT8-sliced product kernel has issued since the last
