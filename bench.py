@@ -597,12 +597,16 @@ def small_n_block(L, local_rank):
         rec = {}
         for tag, par in (("sequential_restarts", False), ("concurrent_restarts", True)):
             gp = g.GaussianProcess(kernel=C(0.1) * RBF(length_scale=[0.1]) + WhiteKernel(1e-4), device=local_rank, parallel_restarts=par)
-            np.random.seed(0)
-            l0 = gp._engine.launch_count()
-            t0 = time.perf_counter()
-            with contextlib.redirect_stdout(io.StringIO()):
-                gp.fit(X, Y)
-            rec[tag] = {"fit_s": time.perf_counter() - t0, "lml": float(gp.gp.log_marginal_likelihood_value_), "kernel": str(gp.kernel),
+            times = []
+            for _ in range(3):                      # the first call creates the restart engines (streams, workspaces); later ones reuse them
+                np.random.seed(0)                   # fit() restarts from the estimator's initial kernel every time
+                l0 = gp._engine.launch_count()
+                t0 = time.perf_counter()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    gp.fit(X, Y)
+                times.append(time.perf_counter() - t0)
+            rec[tag] = {"fit_s": min(times[1:]), "first_fit_s": times[0], "all_fit_s": times,
+                        "lml": float(gp.gp.log_marginal_likelihood_value_), "kernel": str(gp.kernel),
                         "launches_on_main_handle": gp._engine.launch_count() - l0}
         out["optimised_fit_N834_5_restarts"] = rec
     except Exception as exc:  # pragma: no cover
