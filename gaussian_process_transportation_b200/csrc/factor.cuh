@@ -643,6 +643,113 @@ __global__ void __launch_bounds__(256) trsv_back_step_kernel(const double* __res
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// The same back substitution as ONE launch: CTA b owns block row j = T-1-b, keeps z_j and Dinv_j in shared memory and follows the
+// chain  x_{T-1} -> x_{T-2} -> ...  through per-block flags in global memory (flag[k] == epoch: x_k is published).  For every k > j
+// it prefetches the tile L[k,j] (lower triangle: rows of block k, contiguous in the columns of block j) into registers BEFORE
+// spinning on flag[k], so on the chain's critical path a step costs: flag -> 4 KB of x_k -> 192 DFMA per thread -> reduce ->
+// Dinv_j^T z_j from shared memory -> publish.  That is 3-4 us per block against 22-24 us for one launch per block (N = 4096:
+// 0.7 ms of a 5.1 ms fit).  Producers have the LOWER block indices, so with in-order CTA dispatch a spinning CTA never keeps its
+// producer off the machine (the decoupled-look-back argument), whatever T is.  Summation order is fixed: deterministic.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int BACKCHAIN_SMEM_BYTES = TS * TS * (int)sizeof(double);
+
+__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_s32(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+__global__ void __launch_bounds__(256, 1) trsv_back_chain_kernel(const double* __restrict__ Lbuf, long long ld, const double* __restrict__ dinv,
+                                                                 const double* __restrict__ rhs, double* sol, int Npad, int p, int T, int* flags,
+                                                                 int epoch) {
+    extern __shared__ __align__(16) double dsm[];            // Dinv_j, row-major [r][c]
+    __shared__ double zs[MAXP][TS];
+    __shared__ double xs[MAXP][TS];
+    __shared__ double part[8][MAXP][TS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j = T - 1 - (int)blockIdx.x;
+    {
+        const double2* src = reinterpret_cast<const double2*>(dinv + (long long)j * TS * TS);
+        double2* dst = reinterpret_cast<double2*>(dsm);
+#pragma unroll 8
+        for (int e = tid; e < TS * TS / 2; e += 256) dst[e] = src[e];
+        for (int e = tid; e < MAXP * TS; e += 256) zs[e / TS][e % TS] = (e / TS < p) ? rhs[(long long)(e / TS) * Npad + j * TS + (e % TS)] : 0.0;
+    }
+    __syncthreads();
+    for (int k = T - 1; k > j; --k) {
+        // thread (warp, lane): rows c = 16 warp .. 16 warp + 15 of block k, columns r = 4 lane .. 4 lane + 3 of block j
+        double2 u0[16], u1[16];
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+            const double* rowp = Lbuf + ((long long)k * TS + warp * 16 + rr) * ld + (long long)j * TS + lane * 4;
+            u0[rr] = *reinterpret_cast<const double2*>(rowp);
+            u1[rr] = *reinterpret_cast<const double2*>(rowp + 2);
+        }
+        if (tid == 0)
+            while (ld_acquire_gpu_s32(flags + k) != epoch) {}
+        __syncthreads();
+        for (int e = tid; e < p * TS; e += 256) xs[e / TS][e % TS] = __ldcg(sol + (long long)(e / TS) * Npad + k * TS + (e % TS));
+        __syncthreads();
+        for (int q = 0; q < p; ++q) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+                const double xv = xs[q][warp * 16 + rr];
+                a0 = fma(u0[rr].x, xv, a0);
+                a1 = fma(u0[rr].y, xv, a1);
+                a2 = fma(u1[rr].x, xv, a2);
+                a3 = fma(u1[rr].y, xv, a3);
+            }
+            part[warp][q][lane * 4 + 0] = a0;
+            part[warp][q][lane * 4 + 1] = a1;
+            part[warp][q][lane * 4 + 2] = a2;
+            part[warp][q][lane * 4 + 3] = a3;
+        }
+        __syncthreads();
+        for (int e = tid; e < p * TS; e += 256) {
+            const int q = e / TS, c = e % TS;
+            double sacc = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sacc += part[w][q][c];
+            zs[q][c] -= sacc;
+        }
+        // the two barriers of the next round (flag, x_k) separate these reads of part[] from its next writes
+    }
+    __syncthreads();
+    // x_j[c] = sum_r Dinv_j[r][c] z_j[r]
+    for (int q = 0; q < p; ++q) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+            const int r = warp * 16 + rr;
+            const double zv = zs[q][r];
+            const double2 d0 = *reinterpret_cast<const double2*>(dsm + r * TS + lane * 4);
+            const double2 d1 = *reinterpret_cast<const double2*>(dsm + r * TS + lane * 4 + 2);
+            a0 = fma(d0.x, zv, a0);
+            a1 = fma(d0.y, zv, a1);
+            a2 = fma(d1.x, zv, a2);
+            a3 = fma(d1.y, zv, a3);
+        }
+        part[warp][q][lane * 4 + 0] = a0;
+        part[warp][q][lane * 4 + 1] = a1;
+        part[warp][q][lane * 4 + 2] = a2;
+        part[warp][q][lane * 4 + 3] = a3;
+    }
+    __syncthreads();
+    for (int e = tid; e < p * TS; e += 256) {
+        const int q = e / TS, c = e % TS;
+        double sacc = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sacc += part[w][q][c];
+        sol[(long long)q * Npad + j * TS + c] = sacc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_gpu_s32(flags + j, epoch);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // LML scalar terms (sklearn:_gpr.py:613-617): out[0] = sum_q y_q . alpha_q ; out[1] = sum_i log L_ii.  One CTA,
 // fixed summation order (deterministic).
 // ------------------------------------------------------------------------------------------------------------

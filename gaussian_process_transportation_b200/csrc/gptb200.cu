@@ -103,6 +103,9 @@ struct gptb_handle {
     double *Lbuf = nullptr, *Dinv = nullptr, *Minv = nullptr, *Wbuf = nullptr, *gradpart = nullptr, *scal = nullptr;
     double* header = nullptr;
     int* info = nullptr;
+    int* chain_flags = nullptr;              // trsv_back_chain_kernel: flag[k] == chain_epoch once x_k is published
+    int chain_epoch = 0, chain_cap = 0;
+    int back_variant = 1;                    // 1 = one chained launch, 0 = one launch per block (developer A/B)
     CUtensorMap mapL, mapD, mapM, mapW;      // TMA views of Lbuf, Dinv, Minv, Wbuf
     CUtensorMap mapL64;                      // Lbuf with a 64-row box (half-tile trailing update)
     // INT8-sliced variance path (ozaki.cuh): digit planes of the inverse factor + per-row scales
@@ -214,6 +217,7 @@ static int set_kernel_attrs(gptb_handle* h) {
     CU(h, cudaFuncSetAttribute(trtri_level_p2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(kinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(trmm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(trsv_back_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BACKCHAIN_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<4>::SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<4>::SMEM_SKIP_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<5>::SMEM_BYTES));
@@ -289,6 +293,7 @@ extern "C" void gptb_destroy(gptb_handle* h) {
     if (h->scratch) cudaFree(h->scratch);
     if (h->probe) cudaFree(h->probe);
     cudaFree(h->info);
+    cudaFree(h->chain_flags);
     cudaFree(h->scal);
     cudaFree(h->header);
     for (auto& v : h->ev)
@@ -325,6 +330,7 @@ extern "C" int gptb_set_debug_option(gptb_handle* h, const char* name, int value
     if (!strcmp(name, "spatial_shuffle")) h->spatial_shuffle = value != 0;
     else if (!strcmp(name, "oz_force_skip_variant")) h->oz_force_skip = value != 0;
     else if (!strcmp(name, "oz_whatif")) h->oz_whatif = value;
+    else if (!strcmp(name, "back_substitution_variant")) h->back_variant = value != 0;
     else if (!strcmp(name, "batch_cap")) { if (value < 128 || value % 128) GPTB_FAIL(h, -1, "batch_cap must be a multiple of 128"); h->batch_cap = value; }
     else GPTB_FAIL(h, -1, "gptb_set_debug_option: unknown option '%s'", name);
     return 0;
@@ -624,6 +630,22 @@ static int factorize_device(gptb_handle* h) {
 static int solve_alpha(gptb_handle* h) {
     const int T = h->T;
     const long long ld = h->Npad;
+    if (h->back_variant == 1) {
+        if (T > h->chain_cap) {
+            cudaFree(h->chain_flags);
+            h->chain_flags = nullptr;
+            h->chain_cap = 0;
+            CU(h, cudaMalloc(&h->chain_flags, sizeof(int) * (size_t)(T + 64)));
+            CU(h, cudaMemsetAsync(h->chain_flags, 0, sizeof(int) * (size_t)(T + 64), h->stream));
+            h->chain_cap = T + 64;
+            h->chain_epoch = 0;
+        }
+        h->chain_epoch += 1;
+        trsv_back_chain_kernel<<<T, 256, BACKCHAIN_SMEM_BYTES, h->stream>>>(h->Lbuf, ld, h->Dinv, h->tmp2, h->alpha, (int)h->Npad, h->p, T, h->chain_flags,
+                                                                          h->chain_epoch);
+        LAUNCH_CHECK(h);
+        return 0;
+    }
     for (int kt = T - 1; kt >= 0; --kt) {
         trsv_back_step_kernel<<<kt > 0 ? kt : 1, 256, 0, h->stream>>>(h->Lbuf, ld, h->Dinv, h->tmp2, h->alpha, (int)h->Npad, h->p, kt);
         LAUNCH_CHECK(h);
