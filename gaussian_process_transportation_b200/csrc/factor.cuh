@@ -163,49 +163,65 @@ __device__ __forceinline__ void smem_gemm(double* C, int ldc, const double* A, i
     }
 }
 
-// One warp: Cholesky of a 32x32 block (lane i holds row i in a[0..31], lower part meaningful) followed by the inverse of the
-// factor.  On return a[] holds row i of L (entries above the diagonal are unspecified), x[] holds COLUMN `lane` of L^-1
-// (x[r] = Linv[r][lane], zero for r < lane).  Returns the 1-based index of the first non-positive pivot in the block, 0 if none.
-// Broadcasts go through shared memory (`scratch`: 32*34 + 96 doubles, warp-private): the first version broadcast every L[k][j] with
-// a 64-bit shuffle (two SHFL each: 62 per column step, ~1000 for the inverse) and spent 63 % of the diagonal-tile kernel here
-// (tools/diag_prof.py: 19.7 k cycles per block); a column written once and read back with broadcast loads costs a fraction of that.
-constexpr int WB_LD = 34;                                        // row stride of the block copy (16-byte aligned rows)
-constexpr int WARP_BLOCK_SCRATCH = DB * WB_LD + 3 * DB;          // doubles
-__device__ __forceinline__ int warp_potrf_trtri32(double (&a)[DB], double (&x)[DB], int lane, double* scratch) {
+// One warp: Cholesky of a 32x32 block (lane i holds row i in a[0..31], lower part meaningful; dg = a[lane], the lane's own diagonal
+// entry) and, in the same 32 column steps, the inverse of the factor.  On return a[] holds row i of L (entries above the diagonal are
+// unspecified), x[] holds COLUMN `lane` of L^-1 (x[r] = Linv[r][lane], zero for r < lane).  Returns the 1-based index of the first
+// non-positive pivot in the block, 0 if none.
+//   * column j of L is broadcast through shared memory (`scratch`: 64 doubles, warp-private, double-buffered).  The first version
+//     broadcast every L[k][j] with a 64-bit shuffle (62 SHFL per column step, ~1000 for the inverse) and spent 63 % of the
+//     diagonal-tile kernel here (tools/diag_prof.py: 19.7 k cycles per block);
+//   * the inverse is the COLUMN-oriented forward substitution (lane c solves L x = e_c): once x_j is known, the running sums of the
+//     rows below take  s_k += L[k][j] x_j  -- the same broadcast column the factor's rank-1 update reads, so the inverse costs no
+//     extra loads and its short chain (s_j -> x_j) hides under the pivot latency instead of following the factor (17 k -> 7 k cycles);
+//   * the pivot chain never goes through shared memory: every lane keeps its own diagonal entry up to date with its own l
+//     (dg -= l^2, the same value the general update would produce), so a step's critical path is SHFL -> rsqrt -> mul -> DFMA.
+constexpr int WARP_BLOCK_SCRATCH = 2 * DB;                       // doubles
+constexpr double DBL_MIN_POS = 2.2250738585072014e-308;
+// 1/sqrt(d) for a normal positive d, branch-free: MUFU.RSQ64H seed (relative error 2^-22) and one cubic step, the sequence CUDA's
+// rsqrt() uses on its fast path -- without its slow-path branch, which keeps the pivot chain and the rank-1 updates around it in one
+// basic block, so the scheduler overlaps them (with sqrt() + rsqrt() calls the warp sat through ~13 dependent FP64 operations per
+// column before it issued anything else).
+__device__ __forceinline__ double rsqrt_normal(double d) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+    const double e = fma(d, -(y0 * y0), 1.0);
+    const double pc = fma(e, 0.375, 0.5);
+    return fma(pc, y0 * e, y0);
+}
+__device__ __forceinline__ int warp_potrf_trtri32(double (&a)[DB], double (&x)[DB], double dg, int lane, double* scratch) {
     const unsigned full = 0xffffffffu;
-    double* Lb = scratch;                                        // [32][WB_LD]: the factor, row-major
-    double* col = scratch + DB * WB_LD;                          // [2][32]: current column of L, double-buffered
-    double* rinvs = col + 2 * DB;                                // [32]: 1 / L_jj
+    double* col = scratch;                                       // [2][32]: current column of L, double-buffered
     int bad = 0;
 #pragma unroll
+    for (int c = 0; c < DB; ++c) x[c] = 0.0;                     // x[k], k > j: running sum of row k; becomes x_k at step k
+    // software-pipelined by hand: the pivot of step j+1 (SHFL -> rsqrt) is started as soon as the lane's diagonal entry is up to
+    // date, before the rank-1 updates of step j are issued (a warp issues in order)
+    double d = __shfl_sync(full, dg, 0);
+    double rinv = rsqrt_normal(d >= DBL_MIN_POS ? d : 1.0);
+#pragma unroll
     for (int j = 0; j < DB; ++j) {
-        const double d = __shfl_sync(full, a[j], j);
-        if (!(d > 0.0) && bad == 0) bad = j + 1;
-        const double piv = (d > 0.0) ? sqrt(d) : 1.0;
-        const double rinv = (d > 0.0) ? rsqrt(d) : 1.0;        // independent of the sqrt: halves the pivot latency
-        const double l = (lane == j) ? piv : a[j] * rinv;     // column j of L (lanes > j); LAPACK dpotf2 scales by 1/ajj too
-        a[j] = l;
+        const bool ok = d >= DBL_MIN_POS;                     // non-positive (or subnormal) pivot: LAPACK's info, the block carries on with 1
+        if (!ok && bad == 0) bad = j + 1;
+        const double l = a[j] * rinv;                         // column j of L (lanes > j); LAPACK dpotf2 scales by 1/ajj too
+        const double sd = d * rinv;                           // the pivot itself: d * d^-1/2 with one correction step (off the chain)
+        const double lref = fma(fma(-sd, sd, d), 0.5 * rinv, sd);
+        a[j] = (lane == j) ? (ok ? lref : 1.0) : l;
+        dg = fma(-l, l, dg);                                  // own diagonal entry (meaningful on lanes > j)
         double* cj = col + (j & 1) * DB;
         cj[lane] = l;
-        if (lane == j) rinvs[j] = rinv;
+        const double xj = (((lane == j) ? 1.0 : 0.0) - x[j]) * rinv;     // lanes > j: exactly zero
+        x[j] = xj;
+        if (j + 1 < DB) {
+            d = __shfl_sync(full, dg, j + 1);
+            rinv = rsqrt_normal(d >= DBL_MIN_POS ? d : 1.0);
+        }
         __syncwarp();
 #pragma unroll
-        for (int k = j + 1; k < DB; ++k) a[k] = fma(-l, cj[k], a[k]);      // rank-1 update (only i >= k is used later)
-    }
-#pragma unroll
-    for (int c = 0; c < DB; ++c) Lb[lane * WB_LD + c] = a[c];
-    __syncwarp();
-    // inverse: lane c solves L x = e_c by forward substitution; L[r][k] is a broadcast load
-#pragma unroll
-    for (int r = 0; r < DB; ++r) {
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < r; ++k) {
-            const double lrk = Lb[r * WB_LD + k];
-            if (k & 1) s1 = fma(lrk, x[k], s1); else s0 = fma(lrk, x[k], s0);
+        for (int k = j + 1; k < DB; ++k) {
+            const double ck = cj[k];
+            a[k] = fma(-l, ck, a[k]);                         // rank-1 update (only i >= k is used later)
+            x[k] = fma(ck, xj, x[k]);
         }
-        const double rhs = (r == lane) ? 1.0 : 0.0;
-        x[r] = (r < lane) ? 0.0 : (rhs - (s0 + s1)) * rinvs[r];
     }
     __syncwarp();
     return bad;
@@ -229,11 +245,22 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
     double* Tm = Zd + 4 * DB * ZLD;         // [32][DLD]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* tile = Lbuf + (long long)kt * TS * ld + kt * TS;
-    for (int e = tid; e < TS * TS / 2; e += 256) {
-        int r = e >> 6, c2 = (e & 63) << 1;
-        double2 v = *reinterpret_cast<const double2*>(tile + (long long)r * ld + c2);
-        S[r * DLD + c2] = v.x;
-        S[r * DLD + c2 + 1] = v.y;
+    // 32 double2 loads per thread, 16 in flight at a time (the tile comes from L2: latency, not bandwidth)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        double2 v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int e = tid + (half * 16 + u) * 256;
+            v[u] = *reinterpret_cast<const double2*>(tile + (long long)(e >> 6) * ld + ((e & 63) << 1));
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int e = tid + (half * 16 + u) * 256;
+            const int r = e >> 6, c2 = (e & 63) << 1;
+            S[r * DLD + c2] = v[u].x;
+            S[r * DLD + c2 + 1] = v[u].y;
+        }
     }
     __syncthreads();
     stamp();                                 // 1: tile loaded
@@ -244,7 +271,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
             double a[DB], x[DB];
 #pragma unroll
             for (int c = 0; c < DB; ++c) a[c] = S[(j0 + lane) * DLD + j0 + c];
-            const int bad = warp_potrf_trtri32(a, x, lane, Tm);        // Tm is free until the off-diagonal inverse phase
+            const int bad = warp_potrf_trtri32(a, x, S[(j0 + lane) * DLD + j0 + lane], lane, Tm);   // Tm is free until the off-diagonal inverse phase
             if (bad && lane == 0) atomicCAS(info, 0, kt * TS + j0 + bad);
 #pragma unroll
             for (int c = 0; c < DB; ++c) {
@@ -325,7 +352,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_panel_kernel(const __gr
                                                                      const __grid_constant__ CUtensorMap mapD,
                                                                      double* __restrict__ Lbuf, long long ld, int kt,
                                                                      double* __restrict__ rhs, const double* __restrict__ sol, int Npad,
-                                                                     int p) {
+                                                                     int p, int first_tile) {
     extern __shared__ __align__(128) double smem[];
     __shared__ PipeBarriers pipe;
     __shared__ double zs[MAXP][TS];
@@ -333,7 +360,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_panel_kernel(const __gr
     if (rhs != nullptr)
         for (int e = threadIdx.x; e < p * TS; e += GEMM_THREADS) zs[e / TS][e % TS] = sol[(long long)(e / TS) * Npad + kt * TS + (e % TS)];
     pipe_init(&pipe);
-    const int ti = kt + 1 + blockIdx.x;
+    const int ti = first_tile + blockIdx.x;            // kt + 1, or kt + 2 when the spine kernel makes tile (kt+1, kt)
     double acc[8][4][2];
     acc_clear(acc);
     // k-space of this product is the 128 columns of block column kt: offset k so that k-tile 0 is that block
@@ -382,11 +409,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_panel_kernel(const __gr
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_trailing_kernel(const __grid_constant__ CUtensorMap mapL,
                                                                         double* __restrict__ Lbuf, long long ld, int k0, int k1,
-                                                                        int base, int mode, int njobs) {
+                                                                        int base, int mode, int njobs, int job_skip) {
     extern __shared__ __align__(128) double smem[];
     __shared__ PipeBarriers pipe;
     pipe_init(&pipe);
     auto tile_of = [&](int job, int& ti, int& tj) {
+        job += job_skip;                               // 1: the triangle without its first tile (base, base) -- the spine kernel's
         if (mode == 0) {
             int a, b;
             tri_decode(job, a, b);
@@ -450,7 +478,7 @@ __global__ void __launch_bounds__(H_THREADS, 2) potrf_trailing64_kernel(const __
                                                                        const __grid_constant__ CUtensorMap mapL64,
                                                                        double* __restrict__ Lbuf, long long ld, int k0, int k1, int base,
                                                                        int mode, int njobs, int* __restrict__ job_counter,
-                                                                       int reserved_sm) {
+                                                                       int reserved_sm, int job_skip) {
     extern __shared__ __align__(128) double smem[];
     __shared__ __align__(8) uint64_t full[H_NSTAGE], empty[H_NSTAGE], slot_full[2], slot_empty[2];
     __shared__ int job_slot[2];
@@ -463,6 +491,7 @@ __global__ void __launch_bounds__(H_THREADS, 2) potrf_trailing64_kernel(const __
     }
     __syncthreads();
     auto decode = [&](int job, int& ti, int& tj, int& half) {
+        job += job_skip;                               // 2: both halves of tile (base, base) belong to the spine kernel
         half = job & 1;
         const int tjob = job >> 1;
         if (mode == 0) {
@@ -566,6 +595,98 @@ __global__ void __launch_bounds__(H_THREADS, 2) potrf_trailing64_kernel(const __
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[st]);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Spine step: the two tiles between one diagonal tile and the next,
+//     L[k+1,k] = A[k+1,k] Dinv_k^T          (+ its mirror, + the forward-substitution update y_{k+1} -= L[k+1,k] z_k)
+//     A[k+1,k+1] -= L[k+1,k] L[k+1,k]^T     (lower 32-blocks)
+// as ONE launch of an 8-CTA cluster.  As single 128^3 tiles of the panel and look-ahead launches these two products cost
+// 2 x 17 us of DMMA time on one SM each (plus two launches) on the chain  diag(k) -> panel -> column -> diag(k+1), i.e. more than the
+// diagonal tile itself; here each CTA owns a 64 x 32 block of the output (rank = 4 * row half + column quarter), stages its
+// 64 + 32 operand rows in shared memory and runs the small DMMA product of the diagonal-tile kernel (smem_gemm), the second
+// product reading the first one's result back from L2 after a cluster barrier.  The spine stream is then
+// diag(k) -> spine(k) -> diag(k+1); the wide panel / trailing kernels only feed it (factorize_device).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SPINE_CTAS = 8;
+constexpr int SP_LDC = 33, SP_LDY = 9;
+constexpr int SPINE_SMEM_BYTES = (64 * DLD + 32 * DLD + 64 * SP_LDC + 8 * DLD + 64 * SP_LDY) * 8;   // 131,328 B
+
+// rows x 128 doubles from global memory (leading dimension ld, read through L2) into shared memory rows of DLD doubles
+__device__ __forceinline__ void spine_stage_rows(double* dst, const double* src, long long ld, int rows) {
+    const int n2 = rows * 64;
+    for (int e0 = threadIdx.x; e0 < n2; e0 += 256 * 8) {
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * 256;
+            if (e < n2) v[u] = __ldcg(reinterpret_cast<const double2*>(src + (long long)(e >> 6) * ld + ((e & 63) << 1)));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * 256;
+            if (e < n2) *reinterpret_cast<double2*>(dst + (e >> 6) * DLD + ((e & 63) << 1)) = v[u];
+        }
+    }
+}
+
+__global__ void __cluster_dims__(SPINE_CTAS, 1, 1) __launch_bounds__(256, 1)
+    potrf_spine_kernel(double* Lbuf, long long ld, int kt, const double* __restrict__ dinv, double* rhs, const double* __restrict__ sol, int Npad,
+                       int p) {
+    extern __shared__ __align__(16) double sp[];
+    double* As = sp;                          // [64][DLD]
+    double* Bs = As + 64 * DLD;               // [32][DLD]
+    double* Cs = Bs + 32 * DLD;               // [64][SP_LDC]
+    double* Zs = Cs + 64 * SP_LDC;            // [8][DLD]
+    double* Cy = Zs + 8 * DLD;                // [64][SP_LDY]
+    const int tid = threadIdx.x;
+    const int rank = blockIdx.x % SPINE_CTAS, h = rank >> 2, q = rank & 3;
+    double* panel = Lbuf + ((long long)(kt + 1) * TS) * ld + (long long)kt * TS;            // tile (k+1, k)
+    double* mirror = Lbuf + ((long long)kt * TS) * ld + (long long)(kt + 1) * TS;           // tile (k, k+1)
+    double* next = Lbuf + ((long long)(kt + 1) * TS) * ld + (long long)(kt + 1) * TS;       // tile (k+1, k+1)
+    // ---- product 1: P[64h.., 32q..] = A[64h.., :] Dinv[32q.., :]^T; Dinv row c is zero beyond column c -------------------------
+    spine_stage_rows(As, panel + (long long)(64 * h) * ld, ld, 64);
+    spine_stage_rows(Bs, dinv + (long long)kt * TS * TS + (long long)(32 * q) * TS, TS, 32);
+    __syncthreads();
+    smem_gemm<false, false>(Cs, SP_LDC, As, DLD, Bs, DLD, 64, 32, 32 * (q + 1), 1.0, 0.0, false);
+    __syncthreads();
+    for (int e = tid; e < 64 * 32; e += 256) {
+        const int r = e >> 5, c = e & 31;
+        panel[(long long)(64 * h + r) * ld + 32 * q + c] = Cs[r * SP_LDC + c];
+    }
+    for (int e = tid; e < 64 * 32; e += 256) {
+        const int r = e & 63, c = e >> 6;
+        mirror[(long long)(32 * q + c) * ld + 64 * h + r] = Cs[r * SP_LDC + c];
+    }
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    // ---- product 2: A'[64h.., 32q..] -= P[64h.., :] P[32q.., :]^T (blocks entirely above the diagonal are never read) -----------
+    const bool lower = !(h == 0 && q >= 2);
+    const bool fwd = (q == 0) && (rhs != nullptr);
+    if (!lower && !fwd) return;
+    spine_stage_rows(As, panel + (long long)(64 * h) * ld, ld, 64);
+    if (lower) {
+        spine_stage_rows(Bs, panel + (long long)(32 * q) * ld, ld, 32);
+        for (int e = tid; e < 64 * 32; e += 256) {
+            const int r = e >> 5, c = e & 31;
+            Cs[r * SP_LDC + c] = __ldcg(next + (long long)(64 * h + r) * ld + 32 * q + c);
+        }
+    }
+    if (fwd)
+        for (int e = tid; e < 8 * TS; e += 256) Zs[(e >> 7) * DLD + (e & 127)] = ((e >> 7) < p) ? sol[(long long)(e >> 7) * Npad + kt * TS + (e & 127)] : 0.0;
+    __syncthreads();
+    if (lower) smem_gemm<false, false>(Cs, SP_LDC, As, DLD, Bs, DLD, 64, 32, TS, -1.0, 1.0, false);
+    if (fwd) smem_gemm<false, false>(Cy, SP_LDY, As, DLD, Zs, DLD, 64, 8, TS, 1.0, 0.0, false);
+    __syncthreads();
+    if (lower)
+        for (int e = tid; e < 64 * 32; e += 256) {
+            const int r = e >> 5, c = e & 31;
+            next[(long long)(64 * h + r) * ld + 32 * q + c] = Cs[r * SP_LDC + c];
+        }
+    if (fwd && tid < 64 * p) {
+        const int r = tid & 63, qq = tid >> 6;
+        rhs[(long long)qq * Npad + (kt + 1) * TS + 64 * h + r] -= Cy[r * SP_LDY + qq];
     }
 }
 

@@ -95,7 +95,7 @@ struct gptb_handle {
     int flags_stride = 0;                     // 32-bit words per mask row
     int pipeline = 0;                         // 1 overlaps the generator of batch i+1 with the products of batch i (opt-in: measured no gain, the
                                               // int8 products run at the 1 kW power cap, so the two kernels share one energy budget)
-    std::vector<cudaEvent_t> ev_diag, ev_col; // per-step dependencies between the two streams
+    std::vector<cudaEvent_t> ev_diag, ev_col, ev_spine; // per-step dependencies between the two streams
     std::string err;
     long long N = 0, Npad = 0;
     int T = 0, d = 0, p = 0;
@@ -106,6 +106,7 @@ struct gptb_handle {
     int* chain_flags = nullptr;              // trsv_back_chain_kernel: flag[k] == chain_epoch once x_k is published
     int chain_epoch = 0, chain_cap = 0;
     int back_variant = 1;                    // 1 = one chained launch, 0 = one launch per block (developer A/B)
+    int spine_variant = 1;                   // 1 = diag -> spine cluster kernel -> diag on the aux stream, 0 = round-1 schedule (developer A/B)
     CUtensorMap mapL, mapD, mapM, mapW;      // TMA views of Lbuf, Dinv, Minv, Wbuf
     CUtensorMap mapL64;                      // Lbuf with a 64-row box (half-tile trailing update)
     // INT8-sliced variance path (ozaki.cuh): digit planes of the inverse factor + per-row scales
@@ -218,6 +219,7 @@ static int set_kernel_attrs(gptb_handle* h) {
     CU(h, cudaFuncSetAttribute(kinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(trmm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(trsv_back_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BACKCHAIN_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(potrf_spine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPINE_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<4>::SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<4>::SMEM_SKIP_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<5>::SMEM_BYTES));
@@ -300,6 +302,7 @@ extern "C" void gptb_destroy(gptb_handle* h) {
         for (auto& e : v) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : h->ev_diag) cudaEventDestroy(e);
     for (auto e : h->ev_col) cudaEventDestroy(e);
+    for (auto e : h->ev_spine) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_gen[i]); cudaEventDestroy(h->ev_done[i]); }
     cudaEventDestroy(h->ev_start);
     cudaStreamSynchronize(h->gen);
@@ -331,6 +334,7 @@ extern "C" int gptb_set_debug_option(gptb_handle* h, const char* name, int value
     else if (!strcmp(name, "oz_force_skip_variant")) h->oz_force_skip = value != 0;
     else if (!strcmp(name, "oz_whatif")) h->oz_whatif = value;
     else if (!strcmp(name, "back_substitution_variant")) h->back_variant = value != 0;
+    else if (!strcmp(name, "spine_variant")) h->spine_variant = value != 0;
     else if (!strcmp(name, "batch_cap")) { if (value < 128 || value % 128) GPTB_FAIL(h, -1, "batch_cap must be a multiple of 128"); h->batch_cap = value; }
     else GPTB_FAIL(h, -1, "gptb_set_debug_option: unknown option '%s'", name);
     return 0;
@@ -549,11 +553,42 @@ static int launch_scale(gptb_handle* h) {
     return 0;
 }
 
-// Gram + blocked right-looking Cholesky with one step of look-ahead, forward substitution fused in.
+// Gram + blocked right-looking Cholesky with one step of look-ahead, forward substitution fused in.  Two schedules:
+//
+// spine_variant 1 (default): the serial chain lives on the aux stream as small kernels,
+//   aux  stream : diag(k) -> [wait trailing(k-1)] -> spine(k) = tiles (k+1,k) and (k+1,k+1), one 8-CTA cluster -> diag(k+1) -> ...
+//   main stream : [wait diag(k)] panel(k), rows >= k+2 -> [wait spine(k)] trailing(k): every tile of columns >= k+1 but (k+1,k+1)
+// so one step of the chain is diag + spine (~45 + ~12 us) and the wide kernels only have to keep up with it.
+//
+// spine_variant 0 (round 1): the chain is diag(k+1) <- look-ahead column k+1 <- panel(k) <- diag(k), three launches of which two are
+// full 128^3 tiles on one SM each (~17 us of DMMA time apiece):
 //   main stream : panel(k) -> trailing column k+1 -> [event] -> rest of trailing(k)            (wide kernels)
 //   aux  stream : [wait column event] -> diagonal tile k+1 (factor + inverse + z_{k+1}) -> [event]   (one CTA)
-// so the serial diagonal-tile kernel runs underneath the bulk of the previous trailing update.  The persistent
-// trailing kernel is launched on at most (#SM - 1) CTAs to keep one SM free for that diagonal-tile CTA.
+// In both, the persistent trailing kernel leaves one SM free for the diagonal-tile CTA.
+static int launch_trailing(gptb_handle* h, int kt, int base, int skip_first_tile, int nsm) {
+    const long long ld = h->Npad;
+    const int r2 = h->T - base;
+    const int njobs = r2 * (r2 + 1) / 2 - skip_first_tile;
+    if (njobs <= 0) return 0;
+    if (h->trailing_variant == 0) {
+        const int grid = njobs < nsm - 1 ? njobs : nsm - 1;
+        tic(h, 2);
+        potrf_trailing_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->Lbuf, ld, kt, kt + 1, base, 0, njobs, skip_first_tile);
+        toc(h, 2);
+    } else {
+        // half tiles, two CTAs per SM, dynamic queue; SM nsm-1 stays free for the look-ahead diagonal tile
+        const int njobs2 = 2 * njobs;
+        const int grid = njobs2 < 2 * nsm ? njobs2 : 2 * nsm;
+        CU(h, cudaMemsetAsync(h->info + 2, 0, sizeof(int), h->stream));
+        tic(h, 2);
+        potrf_trailing64_kernel<<<grid, H_THREADS, H_SMEM_BYTES, h->stream>>>(h->mapL, h->mapL64, h->Lbuf, ld, kt, kt + 1, base, 0, njobs2, h->info + 2,
+                                                                            njobs2 > 2 * (nsm - 1) ? nsm - 1 : -1, 2 * skip_first_tile);
+        toc(h, 2);
+    }
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
 static int factorize_device(gptb_handle* h) {
     const int T = h->T;
     const long long ld = h->Npad;
@@ -561,11 +596,13 @@ static int factorize_device(gptb_handle* h) {
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
     while ((int)h->ev_diag.size() < T + 1) {
-        cudaEvent_t a, b;
+        cudaEvent_t a, b, c;
         CU(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
         CU(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&c, cudaEventDisableTiming));
         h->ev_diag.push_back(a);
         h->ev_col.push_back(b);
+        h->ev_spine.push_back(c);
     }
     CU(h, cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
     CU(h, cudaMemcpyAsync(h->tmp1, h->Y, sizeof(double) * p * h->Npad, cudaMemcpyDeviceToDevice, h->stream));
@@ -581,39 +618,42 @@ static int factorize_device(gptb_handle* h) {
     potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->aux>>>(h->Lbuf, ld, 0, h->Dinv, h->info, h->tmp1, h->tmp2, Npad, p);
     LAUNCH_CHECK(h);
     CU(h, cudaEventRecord(h->ev_diag[0], h->aux));
-    for (int kt = 0; kt < T; ++kt) {
-        CU(h, cudaStreamWaitEvent(h->stream, h->ev_diag[kt], 0));
-        const int r = T - kt - 1;
-        if (r <= 0) break;
-        potrf_panel_kernel<<<r, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->mapD, h->Lbuf, ld, kt, h->tmp1, h->tmp2, Npad, p);
-        LAUNCH_CHECK(h);
-        // look-ahead column: tiles (i, kt+1), i >= kt+1
-        potrf_trailing_kernel<<<r, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->Lbuf, ld, kt, kt + 1, kt + 1, 1, r);
-        LAUNCH_CHECK(h);
-        CU(h, cudaEventRecord(h->ev_col[kt], h->stream));
-        CU(h, cudaStreamWaitEvent(h->aux, h->ev_col[kt], 0));
-        potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->aux>>>(h->Lbuf, ld, kt + 1, h->Dinv, h->info, h->tmp1, h->tmp2, Npad, p);
-        LAUNCH_CHECK(h);
-        CU(h, cudaEventRecord(h->ev_diag[kt + 1], h->aux));
-        if (r > 1) {
-            const int r2 = r - 1;
-            const int njobs = r2 * (r2 + 1) / 2;
-            if (h->trailing_variant == 0) {
-                const int grid = njobs < nsm - 1 ? njobs : nsm - 1;
-                tic(h, 2);
-                potrf_trailing_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->Lbuf, ld, kt, kt + 1, kt + 2, 0, njobs);
-                toc(h, 2);
-            } else {
-                // half tiles, two CTAs per SM, dynamic queue; SM nsm-1 stays free for the look-ahead diagonal tile
-                const int njobs2 = 2 * njobs;
-                const int grid = njobs2 < 2 * nsm ? njobs2 : 2 * nsm;
-                CU(h, cudaMemsetAsync(h->info + 2, 0, sizeof(int), h->stream));
-                tic(h, 2);
-                potrf_trailing64_kernel<<<grid, H_THREADS, H_SMEM_BYTES, h->stream>>>(h->mapL, h->mapL64, h->Lbuf, ld, kt, kt + 1, kt + 2, 0, njobs2, h->info + 2,
-                                                                                    njobs2 > 2 * (nsm - 1) ? nsm - 1 : -1);
-                toc(h, 2);
-            }
+    if (h->spine_variant == 1) {
+        for (int kt = 0; kt + 1 < T; ++kt) {
+            const int r = T - kt - 1;
+            if (kt > 0) CU(h, cudaStreamWaitEvent(h->aux, h->ev_col[kt - 1], 0));          // trailing(kt-1) has updated tiles (kt+1, kt) and (kt+1, kt+1)
+            potrf_spine_kernel<<<SPINE_CTAS, 256, SPINE_SMEM_BYTES, h->aux>>>(h->Lbuf, ld, kt, h->Dinv, h->tmp1, h->tmp2, Npad, p);
             LAUNCH_CHECK(h);
+            CU(h, cudaEventRecord(h->ev_spine[kt], h->aux));
+            potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->aux>>>(h->Lbuf, ld, kt + 1, h->Dinv, h->info, h->tmp1, h->tmp2, Npad, p);
+            LAUNCH_CHECK(h);
+            CU(h, cudaEventRecord(h->ev_diag[kt + 1], h->aux));
+            if (r > 1) {
+                CU(h, cudaStreamWaitEvent(h->stream, h->ev_diag[kt], 0));
+                potrf_panel_kernel<<<r - 1, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->mapD, h->Lbuf, ld, kt, h->tmp1, h->tmp2, Npad, p, kt + 2);
+                LAUNCH_CHECK(h);
+                CU(h, cudaStreamWaitEvent(h->stream, h->ev_spine[kt], 0));
+                if ((rc = launch_trailing(h, kt, kt + 1, 1, nsm))) return rc;
+                CU(h, cudaEventRecord(h->ev_col[kt], h->stream));
+            }
+        }
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_diag[T - 1], 0));
+    } else {
+        for (int kt = 0; kt < T; ++kt) {
+            CU(h, cudaStreamWaitEvent(h->stream, h->ev_diag[kt], 0));
+            const int r = T - kt - 1;
+            if (r <= 0) break;
+            potrf_panel_kernel<<<r, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->mapD, h->Lbuf, ld, kt, h->tmp1, h->tmp2, Npad, p, kt + 1);
+            LAUNCH_CHECK(h);
+            // look-ahead column: tiles (i, kt+1), i >= kt+1
+            potrf_trailing_kernel<<<r, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->Lbuf, ld, kt, kt + 1, kt + 1, 1, r, 0);
+            LAUNCH_CHECK(h);
+            CU(h, cudaEventRecord(h->ev_col[kt], h->stream));
+            CU(h, cudaStreamWaitEvent(h->aux, h->ev_col[kt], 0));
+            potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->aux>>>(h->Lbuf, ld, kt + 1, h->Dinv, h->info, h->tmp1, h->tmp2, Npad, p);
+            LAUNCH_CHECK(h);
+            CU(h, cudaEventRecord(h->ev_diag[kt + 1], h->aux));
+            if (r > 1 && (rc = launch_trailing(h, kt, kt + 2, 0, nsm))) return rc;
         }
     }
     int info = 0;
