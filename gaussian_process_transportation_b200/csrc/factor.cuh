@@ -233,13 +233,23 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
                                                             int* info, const double* __restrict__ rhs, double* __restrict__ sol,
                                                             int Npad, int p, long long* __restrict__ prof = nullptr) {
     extern __shared__ __align__(16) double sm[];
-    __shared__ double ys[MAXP][TS];
+    __shared__ double ys[8][TS];             // right-hand sides, rows >= p zero (the 8 columns of a DMMA B fragment)
     // prof (developer hook, gptb_test_potrf_tile): clock64 at the phase boundaries, written by thread 0
     int pslot = 0;
-    auto stamp = [&]() { if (prof != nullptr && threadIdx.x == 0) prof[pslot] = clock64(); ++pslot; };
+    auto stamp = [&]() {
+        if (prof != nullptr && threadIdx.x == 0) {
+            prof[pslot] = clock64();
+            if (pslot == 0 || pslot == 12) {              // wall clock (ns) beside the first and last cycle stamp: the SM clock the tile ran at
+                unsigned long long ns;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+                prof[pslot == 0 ? 20 : 21] = (long long)ns;
+            }
+        }
+        ++pslot;
+    };
     stamp();
     if (rhs != nullptr)
-        for (int e = threadIdx.x; e < p * TS; e += 256) ys[e / TS][e % TS] = rhs[(long long)(e / TS) * Npad + kt * TS + (e % TS)];
+        for (int e = threadIdx.x; e < 8 * TS; e += 256) ys[e / TS][e % TS] = (e / TS < p) ? rhs[(long long)(e / TS) * Npad + kt * TS + (e % TS)] : 0.0;
     double* S = sm;                         // [128][DLD]
     double* Zd = sm + TS * DLD;             // [4][32][ZLD]
     double* Tm = Zd + 4 * DB * ZLD;         // [32][DLD]
@@ -327,18 +337,23 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
         else if (bi > bj) v = S[c * DLD + r];
         dk[r * TS + c] = v;
     }
-    if (rhs != nullptr && tid < TS) {
-        const int r = tid, bi = r >> 5, rl = r & 31;
-        double z[MAXP] = {0.0, 0.0, 0.0, 0.0};
-        for (int c = 0; c < bi * DB; ++c) {
-            const double v = S[c * DLD + r];
-            for (int q = 0; q < p; ++q) z[q] = fma(v, ys[q][c], z[q]);
+    if (rhs != nullptr) {
+        // z = Linv y as a DMMA product with the right-hand sides as the 8 (padded) columns of B: 16 strips of 8 rows, two per warp
+        // (w and 15 - w: the work per strip grows with the row).  Off-diagonal blocks are read as (Linv_ij)^T from S's upper half,
+        // the diagonal block from Zd.  (The first version ran 128 threads through a scalar loop with the accumulators indexed by a
+        // run-time p -- local memory -- and took 35 k of the kernel's 114 k cycles.)
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int strip = half == 0 ? warp : 15 - warp;
+            const int r0 = strip * 8, bi = r0 >> 5;
+            double z0 = 0.0, z1 = 0.0;
+            for (int k0 = 0; k0 < bi * DB; k0 += 4) dmma884(z0, z1, S[(k0 + t) * DLD + r0 + g], ys[g][k0 + t]);
+            const double* zd = Zd + (bi * DB + (r0 & 31) + g) * ZLD;
+            for (int k0 = 0; k0 < DB; k0 += 4) dmma884(z0, z1, zd[k0 + t], ys[g][bi * DB + k0 + t]);
+            if (2 * t < p) sol[(long long)(2 * t) * Npad + kt * TS + r0 + g] = z0;
+            if (2 * t + 1 < p) sol[(long long)(2 * t + 1) * Npad + kt * TS + r0 + g] = z1;
         }
-        for (int cc = 0; cc <= rl; ++cc) {
-            const double v = Zd[(bi * DB + rl) * ZLD + cc];
-            for (int q = 0; q < p; ++q) z[q] = fma(v, ys[q][bi * DB + cc], z[q]);
-        }
-        for (int q = 0; q < p; ++q) sol[(long long)q * Npad + kt * TS + r] = z[q];
     }
     __syncthreads();
     stamp();                                 // 12: inverse written, forward substitution done
@@ -482,7 +497,7 @@ __global__ void __launch_bounds__(H_THREADS, 2) potrf_trailing64_kernel(const __
     extern __shared__ __align__(128) double smem[];
     __shared__ __align__(8) uint64_t full[H_NSTAGE], empty[H_NSTAGE], slot_full[2], slot_empty[2];
     __shared__ int job_slot[2];
-    if ((int)smid() == reserved_sm) return;
+    if (reserved_sm >= 0 && (int)smid() >= reserved_sm) return;      // SMs reserved_sm .. #SM-1 stay free for the spine stream
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int i = 0; i < H_NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], H_CONS / 32); }
@@ -602,13 +617,21 @@ __global__ void __launch_bounds__(H_THREADS, 2) potrf_trailing64_kernel(const __
 // Spine step: the two tiles between one diagonal tile and the next,
 //     L[k+1,k] = A[k+1,k] Dinv_k^T          (+ its mirror, + the forward-substitution update y_{k+1} -= L[k+1,k] z_k)
 //     A[k+1,k+1] -= L[k+1,k] L[k+1,k]^T     (lower 32-blocks)
-// as ONE launch of an 8-CTA cluster.  As single 128^3 tiles of the panel and look-ahead launches these two products cost
+// as ONE launch of eight CTAs.  As single 128^3 tiles of the panel and look-ahead launches these two products cost
 // 2 x 17 us of DMMA time on one SM each (plus two launches) on the chain  diag(k) -> panel -> column -> diag(k+1), i.e. more than the
 // diagonal tile itself; here each CTA owns a 64 x 32 block of the output (rank = 4 * row half + column quarter), stages its
 // 64 + 32 operand rows in shared memory and runs the small DMMA product of the diagonal-tile kernel (smem_gemm), the second
-// product reading the first one's result back from L2 after a cluster barrier.  The spine stream is then
+// product reading the first one's result back from L2 after a barrier over the eight CTAs (a counter in global memory: a cluster
+// would have to find its eight SMs inside one GPC, and the SMs the trailing kernel leaves free are not chosen by GPC).  The spine stream is then
 // diag(k) -> spine(k) -> diag(k+1); the wide panel / trailing kernels only feed it (factorize_device).
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_s32(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
 constexpr int SPINE_CTAS = 8;
 constexpr int SP_LDC = 33, SP_LDY = 9;
 constexpr int SPINE_SMEM_BYTES = (64 * DLD + 32 * DLD + 64 * SP_LDC + 8 * DLD + 64 * SP_LDY) * 8;   // 131,328 B
@@ -631,9 +654,9 @@ __device__ __forceinline__ void spine_stage_rows(double* dst, const double* src,
     }
 }
 
-__global__ void __cluster_dims__(SPINE_CTAS, 1, 1) __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 1)
     potrf_spine_kernel(double* Lbuf, long long ld, int kt, const double* __restrict__ dinv, double* rhs, const double* __restrict__ sol, int Npad,
-                       int p) {
+                       int p, int* arrivals, int arrivals_target) {
     extern __shared__ __align__(16) double sp[];
     double* As = sp;                          // [64][DLD]
     double* Bs = As + 64 * DLD;               // [32][DLD]
@@ -649,7 +672,10 @@ __global__ void __cluster_dims__(SPINE_CTAS, 1, 1) __launch_bounds__(256, 1)
     spine_stage_rows(As, panel + (long long)(64 * h) * ld, ld, 64);
     spine_stage_rows(Bs, dinv + (long long)kt * TS * TS + (long long)(32 * q) * TS, TS, 32);
     __syncthreads();
+    if (tid == 0) atomicAdd(arrivals, 1);           // "my rows of A are staged": the product is in place, nobody may store before all have read
     smem_gemm<false, false>(Cs, SP_LDC, As, DLD, Bs, DLD, 64, 32, 32 * (q + 1), 1.0, 0.0, false);
+    if (tid == 0)
+        while (ld_acquire_gpu_s32(arrivals) < arrivals_target - SPINE_CTAS) {}
     __syncthreads();
     for (int e = tid; e < 64 * 32; e += 256) {
         const int r = e >> 5, c = e & 31;
@@ -659,8 +685,15 @@ __global__ void __cluster_dims__(SPINE_CTAS, 1, 1) __launch_bounds__(256, 1)
         const int r = e & 63, c = e >> 6;
         mirror[(long long)(32 * q + c) * ld + 64 * h + r] = Cs[r * SP_LDC + c];
     }
-    __threadfence();
-    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    // all eight CTAs meet again (the launch is 8 CTAs on a stream of its own and the trailing kernel keeps SMs free for it; CTAs that
+    // start late only make the others wait)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(arrivals, 1);
+        while (ld_acquire_gpu_s32(arrivals) < arrivals_target) {}
+    }
+    __syncthreads();
     // ---- product 2: A'[64h.., 32q..] -= P[64h.., :] P[32q.., :]^T (blocks entirely above the diagonal are never read) -----------
     const bool lower = !(h == 0 && q >= 2);
     const bool fwd = (q == 0) && (rhs != nullptr);
@@ -773,13 +806,6 @@ __global__ void __launch_bounds__(256) trsv_back_step_kernel(const double* __res
 // producer off the machine (the decoupled-look-back argument), whatever T is.  Summation order is fixed: deterministic.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int BACKCHAIN_SMEM_BYTES = TS * TS * (int)sizeof(double);
-
-__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu_s32(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 __global__ void __launch_bounds__(256, 1) trsv_back_chain_kernel(const double* __restrict__ Lbuf, long long ld, const double* __restrict__ dinv,
                                                                  const double* __restrict__ rhs, double* sol, int Npad, int p, int T, int* flags,

@@ -95,7 +95,8 @@ struct gptb_handle {
     int flags_stride = 0;                     // 32-bit words per mask row
     int pipeline = 0;                         // 1 overlaps the generator of batch i+1 with the products of batch i (opt-in: measured no gain, the
                                               // int8 products run at the 1 kW power cap, so the two kernels share one energy budget)
-    std::vector<cudaEvent_t> ev_diag, ev_col, ev_spine; // per-step dependencies between the two streams
+    std::vector<cudaEvent_t> ev_diag, ev_col, ev_spine, ev_panel; // per-step dependencies between the factorisation's streams
+    cudaStream_t head = nullptr;             // the two trailing tiles the next spine step needs (factorize_device)
     std::string err;
     long long N = 0, Npad = 0;
     int T = 0, d = 0, p = 0;
@@ -255,6 +256,7 @@ extern "C" int gptb_create(int device, gptb_handle** out) {
     if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_main) != cudaSuccess) { delete h; return -2; }
     if (cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete h; return -2; }
     if (cudaStreamCreateWithPriority(&h->gen, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete h; return -2; }
+    if (cudaStreamCreateWithPriority(&h->head, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete h; return -2; }
     for (int i = 0; i < 2; ++i)
         if (cudaEventCreateWithFlags(&h->ev_gen[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return -2; }
@@ -263,7 +265,7 @@ extern "C" int gptb_create(int device, gptb_handle** out) {
     for (int i = 0; i < 2; ++i)
         if (cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_cd[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_oc[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return -2; }
-    if (cudaMalloc(&h->info, 4 * sizeof(int)) != cudaSuccess || cudaMalloc(&h->scal, 64 * sizeof(double)) != cudaSuccess ||
+    if (cudaMalloc(&h->info, 8 * sizeof(int)) != cudaSuccess || cudaMalloc(&h->scal, 64 * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->header, 32 * sizeof(double)) != cudaSuccess) {
         delete h;
         return -2;
@@ -303,10 +305,12 @@ extern "C" void gptb_destroy(gptb_handle* h) {
     for (auto e : h->ev_diag) cudaEventDestroy(e);
     for (auto e : h->ev_col) cudaEventDestroy(e);
     for (auto e : h->ev_spine) cudaEventDestroy(e);
+    for (auto e : h->ev_panel) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_gen[i]); cudaEventDestroy(h->ev_done[i]); }
     cudaEventDestroy(h->ev_start);
     cudaStreamSynchronize(h->gen);
     cudaStreamDestroy(h->gen);
+    cudaStreamDestroy(h->head);
     cudaStreamDestroy(h->aux);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -565,25 +569,39 @@ static int launch_scale(gptb_handle* h) {
 //   main stream : panel(k) -> trailing column k+1 -> [event] -> rest of trailing(k)            (wide kernels)
 //   aux  stream : [wait column event] -> diagonal tile k+1 (factor + inverse + z_{k+1}) -> [event]   (one CTA)
 // In both, the persistent trailing kernel leaves one SM free for the diagonal-tile CTA.
-static int launch_trailing(gptb_handle* h, int kt, int base, int skip_first_tile, int nsm) {
+// tiles [first, first + count) of the row-major lower-triangle enumeration with origin (base, base); count < 0: to the end
+static int launch_trailing(gptb_handle* h, cudaStream_t st, int kt, int base, int first, int count, int nsm, int* counter) {
     const long long ld = h->Npad;
     const int r2 = h->T - base;
-    const int njobs = r2 * (r2 + 1) / 2 - skip_first_tile;
+    const int njobs = count >= 0 ? count : r2 * (r2 + 1) / 2 - first;
     if (njobs <= 0) return 0;
     if (h->trailing_variant == 0) {
         const int grid = njobs < nsm - 1 ? njobs : nsm - 1;
-        tic(h, 2);
-        potrf_trailing_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->Lbuf, ld, kt, kt + 1, base, 0, njobs, skip_first_tile);
-        toc(h, 2);
+        tic(h, 2, st);
+        potrf_trailing_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(h->mapL, h->Lbuf, ld, kt, kt + 1, base, 0, njobs, first);
+        toc(h, 2, st);
     } else {
-        // half tiles, two CTAs per SM, dynamic queue; SM nsm-1 stays free for the look-ahead diagonal tile
+        // half tiles, two CTAs per SM, dynamic queue.  The spine stream needs SMs of its own while this kernel runs: one for the diagonal
+        // tile, eight for the spine kernel (which cannot share an SM with two of these CTAs).  A long update (njobs large) hides the
+        // spine step anyway -- it can wait for this kernel to drain -- so only the diagonal tile's SM is kept free; a short one leaves
+        // eight.  CTAs that land on a reserved SM exit at once (the queue hands their jobs to the others), so the grid carries spares.
         const int njobs2 = 2 * njobs;
-        const int grid = njobs2 < 2 * nsm ? njobs2 : 2 * nsm;
-        CU(h, cudaMemsetAsync(h->info + 2, 0, sizeof(int), h->stream));
-        tic(h, 2);
-        potrf_trailing64_kernel<<<grid, H_THREADS, H_SMEM_BYTES, h->stream>>>(h->mapL, h->mapL64, h->Lbuf, ld, kt, kt + 1, base, 0, njobs2, h->info + 2,
-                                                                            njobs2 > 2 * (nsm - 1) ? nsm - 1 : -1, 2 * skip_first_tile);
-        toc(h, 2);
+        // The head launch (count >= 0) is itself part of the spine's chain: it takes no part in this and may use the reserved SMs.
+        const int reserve = (h->spine_variant == 1 && njobs <= 640) ? SPINE_CTAS : 1;
+        const int workers = 2 * (nsm - reserve);
+        int grid, reserved_from;
+        if (count < 0 && (njobs2 > workers || reserve > 1)) {
+            grid = (njobs2 < workers ? njobs2 : workers) + 2 * reserve;
+            reserved_from = nsm - reserve;
+        } else {
+            grid = njobs2;
+            reserved_from = -1;
+        }
+        CU(h, cudaMemsetAsync(counter, 0, sizeof(int), st));
+        tic(h, 2, st);
+        potrf_trailing64_kernel<<<grid, H_THREADS, H_SMEM_BYTES, st>>>(h->mapL, h->mapL64, h->Lbuf, ld, kt, kt + 1, base, 0, njobs2, counter, reserved_from,
+                                                                     2 * first);
+        toc(h, 2, st);
     }
     LAUNCH_CHECK(h);
     return 0;
@@ -596,15 +614,18 @@ static int factorize_device(gptb_handle* h) {
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
     while ((int)h->ev_diag.size() < T + 1) {
-        cudaEvent_t a, b, c;
+        cudaEvent_t a, b, c, d;
         CU(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
         CU(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
         CU(h, cudaEventCreateWithFlags(&c, cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&d, cudaEventDisableTiming));
         h->ev_diag.push_back(a);
         h->ev_col.push_back(b);
         h->ev_spine.push_back(c);
+        h->ev_panel.push_back(d);
     }
-    CU(h, cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
+    CU(h, cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));            // LAPACK info
+    CU(h, cudaMemsetAsync(h->info + 4, 0, sizeof(int), h->stream));        // arrivals at the spine kernel's barrier
     CU(h, cudaMemcpyAsync(h->tmp1, h->Y, sizeof(double) * p * h->Npad, cudaMemcpyDeviceToDevice, h->stream));
     int rc = launch_scale(h);
     if (rc) return rc;
@@ -621,8 +642,8 @@ static int factorize_device(gptb_handle* h) {
     if (h->spine_variant == 1) {
         for (int kt = 0; kt + 1 < T; ++kt) {
             const int r = T - kt - 1;
-            if (kt > 0) CU(h, cudaStreamWaitEvent(h->aux, h->ev_col[kt - 1], 0));          // trailing(kt-1) has updated tiles (kt+1, kt) and (kt+1, kt+1)
-            potrf_spine_kernel<<<SPINE_CTAS, 256, SPINE_SMEM_BYTES, h->aux>>>(h->Lbuf, ld, kt, h->Dinv, h->tmp1, h->tmp2, Npad, p);
+            if (kt > 0) CU(h, cudaStreamWaitEvent(h->aux, h->ev_col[kt - 1], 0));          // head(kt-1) has updated tiles (kt+1, kt) and (kt+1, kt+1)
+            potrf_spine_kernel<<<SPINE_CTAS, 256, SPINE_SMEM_BYTES, h->aux>>>(h->Lbuf, ld, kt, h->Dinv, h->tmp1, h->tmp2, Npad, p, h->info + 4, 2 * SPINE_CTAS * (kt + 1));
             LAUNCH_CHECK(h);
             CU(h, cudaEventRecord(h->ev_spine[kt], h->aux));
             potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->aux>>>(h->Lbuf, ld, kt + 1, h->Dinv, h->info, h->tmp1, h->tmp2, Npad, p);
@@ -632,12 +653,19 @@ static int factorize_device(gptb_handle* h) {
                 CU(h, cudaStreamWaitEvent(h->stream, h->ev_diag[kt], 0));
                 potrf_panel_kernel<<<r - 1, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(h->mapL, h->mapD, h->Lbuf, ld, kt, h->tmp1, h->tmp2, Npad, p, kt + 2);
                 LAUNCH_CHECK(h);
+                CU(h, cudaEventRecord(h->ev_panel[kt], h->stream));
+                // head: tiles (kt+2, kt+1) and (kt+2, kt+2) -- jobs 1 and 2 of the triangle at (kt+1, kt+1) -- are all the next spine step
+                // needs from this trailing update; they run on their own stream beside the rest
+                CU(h, cudaStreamWaitEvent(h->head, h->ev_panel[kt], 0));
+                CU(h, cudaStreamWaitEvent(h->head, h->ev_spine[kt], 0));
+                if ((rc = launch_trailing(h, h->head, kt, kt + 1, 1, 2, nsm, h->info + 3))) return rc;
+                CU(h, cudaEventRecord(h->ev_col[kt], h->head));
                 CU(h, cudaStreamWaitEvent(h->stream, h->ev_spine[kt], 0));
-                if ((rc = launch_trailing(h, kt, kt + 1, 1, nsm))) return rc;
-                CU(h, cudaEventRecord(h->ev_col[kt], h->stream));
+                if ((rc = launch_trailing(h, h->stream, kt, kt + 1, 3, -1, nsm, h->info + 2))) return rc;
             }
         }
         CU(h, cudaStreamWaitEvent(h->stream, h->ev_diag[T - 1], 0));
+        if (T > 2) CU(h, cudaStreamWaitEvent(h->stream, h->ev_col[T - 3], 0));             // the last head launch
     } else {
         for (int kt = 0; kt < T; ++kt) {
             CU(h, cudaStreamWaitEvent(h->stream, h->ev_diag[kt], 0));
@@ -653,7 +681,7 @@ static int factorize_device(gptb_handle* h) {
             potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->aux>>>(h->Lbuf, ld, kt + 1, h->Dinv, h->info, h->tmp1, h->tmp2, Npad, p);
             LAUNCH_CHECK(h);
             CU(h, cudaEventRecord(h->ev_diag[kt + 1], h->aux));
-            if (r > 1 && (rc = launch_trailing(h, kt, kt + 2, 0, nsm))) return rc;
+            if (r > 1 && (rc = launch_trailing(h, h->stream, kt, kt + 2, 0, -1, nsm, h->info + 2))) return rc;
         }
     }
     int info = 0;
