@@ -497,7 +497,15 @@ __global__ void __launch_bounds__(H_THREADS, 2) potrf_trailing64_kernel(const __
     extern __shared__ __align__(128) double smem[];
     __shared__ __align__(8) uint64_t full[H_NSTAGE], empty[H_NSTAGE], slot_full[2], slot_empty[2];
     __shared__ int job_slot[2];
-    if (reserved_sm >= 0 && (int)smid() >= reserved_sm) return;      // SMs reserved_sm .. #SM-1 stay free for the spine stream
+    // SMs reserved_sm .. #SM-1 stay free for the spine stream: a CTA that lands there leaves at once and the queue hands its jobs to the
+    // others -- unless it is the last one that could (every other CTA of the grid left the same way: the rest of the GPU was busy with
+    // other streams' or other handles' kernels); job_counter[1] counts the leavers.
+    if (reserved_sm >= 0 && (int)smid() >= reserved_sm) {
+        __shared__ int leave;
+        if (threadIdx.x == 0) leave = atomicAdd(job_counter + 1, 1) < (int)gridDim.x - 1;
+        __syncthreads();
+        if (leave) return;
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int i = 0; i < H_NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], H_CONS / 32); }

@@ -103,7 +103,7 @@ struct gptb_handle {
     double *X = nullptr, *Y = nullptr, *Xs = nullptr, *alpha = nullptr, *tmp1 = nullptr, *tmp2 = nullptr;
     double *Lbuf = nullptr, *Dinv = nullptr, *Minv = nullptr, *Wbuf = nullptr, *gradpart = nullptr, *scal = nullptr;
     double* header = nullptr;
-    int* info = nullptr;
+    int* info = nullptr;                     // [0] LAPACK info, [1] product-kernel tile queue, [2..3] trailing queue + leavers, [4] spine barrier, [5..6] head queue
     int* chain_flags = nullptr;              // trsv_back_chain_kernel: flag[k] == chain_epoch once x_k is published
     int chain_epoch = 0, chain_cap = 0;
     int back_variant = 1;                    // 1 = one chained launch, 0 = one launch per block (developer A/B)
@@ -597,7 +597,7 @@ static int launch_trailing(gptb_handle* h, cudaStream_t st, int kt, int base, in
             grid = njobs2;
             reserved_from = -1;
         }
-        CU(h, cudaMemsetAsync(counter, 0, sizeof(int), st));
+        CU(h, cudaMemsetAsync(counter, 0, 2 * sizeof(int), st));            // [0] job queue, [1] CTAs that left a reserved SM
         tic(h, 2, st);
         potrf_trailing64_kernel<<<grid, H_THREADS, H_SMEM_BYTES, st>>>(h->mapL, h->mapL64, h->Lbuf, ld, kt, kt + 1, base, 0, njobs2, counter, reserved_from,
                                                                      2 * first);
@@ -658,7 +658,7 @@ static int factorize_device(gptb_handle* h) {
                 // needs from this trailing update; they run on their own stream beside the rest
                 CU(h, cudaStreamWaitEvent(h->head, h->ev_panel[kt], 0));
                 CU(h, cudaStreamWaitEvent(h->head, h->ev_spine[kt], 0));
-                if ((rc = launch_trailing(h, h->head, kt, kt + 1, 1, 2, nsm, h->info + 3))) return rc;
+                if ((rc = launch_trailing(h, h->head, kt, kt + 1, 1, 2, nsm, h->info + 5))) return rc;
                 CU(h, cudaEventRecord(h->ev_col[kt], h->head));
                 CU(h, cudaStreamWaitEvent(h->stream, h->ev_spine[kt], 0));
                 if ((rc = launch_trailing(h, h->stream, kt, kt + 1, 3, -1, nsm, h->info + 2))) return rc;

@@ -92,6 +92,8 @@ class _Regressor:
 
 
 class GaussianProcess:
+    MAX_CONCURRENT_FITS = 12                             # engine handles used at once by parallel_restarts (see _optimise_concurrently)
+
     def __init__(self, kernel, alpha=1e-10, optimizer='fmin_l_bfgs_b', n_restarts_optimizer=5, n_targets=None, device=None,
                  variance_mode=None, spatial=None, parallel_restarts=None):
         check_supported(kernel)
@@ -214,27 +216,36 @@ class GaussianProcess:
         gp, eng = self.gp, self._engine
         bounds = kernel_.bounds
         starts = [np.array(kernel_.theta, copy=True)] + [rng.uniform(bounds[:, 0], bounds[:, 1]) for _ in range(gp.n_restarts_optimizer)]
-        while len(self._restart_engines) < len(starts) - 1:
+        # at most MAX_CONCURRENT_FITS handles factorise at once: each factorisation keeps a spine kernel of eight CTAs that meet at a
+        # barrier on the GPU, and the handles of one device must never hold all of its SMs with half-started ones
+        n_eng = min(len(starts), self.MAX_CONCURRENT_FITS)
+        while len(self._restart_engines) < n_eng - 1:
             self._restart_engines.append(_lib.Engine(eng.device))
-        engines = [eng] + self._restart_engines[:len(starts) - 1]
+        engines = [eng] + self._restart_engines[:n_eng - 1]
         for e in engines[1:]:
             e.set_kernel_kind(kernel_kind(kernel_))
             e.set_train(self.X, self.Y)
+        import queue
+        free = queue.SimpleQueue()
+        for e in engines:
+            free.put(e)
 
         def run(i):
-            e = engines[i]
+            e = free.get()
+            try:
+                def obj(theta, eval_gradient=True):
+                    k = kernel_.clone_with_theta(theta)              # per-evaluation clone: the runs share no mutable kernel object
+                    c, ell, s2 = read_params(k, e.d)
+                    info, lml, g = e.lml(c, ell, s2, gp.alpha, want_grad=eval_gradient)
+                    if info > 0:
+                        return (np.inf, np.zeros_like(theta)) if eval_gradient else np.inf
+                    return (-lml, -map_gradient(k, g, e.d)) if eval_gradient else -lml
 
-            def obj(theta, eval_gradient=True):
-                k = kernel_.clone_with_theta(theta)              # per-evaluation clone: the runs share no mutable kernel object
-                c, ell, s2 = read_params(k, e.d)
-                info, lml, g = e.lml(c, ell, s2, gp.alpha, want_grad=eval_gradient)
-                if info > 0:
-                    return (np.inf, np.zeros_like(theta)) if eval_gradient else np.inf
-                return (-lml, -map_gradient(k, g, e.d)) if eval_gradient else -lml
+                return self._constrained_optimization(obj, starts[i], bounds)
+            finally:
+                free.put(e)
 
-            return self._constrained_optimization(obj, starts[i], bounds)
-
-        with ThreadPoolExecutor(max_workers=len(starts)) as pool:
+        with ThreadPoolExecutor(max_workers=n_eng) as pool:
             optima = list(pool.map(run, range(len(starts))))
         self._factor_theta = None
         return optima
