@@ -693,8 +693,7 @@ __global__ void __launch_bounds__(256, 1)
         const int r = e & 63, c = e >> 6;
         mirror[(long long)(32 * q + c) * ld + 64 * h + r] = Cs[r * SP_LDC + c];
     }
-    // all eight CTAs meet again (the launch is 8 CTAs on a stream of its own and the trailing kernel keeps SMs free for it; CTAs that
-    // start late only make the others wait)
+    // all eight CTAs meet again (a cooperative launch: they are on the machine together; the trailing kernel keeps SMs free for them)
     __syncthreads();
     if (tid == 0) {
         __threadfence();

@@ -643,8 +643,14 @@ static int factorize_device(gptb_handle* h) {
         for (int kt = 0; kt + 1 < T; ++kt) {
             const int r = T - kt - 1;
             if (kt > 0) CU(h, cudaStreamWaitEvent(h->aux, h->ev_col[kt - 1], 0));          // head(kt-1) has updated tiles (kt+1, kt) and (kt+1, kt+1)
-            potrf_spine_kernel<<<SPINE_CTAS, 256, SPINE_SMEM_BYTES, h->aux>>>(h->Lbuf, ld, kt, h->Dinv, h->tmp1, h->tmp2, Npad, p, h->info + 4, 2 * SPINE_CTAS * (kt + 1));
-            LAUNCH_CHECK(h);
+            {
+                // cooperative launch: the eight CTAs meet at barriers, so they start only when all of them fit on the machine at once
+                // (with several handles factorising on one GPU, half-started spine kernels must not be able to hold every SM)
+                double* a_L = h->Lbuf; long long a_ld = ld; int a_kt = kt; const double* a_D = h->Dinv; double* a_rhs = h->tmp1; const double* a_sol = h->tmp2;
+                int a_Npad = Npad, a_p = p; int* a_arr = h->info + 4; int a_target = 2 * SPINE_CTAS * (kt + 1);
+                void* args[] = {&a_L, &a_ld, &a_kt, &a_D, &a_rhs, &a_sol, &a_Npad, &a_p, &a_arr, &a_target};
+                CU(h, cudaLaunchCooperativeKernel((const void*)potrf_spine_kernel, dim3(SPINE_CTAS), dim3(256), args, SPINE_SMEM_BYTES, h->aux));
+            }
             CU(h, cudaEventRecord(h->ev_spine[kt], h->aux));
             potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, h->aux>>>(h->Lbuf, ld, kt + 1, h->Dinv, h->info, h->tmp1, h->tmp2, Npad, p);
             LAUNCH_CHECK(h);
