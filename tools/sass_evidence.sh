@@ -15,7 +15,7 @@ for f in funcs:
     c = collections.Counter(m for m in re.findall(r"^\s*/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", f, flags=re.M))
     agg = {w: sum(v for k, v in c.items() if k.split(".")[0] == w) for w in want}
     rows.append((name, sum(c.values()), agg))
-hot = ["ozaki_trmm_kernel", "trmm_sumsq_kernel", "kstar_kernel", "potrf_trailing", "potrf_panel", "potrf_diag", "trtri_level", "kinv_kernel", "gram_lower", "lml_grad_kernel", "slice_rows", "finalize_kernel"]
+hot = ["ozaki_trmm_kernel", "trmm_sumsq_kernel", "kstar_kernel", "potrf_trailing", "potrf_panel", "potrf_diag", "potrf_spine", "trsv_back_chain", "trtri_level", "kinv_kernel", "gram_lower", "lml_grad_kernel", "slice_rows", "finalize_kernel"]
 with open('profiles/r02_sass_census.txt', 'w') as o:
     o.write("# cuobjdump -sass gaussian_process_transportation_b200/lib/libgptb200.so: instruction census per kernel (tools/sass_evidence.sh)\n")
     o.write("# UTCIMMA = tcgen05.mma kind::i8, LDTM = tcgen05.ld, UTMALDG = TMA tensor load, UTCBAR = tcgen05.commit, DMMA = FP64 mma.sync, SYNCS = mbarrier ops\n")
