@@ -32,15 +32,17 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --shared -
 python - <<'PY'
 import re
 t = open('/tmp/ptxas_v.txt').read()
-blocks = re.findall(r"Compiling entry function '([^']+)' for 'sm_100a'\n(?:ptxas info\s+: Function properties for [^\n]+\n\s+[^\n]+\n)?ptxas info\s+: Used ([^\n]+)", t)
-hot = ["ozaki_trmm_kernelILi5", "ozaki_trmm_kernelILi6", "trmm_sumsq", "kstar_kernelILi3ELi3ELi2ELi5ELi8", "kstar_kernelILi3ELi3ELi0", "potrf_trailing64", "potrf_diag", "potrf_panel", "lml_grad_kernelILi3", "gram_lower_kernelILi3", "finalize_kernelILi3ELi3"]
+blocks = re.findall(r"Compiling entry function '([^']+)' for 'sm_100a'\n(?:ptxas info\s+: Function properties for [^\n]+\n\s+([^\n]+)\n)?ptxas info\s+: Used ([^\n]+)", t)
+hot = ["ozaki_trmm_kernelILi5", "ozaki_trmm_kernelILi6", "trmm_sumsq", "kstar_kernelILi3ELi3ELi2ELi5ELi8", "kstar_kernelILi3ELi3ELi0", "potrf_trailing64", "potrf_diag", "potrf_spine", "trsv_back_chain", "potrf_panel", "lml_grad_kernelILi3", "gram_lower_kernelILi3", "finalize_kernelILi3ELi3"]
 with open('profiles/r02_ptxas_v.txt', 'w') as o:
-    o.write("# nvcc -Xptxas -v (sm_100a) resource usage of the hot kernels (tools/sass_evidence.sh); no kernel below spills\n")
+    o.write("# nvcc -Xptxas -v (sm_100a) resource usage of the hot kernels (tools/sass_evidence.sh); stack / spill line shown where non-zero\n")
     spills = re.findall(r"(\d+) bytes spill stores", t)
     o.write(f"# spill stores over the whole library: max {max(map(int, spills)) if spills else 0} bytes\n")
-    for name, used in blocks:
+    for name, props, used in blocks:
         if any(h in name for h in hot):
             o.write(f"{name}\n    {used}\n")
+            if props and not props.strip().startswith("0 bytes stack frame, 0 bytes spill stores"):
+                o.write(f"    {props.strip()}\n")
 print(open('profiles/r02_ptxas_v.txt').read()[:1500])
 PY
 python - <<'PY'
