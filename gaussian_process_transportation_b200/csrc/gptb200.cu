@@ -106,6 +106,9 @@ struct gptb_handle {
     int* info = nullptr;                     // [0] LAPACK info, [1] product-kernel tile queue, [2..3] trailing queue + leavers, [4] spine barrier, [5..6] head queue
     int* chain_flags = nullptr;              // trsv_back_chain_kernel: flag[k] == chain_epoch once x_k is published
     int chain_epoch = 0, chain_cap = 0;
+    double* splitk_ws = nullptr;             // partial tiles of the split-k variance product (small batches), splitk_cap = two per SM
+    int splitk_cap = 0;
+    int splitk_on = 1;                       // developer A/B ("variance_splitk")
     int back_variant = 1;                    // 1 = one chained launch, 0 = one launch per block (developer A/B)
     int spine_variant = 1;                   // 1 = diag -> spine cluster kernel -> diag on the aux stream, 0 = round-1 schedule (developer A/B)
     CUtensorMap mapL, mapD, mapM, mapW;      // TMA views of Lbuf, Dinv, Minv, Wbuf
@@ -219,6 +222,7 @@ static int set_kernel_attrs(gptb_handle* h) {
     CU(h, cudaFuncSetAttribute(trtri_level_p2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(kinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(trmm_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CU(h, cudaFuncSetAttribute(trmm_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(trsv_back_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BACKCHAIN_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(potrf_spine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPINE_SMEM_BYTES));
     CU(h, cudaFuncSetAttribute(oz::ozaki_trmm_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<4>::SMEM_BYTES));
@@ -298,6 +302,7 @@ extern "C" void gptb_destroy(gptb_handle* h) {
     if (h->probe) cudaFree(h->probe);
     cudaFree(h->info);
     cudaFree(h->chain_flags);
+    cudaFree(h->splitk_ws);
     cudaFree(h->scal);
     cudaFree(h->header);
     for (auto& v : h->ev)
@@ -339,6 +344,7 @@ extern "C" int gptb_set_debug_option(gptb_handle* h, const char* name, int value
     else if (!strcmp(name, "oz_whatif")) h->oz_whatif = value;
     else if (!strcmp(name, "back_substitution_variant")) h->back_variant = value != 0;
     else if (!strcmp(name, "spine_variant")) h->spine_variant = value != 0;
+    else if (!strcmp(name, "variance_splitk")) h->splitk_on = value != 0;
     else if (!strcmp(name, "batch_cap")) { if (value < 128 || value % 128) GPTB_FAIL(h, -1, "batch_cap must be a multiple of 128"); h->batch_cap = value; }
     else GPTB_FAIL(h, -1, "gptb_set_debug_option: unknown option '%s'", name);
     return 0;
@@ -773,6 +779,12 @@ static int build_minv(gptb_handle* h) {
         CU(h, cudaMalloc(&h->Minv, sizeof(double) * h->Npad * h->Npad));
         MAKE_MAP(h, &h->mapM, h->Minv, h->Npad, h->Npad, h->Npad);
     }
+    if (!h->splitk_ws) {
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+        CU(h, cudaMalloc(&h->splitk_ws, sizeof(double) * TS * TS * (size_t)(2 * nsm)));
+        h->splitk_cap = 2 * nsm;
+    }
     int rc = ensure_wbuf(h);
     if (rc) return rc;
     h->have_kinv = false;
@@ -1057,6 +1069,29 @@ struct SpatialWs {
     unsigned* flagsA[2];                         // block masks of the batch in slot b (written by the generator, read by the products)
 };
 
+// Split-k plan of the FP64 variance product for small batches (query.cuh: trmm_splitk_kernel).  In units of one 128^3 tile product the
+// one-CTA-per-tile kernel lasts max(T, W / #SM) with W = rowtiles * T(T+1)/2 the whole work, the split one max(KC, W / #SM) plus the
+// reduction: split when the longest k-loop, not the work, sets the time, with the chunk KC = ceil(W / #SM) (or larger if the
+// partial-tile buffer, two tiles per SM, cannot hold that many jobs).  KC = 0: do not split.
+static void trmm_splitk_plan(gptb_handle* h, int rowtiles, int T, int* KC, int* J) {
+    *KC = 0;
+    *J = 0;
+    if (!h->splitk_ws || !h->splitk_on || T < 2) return;
+    const int nsm = h->splitk_cap / 2;
+    const long long work = (long long)rowtiles * T * (T + 1) / 2;
+    int kc = (int)((work + nsm - 1) / nsm);
+    if (kc < 1) kc = 1;
+    for (; 4 * kc <= 3 * T; ++kc) {                  // a chunk above 3/4 of the longest loop is not worth the second kernel
+        int j = 0;
+        for (int t = 0; t < T; ++t) j += (t + kc) / kc;
+        if ((long long)rowtiles * j <= h->splitk_cap) {
+            *KC = kc;
+            *J = j;
+            return;
+        }
+    }
+}
+
 template <int D, int P>
 static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_dev, int B, int Bpad, unsigned flags, int nrhs,
                        unsigned genflags, const QueryOut& out, long long q_off, long long Mtot, double* rhs, double* part,
@@ -1175,8 +1210,22 @@ static int query_chunk(gptb_handle* h, const double* x_dev, const double* vel_de
         Tpart = skipping ? 2 * T64 : T64;           // the skipping kernel writes two partial sums per (tile, row): one per epilogue warp group
     } else if (nrhs > 0) {
         const int rowtiles = (int)(rows_total / TS);
+        int KC = 0, J = 0;
+        trmm_splitk_plan(h, rowtiles, T, &KC, &J);
         tic(h, 0);
-        trmm_sumsq_kernel<<<(unsigned)((long long)rowtiles * T), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(*mapR, h->mapM, T, rowtiles, rows_total, part);
+        int KV = T / 16 < 1 ? 1 : (T / 16 > 8 ? 8 : T / 16), JV = 0;            // matrix-vector form: chunk of k-tiles per job
+        for (int t = 0; t < T; ++t) JV += (t + KV) / KV;
+        if (h->splitk_ws && h->splitk_on && (long long)B * nrhs <= 8 && (long long)JV * 8 <= (long long)h->splitk_cap * TS) {
+            trmv_partial_kernel<<<(unsigned)JV, 512, 0, h->stream>>>(rhs, h->Minv, h->Npad, B, nrhs, Bpad, KV, h->splitk_ws);
+            LAUNCH_CHECK(h);
+            trmv_reduce_kernel<<<(unsigned)T, 128, 0, h->stream>>>(h->splitk_ws, B, nrhs, Bpad, KV, rows_total, part);
+        } else if (KC > 0) {
+            trmm_splitk_kernel<<<(unsigned)(rowtiles * J), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(*mapR, h->mapM, T, KC, J, h->splitk_ws);
+            LAUNCH_CHECK(h);
+            trmm_splitk_reduce_kernel<<<(unsigned)(rowtiles * T), 256, 0, h->stream>>>(h->splitk_ws, T, KC, J, rows_total, part);
+        } else {
+            trmm_sumsq_kernel<<<(unsigned)((long long)rowtiles * T), GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(*mapR, h->mapM, T, rowtiles, rows_total, part);
+        }
         toc(h, 0);
         LAUNCH_CHECK(h);
     }

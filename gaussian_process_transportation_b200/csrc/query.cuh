@@ -392,6 +392,144 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trmm_sumsq_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// The same product for SMALL batches (rowtiles * T below the SM count: a transport of ~100 points, a rollout step, a probe): with one
+// CTA per output tile the launch lasts as long as its longest k-loop, T tiles of 17 us each on ONE SM -- 0.54 ms at N = 4096 for a
+// single query -- while the rest of the machine idles.  Split-k: job (rt, ti, kc) multiplies k-tiles [kc*KC, min((kc+1)*KC, ti+1))
+// and stores its 128 x 128 partial of W; a second kernel adds the partials of one output tile in k order, squares and sums the rows.
+// KC is the smallest chunk for which all jobs fit the machine in one wave (host: trmm_splitk_plan).  Fixed summation order:
+// deterministic, but not bit-identical to the unsplit kernel (the k-sum is associated differently).
+//   job = rt * J + off(ti) + kc,  off(ti) = sum_{t < ti} ceil((t+1)/KC),  J = off(T).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 1) trmm_splitk_kernel(const __grid_constant__ CUtensorMap mapR,
+                                                                     const __grid_constant__ CUtensorMap mapM, int T, int KC, int J,
+                                                                     double* __restrict__ Wpart) {
+    extern __shared__ __align__(128) double smem[];
+    __shared__ PipeBarriers pipe;
+    pipe_init(&pipe);
+    const int job = blockIdx.x, rt = job / J;
+    int rem = job - rt * J, ti = 0;
+    for (;; ++ti) {
+        const int n = (ti + KC) / KC;
+        if (rem < n) break;
+        rem -= n;
+    }
+    const int kb = rem * KC, ke = min(kb + KC, ti + 1);
+    double acc[8][4][2];
+    acc_clear(acc);
+    Operand A{&mapR, rt * TS, 0, MASK_NONE, -1};
+    Operand B{&mapM, ti * TS, 0, MASK_LOWER, ti};
+    gemm_nt_tile(A, B, kb, ke, acc, smem, &pipe);
+    double* out = Wpart + (long long)job * TS * TS;
+    acc_foreach(acc, [&](int r, int c, double v0, double v1) { *reinterpret_cast<double2*>(out + r * TS + c) = make_double2(v0, v1); });
+}
+
+__global__ void __launch_bounds__(256) trmm_splitk_reduce_kernel(const double* __restrict__ Wpart, int T, int KC, int J, long long rows_total,
+                                                                 double* __restrict__ part) {
+    const int ti = blockIdx.x % T, rt = blockIdx.x / T;
+    int off = 0;
+    for (int t = 0; t < ti; ++t) off += (t + KC) / KC;
+    const int n = (ti + KC) / KC;
+    const double* base = Wpart + ((long long)rt * J + off) * TS * TS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 4
+    for (int rr = 0; rr < 16; ++rr) {
+        const int r = warp * 16 + rr;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        for (int kc = 0; kc < n; ++kc) {
+            const double* p = base + (long long)kc * TS * TS + r * TS + lane * 4;
+            const double2 a = *reinterpret_cast<const double2*>(p);
+            const double2 b = *reinterpret_cast<const double2*>(p + 2);
+            s0 += a.x; s1 += a.y; s2 += b.x; s3 += b.y;
+        }
+        double q = s0 * s0;
+        q = fma(s1, s1, q);
+        q = fma(s2, s2, q);
+        q = fma(s3, s3, q);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        if (lane == 0) part[(long long)ti * rows_total + (long long)rt * TS + r] = q;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// ... and for at most EIGHT right-hand-side rows (one query with its polarisation rows: a rollout step, a control-loop query): the
+// tile engine would pad every row to a 128-row tile -- seven tiles' worth of products for one point with derivative_of_variance --
+// so this is the matrix-vector form instead: L^-1 is streamed ONCE (it stays in L2 between the steps of a rollout), the right-hand
+// sides are the eight columns of the DMMA B fragment.  A CTA works on one 128-row tile of L^-1 with 16 warps of 8 rows; a lane reads 32 contiguous bytes of its row per step and feeds them to four DMMAs (the k-slot <-> lane map is the same
+// for both operands, so any consistent assignment is a valid product).  Column n is right-hand side n / B of query n % B.
+// Jobs are (tile ti, chunk kc of KC k-tiles), enumerated as in the split-k kernel, so the triangular matrix spreads evenly over the SMs
+// (one CTA per tile left the last tile's 128 x N block to a single SM's load bandwidth); each job stores its 128 x 8 partial of W and
+// trmv_reduce_kernel adds a tile's partials in k order, squares and sums the rows.
+__global__ void __launch_bounds__(512) trmv_partial_kernel(const double* __restrict__ rhs, const double* __restrict__ Minv, long long ld, int B,
+                                                           int nrhs, int Bpad, int KC, double* __restrict__ Wpart) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    int rem = blockIdx.x, ti = 0;
+    for (;; ++ti) {
+        const int n = (ti + KC) / KC;
+        if (rem < n) break;
+        rem -= n;
+    }
+    const int i0 = ti * TS + warp * 8;
+    const bool valid = g < B * nrhs;
+    const long long rrow = valid ? (long long)(g / B) * Bpad + (g % B) : 0;
+    const double* rp = rhs + rrow * ld + 4 * t;
+    const double* mp = Minv + (long long)(i0 + g) * ld + 4 * t;
+    double c0 = 0.0, c1 = 0.0;
+    const int kbeg = rem * KC * TS;
+    const int kend = min(kbeg + KC * TS, i0 + 8);       // columns k < i0 + 8 can be non-zero in rows i0 .. i0 + 7
+#pragma unroll 2
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
+        double2 a01 = *reinterpret_cast<const double2*>(mp + k0);
+        double2 a23 = *reinterpret_cast<const double2*>(mp + k0 + 2);
+        double2 b01 = *reinterpret_cast<const double2*>(rp + k0);
+        double2 b23 = *reinterpret_cast<const double2*>(rp + k0 + 2);
+        if (!valid) { b01 = make_double2(0.0, 0.0); b23 = b01; }
+        if (k0 + 16 > i0) {                             // the diagonal block: L^-1 is lower triangular, the buffer holds its mirror above
+            const int k = k0 + 4 * t, i = i0 + g;
+            if (k > i) a01.x = 0.0;
+            if (k + 1 > i) a01.y = 0.0;
+            if (k + 2 > i) a23.x = 0.0;
+            if (k + 3 > i) a23.y = 0.0;
+        }
+        dmma884(c0, c1, a01.x, b01.x);
+        dmma884(c0, c1, a01.y, b01.y);
+        dmma884(c0, c1, a23.x, b23.x);
+        dmma884(c0, c1, a23.y, b23.y);
+    }
+    // c0, c1 = partial W[i0 + g][n = 2t, 2t + 1]
+    *reinterpret_cast<double2*>(Wpart + (long long)blockIdx.x * (TS * 8) + (warp * 8 + g) * 8 + 2 * t) = make_double2(c0, c1);
+}
+
+__global__ void __launch_bounds__(128) trmv_reduce_kernel(const double* __restrict__ Wpart, int B, int nrhs, int Bpad, int KC, long long rows_total,
+                                                          double* __restrict__ part) {
+    __shared__ double red[4][8];
+    const int ti = blockIdx.x, i = threadIdx.x, lane = i & 31, warp = i >> 5;
+    int off = 0;
+    for (int t = 0; t < ti; ++t) off += (t + KC) / KC;
+    const int n = (ti + KC) / KC;
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int kc = 0; kc < n; ++kc) {
+        const double* p = Wpart + (long long)(off + kc) * (TS * 8) + i * 8;
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(p + c);
+            s[c] += v.x;
+            s[c + 1] += v.y;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        double q = s[c] * s[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        if (lane == 0) red[warp][c] = q;
+    }
+    __syncthreads();
+    if (i < 8 && i < B * nrhs) part[(long long)ti * rows_total + (long long)(i / B) * Bpad + (i % B)] = (red[0][i] + red[1][i]) + (red[2][i] + red[3][i]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Joint posterior covariance (GaussianProcess.predict(return_cov=True) / samples(); gaussian_process.py:50-60,
 // sklearn:_gpr.py:470-475): W = RHS * Linv^T is materialised once (same tile engine, store epilogue), then
 //   cov[a][b] = k(x_a, x_b) + s2*[a==b] - sum_k W[a][k] W[b][k].

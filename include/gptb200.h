@@ -222,7 +222,9 @@ int gptb_executed_products(gptb_handle* h, int64_t* pairs, int reset);
 /* developer switches, none of them on a hot path (A/B measurements only): "spatial_shuffle" (1 default; 0 keeps the plain Z-order,
  * before gptb_set_train), "oz_force_skip_variant" (1: the dense case runs through the skipping loops), "oz_whatif" (bit mask, acts
  * only in a -DGPTB_OZ_WHATIF build of the library: tools/whatif.py), "batch_cap" (queries per device batch), "back_substitution_variant"
- * (1 default: one flag-chained launch; 0: one launch per 128-row block). */
+ * (1 default: one flag-chained launch; 0: one launch per 128-row block), "spine_variant" (1 default: diag -> spine kernel -> diag on a
+ * stream of its own; 0: the round-1 factorisation schedule), "variance_splitk" (1 default: small batches take the matrix-vector /
+ * split-k forms of the FP64 variance product; 0: always one CTA per output tile). */
 int gptb_set_debug_option(gptb_handle* h, const char* name, int value);
 /* 64 cycle counters of CTA 0's roles in the last skipping product launch (all zero unless the library was built with
  * -DGPTB_OZ_WHATIF); the first call allocates the buffer, later launches fill it.  Layout: tools/whatif.py. */

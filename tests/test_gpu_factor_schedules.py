@@ -122,3 +122,40 @@ def test_handles_factorising_concurrently_agree_with_a_lone_one():
     assert not errs, errs
     for a in out:
         assert a is not None and np.array_equal(a, want)
+
+
+@pytest.mark.parametrize("N", [300, 834, 4096])
+def test_small_batch_variance_paths_agree_with_the_tile_path(N):
+    """FP64 variance product: batches of at most eight right-hand-side rows take the matrix-vector kernels, batches too small to fill
+    the machine the split-k kernels (csrc/query.cuh); both must reproduce what the one-CTA-per-tile kernel gives for the same points
+    (switch "variance_splitk" off, and the same points inside a large batch)."""
+    from gaussian_process_transportation_b200 import _lib as L
+    X, Y = problem(N, seed=5)
+    rng = np.random.default_rng(9)
+    eng = L.Engine(0)
+    try:
+        eng.set_train(X, Y)
+        assert eng.factorize(0.1, np.array([0.1, 0.15, 0.2]), 1e-4, 1e-10, want_lml=False)[0] == 0
+        eng.prepare_variance()
+        big = rng.random((3000, 3))
+        flags_all = L.MEAN | L.STD | L.JAC | L.JACVAR | L.DVAR
+        ref_big = eng.query(big, flags_all)
+        for M, flags in ((1, L.MEAN | L.STD), (1, L.MEAN | L.STD | L.DVAR), (2, L.MEAN | L.STD | L.JAC | L.JACVAR), (8, L.MEAN | L.STD), (9, L.MEAN | L.STD),
+                         (100, L.MEAN | L.STD | L.JAC), (100, flags_all), (400, L.MEAN | L.STD)):
+            xq = big[:M]
+            eng.set_debug_option("variance_splitk", 1)
+            a = eng.query(xq, flags)
+            eng.set_debug_option("variance_splitk", 0)
+            b = eng.query(xq, flags)
+            eng.set_debug_option("variance_splitk", 1)
+            for key in a:
+                scale = max(np.max(np.abs(b[key])), 1e-300)
+                assert np.max(np.abs(a[key] - b[key])) <= 1e-11 * scale + 1e-13, (M, key)
+                want = ref_big[key][:, :M] if key == "dvar" else ref_big[key][:M]
+                assert np.max(np.abs(a[key] - want)) <= 1e-11 * scale + 1e-13, (M, key, "vs large batch")
+            # deterministic
+            a2 = eng.query(xq, flags)
+            for key in a:
+                assert np.array_equal(a[key], a2[key]), (M, key)
+    finally:
+        eng.close()
