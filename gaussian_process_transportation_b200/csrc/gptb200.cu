@@ -1271,6 +1271,15 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     if (flags & (GPTB_STD | GPTB_DVAR)) { nrhs = 1; genflags |= 1u; }
     if (flags & (GPTB_JACVAR | GPTB_DVAR)) { nrhs = 1 + d; genflags |= 2u; }
     if (flags & GPTB_DVAR) { nrhs = 1 + 2 * d; genflags |= 4u | 1u; }
+    // A handful of right-hand-side rows (a control-loop query, a rollout step): the matrix-vector form of the exact FP64 product
+    // (trmv_partial_kernel) streams L^-1 once and beats the tiled INT8-sliced products, which are built for throughput -- so such a
+    // call runs as if the handle were in "fp64" mode.  L^-1 in FP64 is kept in INT8 mode anyway (the guard's reference path).
+    struct ModeRestore {
+        gptb_handle* h;
+        int saved;
+        ~ModeRestore() { h->var_mode = saved; }
+    } mode_restore{h, h->var_mode};
+    if (nrhs > 0 && h->var_mode == 1 && h->splitk_on && h->have_minv && h->splitk_ws && M * nrhs <= 8) h->var_mode = 0;
     if (nrhs > 0 && h->var_mode == 1) {
         int rc = build_bplanes(h);
         if (rc) return rc;

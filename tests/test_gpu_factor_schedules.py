@@ -159,3 +159,29 @@ def test_small_batch_variance_paths_agree_with_the_tile_path(N):
                 assert np.array_equal(a[key], a2[key]), (M, key)
     finally:
         eng.close()
+
+
+def test_tiny_batches_in_int8_mode_take_the_exact_matrix_vector_path():
+    """A call with at most eight right-hand-side rows runs through the FP64 matrix-vector product whatever the handle's variance mode
+    (gptb_query_dev): its std / dvar equal the "fp64" handle's bit for bit, while a large batch in INT8 mode differs from it at 1e-9."""
+    from gaussian_process_transportation_b200 import _lib as L
+    N = 2048
+    X, Y = problem(N, seed=7)
+    rng = np.random.default_rng(11)
+    xq = rng.random((600, 3))
+    out = {}
+    for mode in ("fp64", "int8w5"):
+        eng = L.Engine(0)
+        try:
+            eng.set_variance_mode(*L.parse_variance_mode(mode))
+            eng.set_train(X, Y)
+            assert eng.factorize(0.1, np.full(3, 0.1), 1e-4, 1e-10, want_lml=False)[0] == 0
+            eng.prepare_variance()
+            out[mode] = (eng.query(xq[:1], L.MEAN | L.STD | L.DVAR), eng.query(xq[:8], L.MEAN | L.STD), eng.query(xq, L.MEAN | L.STD))
+        finally:
+            eng.close()
+    for i in (0, 1):
+        for key in out["fp64"][i]:
+            assert np.array_equal(out["fp64"][i][key], out["int8w5"][i][key]), (i, key)
+    big = np.max(np.abs(out["fp64"][2]["std"] - out["int8w5"][2]["std"]))
+    assert 0.0 < big < 1e-7 * np.sqrt(0.1 + 1e-4)
