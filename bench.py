@@ -574,6 +574,13 @@ def small_n_block(L, local_rank):
             t0 = time.perf_counter(); eng.query(xq, fl); t_q.append(time.perf_counter() - t0)
         out[tag] = {"fit_ms": 1e3 * float(np.median(t_fit)), "lml_grad_ms": 1e3 * float(np.median(t_lml)), "apply_ms": 1e3 * float(np.median(t_q)),
                     "apply_query_points_per_s": Mq / float(np.median(t_q))}
+        # one point per call (a control loop): mean + std, and with derivative_of_variance (the reference's rollout step)
+        for key, f1 in (("one_point_mean_std_us", L.MEAN | L.STD), ("one_point_mean_std_dvar_us", L.MEAN | L.STD | L.DVAR)):
+            eng.query(xq[:1], f1)
+            t1 = []
+            for _ in range(50):
+                t0 = time.perf_counter(); eng.query(xq[:1], f1); t1.append(time.perf_counter() - t0)
+            out[tag][key] = 1e6 * float(np.median(t1))
         if d == 3:
             # minimum-variance stabilised rollouts (plot_utils.py:298-310: 1000 sequential single-point predict + derivative_of_variance
             # calls in the reference), device-resident loop; K start points advance together
