@@ -110,7 +110,7 @@ struct gptb_handle {
     int splitk_cap = 0;
     int splitk_on = 1;                       // developer A/B ("variance_splitk")
     int back_variant = 1;                    // 1 = one chained launch, 0 = one launch per block (developer A/B)
-    int spine_variant = 1;                   // 1 = diag -> spine cluster kernel -> diag on the aux stream, 0 = round-1 schedule (developer A/B)
+    int spine_variant = 1;                   // 1 = diag -> spine kernel -> diag on the aux stream, 0 = round-1 schedule (developer A/B)
     CUtensorMap mapL, mapD, mapM, mapW;      // TMA views of Lbuf, Dinv, Minv, Wbuf
     CUtensorMap mapL64;                      // Lbuf with a 64-row box (half-tile trailing update)
     // INT8-sliced variance path (ozaki.cuh): digit planes of the inverse factor + per-row scales
@@ -566,9 +566,11 @@ static int launch_scale(gptb_handle* h) {
 // Gram + blocked right-looking Cholesky with one step of look-ahead, forward substitution fused in.  Two schedules:
 //
 // spine_variant 1 (default): the serial chain lives on the aux stream as small kernels,
-//   aux  stream : diag(k) -> [wait trailing(k-1)] -> spine(k) = tiles (k+1,k) and (k+1,k+1), one 8-CTA cluster -> diag(k+1) -> ...
+//   aux  stream : diag(k) -> [wait head(k-1)] -> spine(k) = tiles (k+1,k) and (k+1,k+1), eight CTAs, cooperative -> diag(k+1) -> ...
 //   main stream : [wait diag(k)] panel(k), rows >= k+2 -> [wait spine(k)] trailing(k): every tile of columns >= k+1 but (k+1,k+1)
-// so one step of the chain is diag + spine (~45 + ~12 us) and the wide kernels only have to keep up with it.
+//                 and the two head tiles
+//   head stream : [wait panel(k), spine(k)] tiles (k+2,k+1) and (k+2,k+2) of trailing(k) -- all the next spine step reads
+// so one step of the chain is diag + spine (~42 + ~14 us) and the wide kernels only have to keep up with it.
 //
 // spine_variant 0 (round 1): the chain is diag(k+1) <- look-ahead column k+1 <- panel(k) <- diag(k), three launches of which two are
 // full 128^3 tiles on one SM each (~17 us of DMMA time apiece):
