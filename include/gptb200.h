@@ -89,7 +89,10 @@ int gptb_lml(gptb_handle* h, double c, const double* ell, double s2, double jitt
  * mode 3 = mode 2 with slices = 5 plus the first DROPPED diagonal of plane products (a + b = S: 19 products instead of 15).  With
  * 8-bit planes the error of the 15-product scheme is that dropped diagonal, not the 40-bit operands (tools/plane_error_study.py: std
  * error 9.0e-9 -> 5.5e-10 at N = 4096), so this buys the accuracy of a sixth plane for 27 % instead of 40 % more tensor work and no
- * extra operand traffic. */
+ * extra operand traffic.
+ * Whatever the mode, a query call with at most eight right-hand-side rows in all (queries x (1 | 1+d | 1+2d) for STD | JACVAR | DVAR:
+ * a control-loop query, a rollout step) is evaluated by the exact FP64 matrix-vector product -- it streams L^-1 once and is faster
+ * than any tiled form at that size; FP64-mode batches too small to fill the GPU with tiles run the tile product split along k. */
 int gptb_set_variance_mode(gptb_handle* h, int mode, int slices);
 
 /* ---- run-time accuracy guard of the INT8-sliced path (on by default).  Before the first variance query of a model (and in
