@@ -773,6 +773,12 @@ static int ensure_wbuf(gptb_handle* h) {
 }
 
 static int build_minv(gptb_handle* h) {
+    if (!h->splitk_ws) {                     // also for a model that arrived by gptb_state_commit (have_minv set, nothing built here)
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+        CU(h, cudaMalloc(&h->splitk_ws, sizeof(double) * TS * TS * (size_t)(2 * nsm)));
+        h->splitk_cap = 2 * nsm;
+    }
     if (h->have_minv) return 0;
     if (!h->have_factor) GPTB_FAIL(h, -1, "no factorisation available");
     const int T = h->T;
@@ -780,12 +786,6 @@ static int build_minv(gptb_handle* h) {
     if (!h->Minv) {
         CU(h, cudaMalloc(&h->Minv, sizeof(double) * h->Npad * h->Npad));
         MAKE_MAP(h, &h->mapM, h->Minv, h->Npad, h->Npad, h->Npad);
-    }
-    if (!h->splitk_ws) {
-        int nsm = 148;
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
-        CU(h, cudaMalloc(&h->splitk_ws, sizeof(double) * TS * TS * (size_t)(2 * nsm)));
-        h->splitk_cap = 2 * nsm;
     }
     int rc = ensure_wbuf(h);
     if (rc) return rc;
