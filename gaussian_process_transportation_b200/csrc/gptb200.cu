@@ -134,7 +134,7 @@ struct gptb_handle {
     double* ws = nullptr;
     size_t ws_bytes = 0;
     long long ws_limit = 16LL << 30;
-    long long batch_cap = 131072;             // queries per batch (debug option "batch_cap"): 65536 -> 131072 measured 3-5 % faster (fewer sort / finalize / launch gaps per query)
+    long long batch_cap = 524288;             // queries per batch (debug option "batch_cap"), where the workspace limit allows: c3 12.84 / 13.05 / 13.25 / 13.64 M q/s at 65536 / 131072 / 262144 / 524288 (fewer sort / finalize / launch tails per query; tools/batch_cap_ab.py)
     // staging for the host-pointer query: two device buffer sets, slices of HOST_SLICE queries; H2D of slice i+1 (s_h2d) and D2H of
     // slice i-1 (s_d2h) run under the kernels of slice i (main stream)
     double* stage[2] = {nullptr, nullptr};
@@ -1402,8 +1402,8 @@ extern "C" int gptb_query_dev(gptb_handle* h, const double* x_dev, int64_t M, ui
     return 0;
 }
 
-// Host-pointer query: staged through two device buffer sets in slices of HOST_SLICE queries, so that arbitrarily long query streams
-// (BASELINE configs 4/5: 2^26 .. 2^29 points) need ~50 MB of staging, and pipelined: the H2D copy of slice i+1 and the D2H copy of
+// Host-pointer query: staged through two device buffer sets in slices of at most 2^19 queries, so that arbitrarily long query streams
+// (BASELINE configs 4/5: 2^26 .. 2^29 points) need ~150 MB of staging, and pipelined: the H2D copy of slice i+1 and the D2H copy of
 // slice i-1 run on their own streams under the kernels of slice i.  (Round 1 copied a 4M-point slice in, ran it, copied it out and
 // synchronised: the copies were 3 % of a step on one GPU and the only thing bending the 8-GPU scaling curve, where eight ranks share
 // the host path.)  A call that fits one slice uses the main stream only (no event hops on the latency path of small queries).
@@ -1429,8 +1429,22 @@ extern "C" int gptb_query(gptb_handle* h, const double* x, int64_t M, uint32_t f
                     {nullptr, ((flags & GPTB_VELOCITY) && (flags & GPTB_JACVAR)) ? vvar : nullptr, (size_t)p, 0},
                     {nullptr, (flags & GPTB_JPHI) ? jphi : nullptr, (size_t)d * d, 0},
                     {nullptr, (flags & GPTB_DVAR) ? dvar : nullptr, (size_t)d, 0}};
-    const int64_t slice = (M < HOST_SLICE) ? M : HOST_SLICE;
-    const int64_t nslices = (M + slice - 1) / slice;
+    // slice plan: large slices (one device batch each: the kernels run 4 % faster on 2^19 queries than on 2^17) with a small LAST one,
+    // because what the pipeline cannot hide is the H2D copy of the first slice (inputs only: small) and the D2H copy of the last
+    const int64_t BIG = (h->batch_cap > HOST_SLICE) ? ((h->batch_cap < (1 << 19)) ? h->batch_cap : (int64_t)(1 << 19)) : HOST_SLICE;
+    std::vector<std::pair<int64_t, int64_t>> plan;       // (first query, count)
+    if (M <= HOST_SLICE) {
+        plan.emplace_back(0, M);
+    } else {
+        const int64_t TAIL = HOST_SLICE / 2;
+        int64_t q = 0, rem = M;
+        while (rem > BIG + TAIL) { plan.emplace_back(q, BIG); q += BIG; rem -= BIG; }
+        if (rem > TAIL) { plan.emplace_back(q, rem - TAIL); q += rem - TAIL; rem = TAIL; }
+        plan.emplace_back(q, rem);
+    }
+    int64_t slice = 0;
+    for (auto& pl : plan) slice = pl.second > slice ? pl.second : slice;
+    const int64_t nslices = (int64_t)plan.size();
     const int nsets = nslices > 1 ? 2 : 1;
     size_t tot = 0;
     for (auto& sg : segs) {
@@ -1460,8 +1474,8 @@ extern "C" int gptb_query(gptb_handle* h, const double* x, int64_t M, uint32_t f
         CU(h, cudaStreamWaitEvent(sin, h->ev_start, 0));
     }
     for (int64_t is = 0; is < nslices; ++is) {
-        const int64_t q0 = is * slice;
-        const int64_t m = (M - q0 < slice) ? (M - q0) : slice;
+        const int64_t q0 = plan[is].first;
+        const int64_t m = plan[is].second;
         const int set = piped ? (int)(is & 1) : 0;
         if (piped && is >= 2) CU(h, cudaStreamWaitEvent(sin, h->ev_cd[set], 0));          // the kernels of slice is-2 have consumed this set's inputs
         for (int i = 0; i < 2; ++i)
