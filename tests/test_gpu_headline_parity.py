@@ -303,9 +303,12 @@ def test_int8_spatial_path_on_ragged_shapes_vs_oracle(n, d, m):
     eng.close()
 
 
-def test_pipelined_host_query_equals_device_slices():
-    """gptb_query (host pointers) pipelines 131072-query slices over two copy streams; the result must be the device-resident result
-    slice by slice (bit for bit), including the (d, M) layout of derivative_of_variance across slices."""
+@pytest.mark.parametrize("M", [131072 + 5000, 2 * 131072 + 4321, 524288 + 65536 + 7777])
+def test_pipelined_host_query_equals_device_slices(M):
+    """gptb_query (host pointers) pipelines slices of up to 2^19 queries with a 65536-query tail over two copy streams (one, two and
+    three slices here); the result must be the device-resident result of any other slicing (bit for bit), including the (d, M) layout
+    of derivative_of_variance across slices.  (Pieces of a few queries would take the small-batch variance kernels, which agree to
+    1e-13 but not bit for bit -- tests/test_gpu_factor_schedules.py -- so every piece here is thousands of queries.)"""
     import torch
     from gaussian_process_transportation_b200 import _lib as L
     from oracle.gp_oracle import synthetic_pairs
@@ -313,13 +316,12 @@ def test_pipelined_host_query_equals_device_slices():
     eng = L.Engine(0)
     eng.set_train(S, T - S)
     eng.factorize(0.1, [0.1, 0.15, 0.2], 1e-4, 1e-10)
-    M = 2 * 131072 + 4321
     x = np.random.default_rng(0).random((M, 3))
     vel = np.random.default_rng(1).standard_normal((M, 3))
     fl = L.MEAN | L.STD | L.JAC | L.JACVAR | L.DVAR | L.VELOCITY | L.JPHI | L.TRANSPORT
     o = eng.query(x, fl, vel=vel)
     xd = torch.from_numpy(x).cuda(); vd = torch.from_numpy(vel).cuda()
-    for lo in (0, 131072, 262144):
+    for lo in range(0, M, 131072):
         m = min(131072, M - lo)
         bufs = {k: torch.empty(s, dtype=torch.float64, device="cuda") for k, s in
                 dict(mean=(m, 3), std=(m, 3), jac=(m, 3, 3), jacvar=(m, 3, 3), xhat=(m, 3), vhat=(m, 3), vvar=(m, 3), jphi=(m, 3, 3), dvar=(3, m)).items()}
